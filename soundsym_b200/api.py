@@ -1,0 +1,500 @@
+"""Host-side mirror of the reference crate's public API for the hot path, on top of the C ABI.
+
+Rust is not installed in this image, so instead of the `extern "C"` shim shown in INTEGRATION.md this module plays the
+host role: same type names, method names, argument meaning and error behaviour as src/lib.rs / src/sound.rs, so the
+parity tests read like the reference's own tests. All numerics happen in libsoundsym_b200.so on the GPU; this file
+only owns host buffers (numpy f64, like the reference's Vec<f64>) and calls through ctypes.
+
+    Sound::from_samples / from_path / push_samples / max_power / mfccs / mean_mfccs / num_frames   src/sound.rs:92-212
+    SoundDictionary::{new, from_segments, add_segments, match_sound, at_distance}                  src/sound.rs:290-370
+    SoundSequence::{new, clone_from_dictionary, to_sound, morph_to, from_distances, distances}     src/sound.rs:390-483
+    Partitioner::{new, depth, threshold, train(model), partition, partition_other}                 src/lib.rs:67-151
+"""
+import ctypes as C
+import struct
+
+import numpy as np
+
+from . import _lib
+from ._lib import SS_COSINE_REF, SS_DTW, SoundsymError
+
+NCOEFFS, NCLUSTERS, HOP, BIN = 12, 26, 256, 1024  # src/lib.rs:22-25
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """ss_ctx: one device, one stream. Not thread-safe (like the reference, which is single-threaded)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.ss_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SoundsymError(rc, self.lib.ss_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ss_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise SoundsymError(rc, self.lib.ss_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.lib.ss_ctx_stream(self.h)
+
+    def sync(self):
+        self.check(self.lib.ss_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.ss_ctx_launch_count(self.h))
+
+    # ---- MFCC subsystem ------------------------------------------------------------------------------------------
+    def decode_pcm(self, pcm, bits):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        out = np.empty(pcm.shape[0], dtype=np.float64)
+        self.check(self.lib.ss_decode_pcm(self.h, _ptr(pcm), pcm.shape[0], int(bits), _ptr(out)))
+        return out
+
+    def analyze(self, samples, sample_rate=44100.0, ncoeffs=NCOEFFS):
+        """Sound::from_samples' three analyses in one call -> (mfcc [frames, C], max_power, mean_mfccs [C])."""
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        n = samples.shape[0]
+        frames = C.c_size_t()
+        self.check(self.lib.ss_frame_count(n, C.byref(frames)))
+        mfcc = np.empty((frames.value, ncoeffs), dtype=np.float64)
+        mean = np.empty(ncoeffs, dtype=np.float64)
+        mp = C.c_double()
+        self.check(self.lib.ss_sound_analyze(self.h, _ptr(samples), n, float(sample_rate), int(ncoeffs), _ptr(mfcc),
+                                             C.byref(frames), C.byref(mp), _ptr(mean)))
+        return mfcc, float(mp.value), mean
+
+    def mfcc(self, samples, sample_rate=44100.0, ncoeffs=NCOEFFS):
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        frames = C.c_size_t()
+        self.check(self.lib.ss_frame_count(samples.shape[0], C.byref(frames)))
+        out = np.empty((frames.value, ncoeffs), dtype=np.float64)
+        self.check(self.lib.ss_mfcc(self.h, _ptr(samples), samples.shape[0], float(sample_rate), int(ncoeffs), _ptr(out), C.byref(frames)))
+        return out
+
+    def max_power(self, samples):
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        out = C.c_double()
+        self.check(self.lib.ss_max_power(self.h, _ptr(samples), samples.shape[0], C.byref(out)))
+        return float(out.value)
+
+    # ---- segmentation subsystem ------------------------------------------------------------------------------------
+    @staticmethod
+    def _gmm(model):
+        if model is None:
+            return None, None
+        means, covs, weights = (np.ascontiguousarray(m, dtype=np.float64) for m in model)
+        g = _lib.ss_gmm(int(means.shape[0]), int(means.shape[1]), means.ctypes.data, covs.ctypes.data, weights.ctypes.data)
+        return g, (means, covs, weights)
+
+    def symbols(self, mfcc, model, want_posteriors=False):
+        mfcc = np.ascontiguousarray(mfcc, dtype=np.float64)
+        g, keep = self._gmm(model)
+        out = np.empty(mfcc.shape[0], dtype=np.uint8)
+        post = np.empty((mfcc.shape[0], keep[0].shape[0]), dtype=np.float64) if (want_posteriors and keep) else None
+        self.check(self.lib.ss_symbols(self.h, _ptr(mfcc), mfcc.shape[0], C.byref(g) if g else None, _ptr(out), _ptr(post)))
+        return (out, post) if want_posteriors else out
+
+    def vote_split(self, symbols, depth, threshold):
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        n = symbols.shape[0]
+        votes = np.zeros(n + 1, dtype=np.uint32)
+        lens = np.empty(max(n, 1), dtype=np.uint64)
+        nseg = C.c_size_t()
+        self.check(self.lib.ss_vote_split(self.h, _ptr(symbols), n, int(depth), int(threshold), _ptr(votes), _ptr(lens), C.byref(nseg)))
+        return votes, lens[: nseg.value].copy()
+
+    def partition(self, mfcc, model, depth, threshold):
+        mfcc = np.ascontiguousarray(mfcc, dtype=np.float64)
+        g, keep = self._gmm(model)
+        lens = np.empty(max(mfcc.shape[0], 1), dtype=np.uint64)
+        nseg = C.c_size_t()
+        self.check(self.lib.ss_partition(self.h, _ptr(mfcc), mfcc.shape[0], C.byref(g) if g else None, int(depth), int(threshold),
+                                         _ptr(lens), C.byref(nseg)))
+        return lens[: nseg.value].copy()
+
+    # ---- matcher subsystem -----------------------------------------------------------------------------------------
+    def resynth(self, dict_samples, dict_sample_offsets, match_idx, target_lens):
+        ds = np.ascontiguousarray(dict_samples, dtype=np.float64)
+        do = np.ascontiguousarray(dict_sample_offsets, dtype=np.uint64)
+        mi = np.ascontiguousarray(match_idx, dtype=np.uint32)
+        tl = np.ascontiguousarray(target_lens, dtype=np.uint64)
+        out = np.empty(int(tl.sum()), dtype=np.float64)
+        self.check(self.lib.ss_resynth(self.h, _ptr(ds), _ptr(do), do.shape[0] - 1, _ptr(mi), _ptr(tl), mi.shape[0], _ptr(out)))
+        return out
+
+    def sequence_distances(self, mean_rows):
+        m = np.ascontiguousarray(mean_rows, dtype=np.float64)
+        out = np.empty(max(m.shape[0] - 1, 0), dtype=np.float64)
+        self.check(self.lib.ss_sequence_distances(self.h, _ptr(m), m.shape[0], m.shape[1], _ptr(out)))
+        return out
+
+
+class DeviceDictionary:
+    """ss_dict: a dictionary (or one shard) resident in HBM. Offsets are in FRAMES."""
+
+    def __init__(self, ctx, mfcc_flat, frame_offsets, ncoeffs=None, index_base=0):
+        self.ctx = ctx
+        mfcc_flat = np.ascontiguousarray(mfcc_flat, dtype=np.float64)
+        off = np.ascontiguousarray(frame_offsets, dtype=np.uint64)
+        if ncoeffs is None:
+            ncoeffs = mfcc_flat.shape[1]
+        self.ncoeffs = int(ncoeffs)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ss_dict_create(ctx.h, _ptr(mfcc_flat), _ptr(off), off.shape[0] - 1, self.ncoeffs, int(index_base), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.ss_dict_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.ctx.lib.ss_dict_len(self.h))
+
+    def match(self, q_flat, q_frame_offsets, mode=SS_DTW, k=1, targets=None):
+        """ss_dict_match with HOST buffers -> (idx u32 [nq, k], dist f64 [nq, k])."""
+        q = np.ascontiguousarray(q_flat, dtype=np.float64)
+        qo = np.ascontiguousarray(q_frame_offsets, dtype=np.uint64)
+        nq = qo.shape[0] - 1
+        idx = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float64)
+        t = np.ascontiguousarray(targets, dtype=np.float64) if targets is not None else None
+        self.ctx.check(self.ctx.lib.ss_dict_match(self.h, _ptr(q), _ptr(qo), nq, int(mode), _ptr(t), int(k), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    @property
+    def last_work(self):
+        return int(self.ctx.lib.ss_dict_last_work(self.h))
+
+    @property
+    def last_uncertified(self):
+        return int(self.ctx.lib.ss_dict_last_uncertified(self.h))
+
+
+class DeviceQueries:
+    """ss_queries: a prepared query batch resident in HBM."""
+
+    def __init__(self, ctx, q_flat, q_frame_offsets, ncoeffs=None):
+        self.ctx = ctx
+        q = np.ascontiguousarray(q_flat, dtype=np.float64)
+        qo = np.ascontiguousarray(q_frame_offsets, dtype=np.uint64)
+        if ncoeffs is None:
+            ncoeffs = q.shape[1]
+        self.nq = qo.shape[0] - 1
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ss_queries_create(ctx.h, _ptr(q), _ptr(qo), self.nq, int(ncoeffs), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.ss_queries_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's types
+# ---------------------------------------------------------------------------------------------------------------
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class Sound:
+    """src/sound.rs:71-213. samples / mfccs are host f64 arrays; analyses run on the GPU."""
+
+    def __init__(self, samples, sample_rate, mfccs, max_power, mean_mfccs, name=None, ctx=None):
+        self.name = name
+        self._samples = samples
+        self._sample_rate = float(sample_rate)
+        self._mfccs = mfccs
+        self._max_power = max_power
+        self._mean_mfccs = mean_mfccs
+        self._ctx = ctx
+
+    @classmethod
+    def from_samples(cls, samples, sample_rate, mfccs=None, name=None, ctx=None):
+        """Sound::from_samples (src/sound.rs:92-112). When mfccs are supplied they are kept (the reference recomputes
+        and discards them, :94 — functionally invisible)."""
+        ctx = ctx or default_context()
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        m, mp, mean = ctx.analyze(samples, sample_rate, NCOEFFS)
+        if mfccs is not None:
+            m = np.ascontiguousarray(mfccs, dtype=np.float64).reshape(-1, NCOEFFS)
+            with np.errstate(all="ignore"):
+                mean = m.sum(axis=0) / m.shape[0] if m.shape[0] else np.full(NCOEFFS, np.nan)
+        return cls(samples, sample_rate, m, mp, mean, name, ctx)
+
+    @classmethod
+    def from_path(cls, path, ctx=None):
+        """Sound::from_path (src/sound.rs:116-126): integer PCM WAV, mono; sample conversion on the GPU."""
+        import os
+        ctx = ctx or default_context()
+        pcm, sr, bits = _read_wav_pcm(path)
+        samples = ctx.decode_pcm(pcm, bits)
+        return cls.from_samples(samples, sr, None, os.path.splitext(os.path.basename(path))[0], ctx)
+
+    def push_samples(self, new_samples):
+        """Sound::push_samples (src/sound.rs:145-164), including its running-mean rule `(old*n0 + new*n1) * 0.5`."""
+        initial = self.num_frames()
+        self._samples = np.concatenate([self._samples, np.asarray(new_samples, dtype=np.float64)])
+        tail = self._samples[initial * HOP:]
+        m, mp, mean = self._ctx.analyze(tail, self._sample_rate, NCOEFFS)
+        self._mfccs = np.concatenate([self._mfccs, m], axis=0)
+        new_frames = self.num_frames() - initial
+        with np.errstate(all="ignore"):
+            self._mean_mfccs = (self._mean_mfccs * initial + mean * new_frames) * 0.5
+        self._max_power = max(self._max_power, mp)
+
+    def max_power(self):
+        return self._max_power
+
+    def samples(self):
+        return self._samples
+
+    def sample_rate(self):
+        return self._sample_rate
+
+    def mfccs(self):
+        return self._mfccs.reshape(-1)
+
+    def mfcc_arrays(self):
+        return self._mfccs
+
+    def mean_mfccs(self):
+        return self._mean_mfccs
+
+    def num_frames(self):
+        return self._mfccs.shape[0]
+
+    def write_file(self, path):
+        """Sound::write_file (src/sound.rs:129-143): 32-bit int PCM, (i32::MAX as f64 * sample) as i32."""
+        s = np.clip(np.trunc(self._samples * 2147483647.0), -2147483648.0, 2147483647.0).astype("<i4")
+        with open(path, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", 36 + s.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, int(self._sample_rate),
+                    int(self._sample_rate) * 4, 4, 32) + b"data" + struct.pack("<I", s.nbytes))
+            f.write(s.tobytes())
+
+
+def _read_wav_pcm(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError("not a RIFF/WAVE file: %s" % path)
+    pos, fmt, pcm = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+        body = data[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            _, _, sr, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+            fmt = (sr, bits)
+        elif cid == b"data":
+            bits = fmt[1]
+            if bits == 16:
+                pcm = np.frombuffer(body, dtype="<i2").astype(np.int32)
+            elif bits == 24:
+                b = np.frombuffer(body[: len(body) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+                v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+                pcm = np.where(v & 0x800000, v - (1 << 24), v).astype(np.int32)
+            elif bits == 32:
+                pcm = np.frombuffer(body, dtype="<i4").astype(np.int32)
+            else:
+                raise ValueError("unsupported bits per sample: %d" % bits)
+        pos += 8 + size + (size & 1)
+    return pcm, float(fmt[0]), fmt[1]
+
+
+class SoundDictionary:
+    """src/sound.rs:288-371. `mode` selects the matcher: SS_COSINE_REF is the reference's, SS_DTW the extension."""
+
+    def __init__(self, ctx=None, mode=SS_COSINE_REF):
+        self.sounds = []
+        self.mode = mode
+        self._ctx = ctx or default_context()
+        self._dev = None
+
+    @classmethod
+    def from_segments(cls, sound, segments, ctx=None, mode=SS_COSINE_REF):
+        d = cls(ctx or sound._ctx, mode)
+        d.add_segments(sound, segments)
+        return d
+
+    def add_segments(self, sound, segments):
+        """src/sound.rs:330-343: segment i takes seg_i samples and (seg_i / HOP) * NCOEFFS MFCC values, in order."""
+        spos, fpos = 0, 0
+        samples, mfccs = sound.samples(), sound.mfcc_arrays()
+        for seg in segments:
+            seg = int(seg)
+            nf = seg // HOP
+            samp = samples[spos:spos + seg]
+            m = mfccs[fpos:fpos + nf]
+            spos += seg
+            fpos += nf
+            # Sound::from_samples(samp, sr, Some(mfccs), None): max_power of the cut is analysed lazily here (it is
+            # not on the matcher path); mean of the supplied MFCC rows as analyze_mean_mfccs.
+            with np.errstate(all="ignore"):
+                mean = m.sum(axis=0) / m.shape[0] if m.shape[0] else np.full(NCOEFFS, np.nan)
+            self.sounds.append(Sound(samp, sound.sample_rate(), m, None, mean, None, sound._ctx))
+        self._dev = None
+
+    def _device(self):
+        if self._dev is None:
+            if not self.sounds:
+                raise SoundsymError(_lib.SS_ERR_EMPTY_DICT, "match against an empty dictionary")
+            lens = np.array([s.num_frames() for s in self.sounds], dtype=np.uint64)
+            off = np.zeros(len(lens) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum(lens)
+            flat = np.concatenate([s.mfcc_arrays() for s in self.sounds], axis=0) if int(off[-1]) else np.zeros((0, NCOEFFS))
+            self._dev = DeviceDictionary(self._ctx, flat, off, NCOEFFS)
+        return self._dev
+
+    def match_indices(self, sounds, targets=None, k=1):
+        """batched at_distance: one query per sound -> (idx [nq, k], dist [nq, k])."""
+        lens = np.array([s.num_frames() for s in sounds], dtype=np.uint64)
+        off = np.zeros(len(lens) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        flat = np.concatenate([s.mfcc_arrays() for s in sounds], axis=0) if int(off[-1]) else np.zeros((0, NCOEFFS))
+        return self._device().match(flat, off, self.mode, k, targets)
+
+    def at_distance(self, distance, other):
+        """src/sound.rs:351-370 (always Some)."""
+        idx, _ = self.match_indices([other], [distance])
+        return self.sounds[int(idx[0, 0])]
+
+    def match_sound(self, other):
+        """src/sound.rs:346-348."""
+        return self.at_distance(1.0, other)
+
+
+class SoundSequence:
+    """src/sound.rs:373-484."""
+
+    def __init__(self, sounds, ctx=None):
+        self._sounds = list(sounds)
+        self._ctx = ctx or (self._sounds[0]._ctx if self._sounds else default_context())
+        if len(self._sounds) >= 2:
+            self._distances = self._ctx.sequence_distances(np.stack([s.mean_mfccs() for s in self._sounds]))
+        else:
+            self._distances = np.zeros(0)
+
+    def sounds(self):
+        return self._sounds
+
+    def distances(self):
+        return self._distances
+
+    def clone_from_dictionary(self, dictionary):
+        """src/sound.rs:451-472: nearest dictionary sound per segment (ONE batched match), zero-padded / truncated to
+        the target segment's length on the GPU (ss_resynth)."""
+        if not self._sounds:
+            return SoundSequence([], self._ctx)
+        idx, _ = dictionary.match_indices(self._sounds)
+        idx = idx[:, 0]
+        dlens = np.array([len(s.samples()) for s in dictionary.sounds], dtype=np.uint64)
+        doff = np.zeros(len(dlens) + 1, dtype=np.uint64)
+        doff[1:] = np.cumsum(dlens)
+        dsamples = np.concatenate([s.samples() for s in dictionary.sounds]) if int(doff[-1]) else np.zeros(0)
+        tlens = np.array([len(s.samples()) for s in self._sounds], dtype=np.uint64)
+        out = self._ctx.resynth(dsamples, doff, idx, tlens)
+        sounds, pos = [], 0
+        for t, s in enumerate(self._sounds):
+            ln = int(tlens[t])
+            m = dictionary.sounds[int(idx[t])]
+            if ln == len(m.samples()):
+                sounds.append(m)  # shares the Arc (src/sound.rs:463-464)
+            else:
+                sounds.append(Sound.from_samples(out[pos:pos + ln], s.sample_rate(), None, None, self._ctx))
+            pos += ln
+        seq = SoundSequence(sounds, self._ctx)
+        seq._assembled = out
+        return seq
+
+    def morph_to(self, distances, dictionary):
+        """src/sound.rs:440-449 (batched: one at_distance per (sound, distance) pair)."""
+        n = min(len(self._sounds), len(distances))
+        idx, _ = dictionary.match_indices(self._sounds[:n], list(distances[:n]))
+        return SoundSequence([dictionary.sounds[int(i)] for i in idx[:, 0]], self._ctx)
+
+    @classmethod
+    def from_distances(cls, distances, start, dictionary):
+        """src/sound.rs:405-417: inherently sequential chain of nq = 1 matches."""
+        sounds = [start]
+        for d in distances:
+            sounds.append(dictionary.at_distance(d, sounds[-1]))
+        return cls(sounds)
+
+    def to_sound(self):
+        """src/sound.rs:475-483."""
+        if getattr(self, "_assembled", None) is not None:
+            samples = self._assembled
+        else:
+            samples = np.concatenate([s.samples() for s in self._sounds]) if self._sounds else np.zeros(0)
+        sr = self._sounds[0].sample_rate() if self._sounds else 44100.0
+        return Sound.from_samples(samples, sr, None, None, self._ctx)
+
+
+class Partitioner:
+    """src/lib.rs:62-151. `model` = (means, covs, weights) of the 26-component GMM, or None before train()."""
+
+    def __init__(self, sound, ctx=None):
+        self.sound = sound
+        self.depth = 5
+        self.threshold = 4
+        self.model = None
+        self._ctx = ctx or sound._ctx or default_context()
+
+    def set_depth(self, depth):
+        self.depth = int(depth)
+        return self
+
+    def set_threshold(self, threshold):
+        self.threshold = int(threshold)
+        return self
+
+    def train(self, model):
+        """Partitioner::train (src/lib.rs:101-107). EM training is not on the data-parallel path (SURVEY.md §8f-1:
+        the reference's is randomly seeded, so parity is only defined GIVEN a model); the caller supplies one."""
+        self.model = model
+
+    def partition_other(self, sound):
+        """src/lib.rs:112-144: segment lengths in samples; error "Must first train model" without a model."""
+        return self._ctx.partition(sound.mfcc_arrays(), self.model, self.depth, self.threshold)
+
+    def partition(self):
+        return self.partition_other(self.sound)

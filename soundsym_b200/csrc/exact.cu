@@ -1,0 +1,367 @@
+// exact.cu — f64 kernels whose arithmetic must equal the CPU path operation for operation. This translation unit is
+// compiled with --fmad=false so that a*b+c stays a rounded multiply followed by a rounded add, as rustc emits it.
+//
+//   cosine-ref matcher   cosine_sim / norm / at_distance, src/sound.rs:23-38, 351-370 (+ rulinalg::utils::dot [RECALL A9])
+//   DTW refine           the oracle's f64 recurrence (ASSUMPTIONS.h A8) on the candidates the fp32 scan kept
+//   top-k merge          (distance, index) lexicographic merge of per-shard lists
+#include <algorithm>
+
+#include "match.cuh"
+
+namespace ss {
+
+constexpr double kInf = __builtin_huge_val();
+
+// ---------------------------------------------------------------------------------------------------------------
+// norm(me) = fold(0, |memo, item| item*item + memo)   src/sound.rs:36-38 — one thread per segment, sequential
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_seg_norm(const double* __restrict__ v, const uint64_t* __restrict__ off, size_t nseg, int c,
+                           double* __restrict__ out) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const double* p = v + off[s] * c;
+    const size_t n = (size_t)(off[s + 1] - off[s]) * c;
+    double memo = 0.0;
+    for (size_t i = 0; i < n; i++) memo = p[i] * p[i] + memo;
+    out[s] = memo;
+}
+
+// f64 lane layout for the cosine matcher: element e of query lane l of group g at [(rowbase*c + e) * 32 + l]
+__global__ void k_query_lanes64(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c,
+                                const uint32_t* __restrict__ group_len, const uint32_t* __restrict__ group_rowbase,
+                                const uint32_t* __restrict__ group_qid, double* __restrict__ lanes) {
+    const uint32_t g = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = group_len[g] * (uint32_t)c;
+    const uint32_t qid = group_qid[g * 32 + lane];
+    double* dst = lanes + (size_t)group_rowbase[g] * c * 32 + lane;
+    const double* src = qid != 0xFFFFFFFFu ? mfcc + off[qid] * c : nullptr;
+    for (uint32_t e = threadIdx.x >> 5; e < n; e += blockDim.x >> 5) dst[(size_t)e * 32] = src ? src[e] : 0.0;
+}
+
+// one thread per (query, dictionary segment) pair: lanes are 32 equal-length queries, the dictionary segment is
+// warp-uniform (broadcast loads). Accumulation order is rulinalg's dot (A9): 8 interleaved partial sums, then the tail.
+__global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff,
+                                                     const double* __restrict__ dnorm, int c, const uint32_t* __restrict__ slice_seg,
+                                                     uint32_t nslices, const double* __restrict__ qlanes,
+                                                     const uint32_t* __restrict__ group_len,
+                                                     const uint32_t* __restrict__ group_rowbase,
+                                                     const uint32_t* __restrict__ group_qid, uint32_t ngroups,
+                                                     const double* __restrict__ qnorm, const double* __restrict__ targets,
+                                                     double* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qb = blockIdx.x / nslices, slice = blockIdx.x % nslices;
+    const uint32_t g = qb * 4 + warp;
+    if (g >= ngroups) return;
+    const uint32_t qid = group_qid[g * 32 + lane];
+    const size_t kq = (size_t)group_len[g] * c;
+    const double* y = qlanes + (size_t)group_rowbase[g] * c * 32 + lane;
+    const double nq = qid != 0xFFFFFFFFu ? qnorm[qid] : 1.0;
+    const double target = (qid != 0xFFFFFFFFu && targets) ? targets[qid] : 1.0;
+    double best = 2.0;  // fold((0, 2.0)), src/sound.rs:361
+    uint32_t best_idx = 0xFFFFFFFFu;
+    for (uint32_t s = slice_seg[slice]; s < slice_seg[slice + 1]; s++) {
+        const double* x = dmfcc + doff[s] * c;
+        const size_t kd = (size_t)(doff[s + 1] - doff[s]) * c;
+        const size_t len = kd < kq ? kd : kq;
+        double p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
+        size_t e = 0;
+        for (; e + 8 <= len; e += 8) {
+            p0 = p0 + __ldg(x + e + 0) * y[(e + 0) * 32];
+            p1 = p1 + __ldg(x + e + 1) * y[(e + 1) * 32];
+            p2 = p2 + __ldg(x + e + 2) * y[(e + 2) * 32];
+            p3 = p3 + __ldg(x + e + 3) * y[(e + 3) * 32];
+            p4 = p4 + __ldg(x + e + 4) * y[(e + 4) * 32];
+            p5 = p5 + __ldg(x + e + 5) * y[(e + 5) * 32];
+            p6 = p6 + __ldg(x + e + 6) * y[(e + 6) * 32];
+            p7 = p7 + __ldg(x + e + 7) * y[(e + 7) * 32];
+        }
+        double sum = 0.0;
+        sum = sum + (p0 + p4);
+        sum = sum + (p1 + p5);
+        sum = sum + (p2 + p6);
+        sum = sum + (p3 + p7);
+        for (; e < len; e++) sum = sum + __ldg(x + e) * y[e * 32];
+        const double nrm = dnorm[s] * nq;     // norm(me) * norm(you), src/sound.rs:30
+        const double sim = sum / nrm;         // src/sound.rs:32
+        const double dist = fabs(sim - target);  // src/sound.rs:359
+        if (dist < best) {                    // strict '<': first minimum wins, NaN never wins (src/sound.rs:362)
+            best = dist;
+            best_idx = s;
+        }
+    }
+    const size_t o = (size_t)slice * ngroups * 32 + (size_t)g * 32 + lane;
+    part_dist[o] = best;
+    part_idx[o] = best_idx;
+}
+
+__global__ void k_cosine_merge(const double* __restrict__ part_dist, const uint32_t* __restrict__ part_idx, uint32_t nslices,
+                               uint32_t nslots, const uint32_t* __restrict__ group_qid, uint32_t index_base,
+                               uint32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    const uint32_t qid = group_qid[slot];
+    if (qid == 0xFFFFFFFFu) return;
+    double best = 2.0;
+    uint32_t idx = 0;  // nothing < 2.0 -> index 0, as the reference's fold seed (src/sound.rs:361, 369)
+    for (uint32_t sl = 0; sl < nslices; sl++) {
+        const double d = part_dist[(size_t)sl * nslots + slot];
+        if (d < best) {
+            best = d;
+            idx = part_idx[(size_t)sl * nslots + slot];
+        }
+    }
+    out_idx[qid] = idx + index_base;
+    out_dist[qid] = best;
+}
+
+// empty queries never reach a lane: their similarity is 0/0 = NaN against everything, so the fold keeps (0, 2.0)
+__global__ void k_fill_result(uint32_t* __restrict__ idx, double* __restrict__ dist, size_t n, uint32_t idx_v, double dist_v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        idx[i] = idx_v;
+        dist[i] = dist_v;
+    }
+}
+
+int cosine_dict_build(ss_dict* d) {
+    ss_ctx* ctx = d->ctx;
+    SS_CUDA(ctx, d->d_norm.reserve(std::max<size_t>(d->nseg, 1)));
+    if (d->nseg) {
+        k_seg_norm<<<ceil_div((long long)d->nseg, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->nseg, d->c, d->d_norm.p);
+        SS_LAUNCHED(ctx);
+    }
+    return SS_OK;
+}
+
+int cosine_queries_build(ss_queries* q) {
+    ss_ctx* ctx = q->ctx;
+    SS_TRY(dtw_queries_build(q));  // shares the length-sorted group tables
+    if (q->cos_built) return SS_OK;
+    SS_CUDA(ctx, q->d_norm.reserve(std::max<size_t>(q->nq, 1)));
+    if (q->nq) {
+        k_seg_norm<<<ceil_div((long long)q->nq, 128), 128, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->nq, q->c, q->d_norm.p);
+        SS_LAUNCHED(ctx);
+    }
+    SS_CUDA(ctx, q->d_lane64.reserve(std::max<uint64_t>(q->total_rows, 1) * q->c * 32));
+    if (q->ngroups) {
+        k_query_lanes64<<<q->ngroups, 256, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, q->d_group_len.p,
+                                                            q->d_group_rowbase.p, q->d_group_qid.p, q->d_lane64.p);
+        SS_LAUNCHED(ctx);
+    }
+    q->cos_built = true;
+    return SS_OK;
+}
+
+int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_t* d_out_idx, double* d_out_dist) {
+    ss_ctx* ctx = d->ctx;
+    SS_TRY(cosine_queries_build(q));
+    // work = sum over pairs of min(Kq, Kd) products
+    {
+        std::vector<uint64_t> dl(d->nseg);
+        for (size_t s = 0; s < d->nseg; s++) dl[s] = d->h_off[s + 1] - d->h_off[s];
+        std::sort(dl.begin(), dl.end());
+        std::vector<uint64_t> pre(dl.size() + 1, 0);
+        for (size_t s = 0; s < dl.size(); s++) pre[s + 1] = pre[s] + dl[s];
+        uint64_t work = 0;
+        for (size_t i = 0; i < q->nq; i++) {
+            const uint64_t lq = q->h_off[i + 1] - q->h_off[i];
+            const size_t pos = std::upper_bound(dl.begin(), dl.end(), lq) - dl.begin();
+            work += pre[pos] + (uint64_t)(dl.size() - pos) * lq;
+        }
+        d->last_work = work * (uint64_t)d->c;
+    }
+    if (q->nq) {
+        k_fill_result<<<ceil_div((long long)q->nq, 256), 256, 0, ctx->stream>>>(d_out_idx, d_out_dist, q->nq, d->index_base, 2.0);
+        SS_LAUNCHED(ctx);
+    }
+    const uint32_t nqb = (q->ngroups + 3) / 4;
+    if (!nqb || !d->nseg) return SS_OK;
+    const uint32_t nslots = q->ngroups * 32;
+    uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)d->nseg, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
+    std::vector<uint32_t> ss(1, 0);
+    {
+        const uint64_t total = d->total_frames + d->nseg;  // +1 per segment so empty segments still spread
+        uint64_t acc = 0;
+        for (size_t s = 0; s < d->nseg; s++) {
+            if (s > 0 && ss.size() < nslices && acc >= (uint64_t)ss.size() * ((total + nslices - 1) / nslices)) ss.push_back((uint32_t)s);
+            acc += d->h_off[s + 1] - d->h_off[s] + 1;
+        }
+        ss.push_back((uint32_t)d->nseg);
+        nslices = (uint32_t)ss.size() - 1;
+    }
+    SS_TRY(upload(ctx, d->d_slice_tile, ss.data(), ss.size()));
+    SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
+    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
+    k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->d_norm.p, d->c, d->d_slice_tile.p, nslices,
+                                                         q->d_lane64.p, q->d_group_len.p, q->d_group_rowbase.p, q->d_group_qid.p,
+                                                         q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p);
+    SS_LAUNCHED(ctx);
+    k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices, nslots,
+                                                                  q->d_group_qid.p, d->index_base, d_out_idx, d_out_dist);
+    SS_LAUNCHED(ctx);
+    // the slice table is read by the async upload: keep the host vector alive until it has been consumed
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DTW refine: exact f64 recurrence on the candidates. One thread per (query slot, candidate); the DP row lives in a
+// global scratch laid out [column][pair] so that neighbouring threads touch neighbouring addresses.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                              const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid,
+                              const uint32_t* __restrict__ cand_idx, uint32_t pair_begin, uint32_t pair_end, int kp,
+                              double* __restrict__ rows, uint32_t row_pairs, double* __restrict__ exact) {
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pair = pair_begin + local;
+    if (pair >= pair_end) return;
+    const uint32_t qid = group_qid[pair / kp];
+    const uint32_t idx = cand_idx[pair];
+    if (qid == 0xFFFFFFFFu || idx == 0xFFFFFFFFu) {
+        exact[pair] = kInf;
+        return;
+    }
+    const double* a = qmfcc + qoff[qid] * c;
+    const double* b = dmfcc + doff[idx] * c;
+    const uint32_t la = (uint32_t)(qoff[qid + 1] - qoff[qid]), lb = (uint32_t)(doff[idx + 1] - doff[idx]);
+    double* row = rows + local;
+    double last = kInf;
+    for (uint32_t i = 0; i < la; i++) {
+        double ar[SS_MAX_NCOEFFS];
+#pragma unroll
+        for (int k = 0; k < SS_MAX_NCOEFFS; k++) ar[k] = k < c ? a[(size_t)i * c + k] : 0.0;
+        double left = kInf, diag = kInf;  // D(i, j-1), D(i-1, j-1)
+        for (uint32_t j = 0; j < lb; j++) {
+            double cost = 0.0;
+#pragma unroll
+            for (int k = 0; k < SS_MAX_NCOEFFS; k++)
+                if (k < c) {
+                    const double dlt = ar[k] - b[(size_t)j * c + k];
+                    cost = cost + dlt * dlt;
+                }
+            const double up = i ? row[(size_t)j * row_pairs] : kInf;  // D(i-1, j)
+            double m;
+            if (i == 0 && j == 0) m = 0.0;
+            else m = fmin(fmin(up, left), diag);
+            const double cur = cost + m;
+            row[(size_t)j * row_pairs] = cur;
+            diag = up;
+            left = cur;
+        }
+        last = left;
+    }
+    exact[pair] = (la && lb) ? last / (double)(la + lb) : kInf;
+}
+
+__global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
+                               const double* __restrict__ exact, const uint32_t* __restrict__ group_qid, uint32_t nslots, int kp,
+                               int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb,
+                               uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, unsigned long long* __restrict__ counters) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    const uint32_t qid = group_qid[slot];
+    if (qid == 0xFFFFFFFFu) return;
+    double dv[kMaxKeep];
+    uint32_t iv[kMaxKeep];
+    int n = 0;
+    for (int s = 0; s < kp; s++) {  // insertion sort by (distance, index); NaN / inf candidates are dropped
+        const double dd = exact[(size_t)slot * kp + s];
+        const uint32_t ii = cand_idx[(size_t)slot * kp + s];
+        if (ii == 0xFFFFFFFFu || !(dd < kInf)) continue;
+        int pos = n;
+        while (pos > 0 && (dd < dv[pos - 1] || (dd == dv[pos - 1] && ii < iv[pos - 1]))) {
+            dv[pos] = dv[pos - 1];
+            iv[pos] = iv[pos - 1];
+            pos--;
+        }
+        dv[pos] = dd;
+        iv[pos] = ii;
+        n++;
+    }
+    for (int s = 0; s < k; s++) {
+        out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
+        out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
+    }
+    // certification: every pair outside the candidate list has scan distance >= the list's worst entry; the scan's
+    // absolute error on a normalised distance is bounded by E, so such a pair's exact distance is > worst - E.
+    const float worst = cand_adist[(size_t)slot * kp + kp - 1];
+    if (worst < __int_as_float(0x7f800000)) {
+        const double E = 4e-6 * ((double)max_na[0] + (double)max_nb[0]);
+        const double kth = n >= k ? dv[k - 1] : kInf;
+        if (!((double)worst - E > kth)) atomicAdd(&counters[0], 1ull);
+    }
+}
+
+int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, uint32_t* d_out_idx, double* d_out_dist) {
+    ss_ctx* ctx = d->ctx;
+    if (q->nq) {
+        k_fill_result<<<ceil_div((long long)q->nq * k, 256), 256, 0, ctx->stream>>>(d_out_idx, d_out_dist, q->nq * (size_t)k,
+                                                                                   0xFFFFFFFFu, kInf);
+        SS_LAUNCHED(ctx);
+    }
+    SS_CUDA(ctx, d->d_counters.reserve(4));
+    SS_CUDA(ctx, cudaMemsetAsync(d->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (!nslots || !d->ntiles) return SS_OK;
+    const uint32_t npairs = nslots * (uint32_t)kp;
+    SS_CUDA(ctx, d->d_cand_exact.reserve(npairs));
+    const uint32_t max_ld = std::max<uint32_t>(d->max_len, 1);
+    const uint64_t budget = 32ull << 20;  // doubles of DP-row scratch (256 MB)
+    const uint32_t batch = (uint32_t)std::min<uint64_t>(npairs, std::max<uint64_t>(1024, budget / max_ld));
+    SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)batch * max_ld));
+    for (uint32_t pb = 0; pb < npairs; pb += batch) {
+        const uint32_t pe = std::min<uint32_t>(npairs, pb + batch);
+        k_dtw_rescore<<<ceil_div(pe - pb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
+                                                                     q->d_group_qid.p, d->d_cand_idx.p, pb, pe, kp,
+                                                                     d->d_rescore_rows.p, batch, d->d_cand_exact.p);
+        SS_LAUNCHED(ctx);
+    }
+    k_dtw_finalize<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_idx.p, d->d_cand_adist.p, d->d_cand_exact.p,
+                                                                  q->d_group_qid.p, nslots, kp, k, d->index_base, q->d_max_norm.p,
+                                                                  d->d_max_norm.p, d_out_idx, d_out_dist, d->d_counters.p);
+    SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// merge of per-shard top-k lists, list-major [nlists][nq][k] -> [nq][k]; (distance, index) lexicographic
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_topk_merge(const uint32_t* __restrict__ idx, const double* __restrict__ dist, int nlists, size_t nq, int k,
+                             uint32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    const size_t qi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    double dv[SS_MAX_TOPK];
+    uint32_t iv[SS_MAX_TOPK];
+    int n = 0;
+    for (int l = 0; l < nlists; l++)
+        for (int s = 0; s < k; s++) {
+            const double dd = dist[((size_t)l * nq + qi) * k + s];
+            const uint32_t ii = idx[((size_t)l * nq + qi) * k + s];
+            if (ii == 0xFFFFFFFFu || dd != dd) continue;
+            if (n == k && !(dd < dv[k - 1] || (dd == dv[k - 1] && ii < iv[k - 1]))) continue;
+            int pos = n < k ? n : k - 1;
+            while (pos > 0 && (dd < dv[pos - 1] || (dd == dv[pos - 1] && ii < iv[pos - 1]))) {
+                dv[pos] = dv[pos - 1];
+                iv[pos] = iv[pos - 1];
+                pos--;
+            }
+            dv[pos] = dd;
+            iv[pos] = ii;
+            if (n < k) n++;
+        }
+    for (int s = 0; s < k; s++) {
+        out_idx[qi * k + s] = s < n ? iv[s] : 0xFFFFFFFFu;
+        out_dist[qi * k + s] = s < n ? dv[s] : kInf;
+    }
+}
+
+int topk_merge_dev(ss_ctx* ctx, const uint32_t* d_idx, const double* d_dist, int nlists, size_t nq, int k, uint32_t* d_out_idx,
+                   double* d_out_dist) {
+    if (k < 1 || k > SS_MAX_TOPK || nlists < 1) return set_error(ctx, SS_ERR_INVALID, "topk_merge: bad k / nlists");
+    if (!nq) return SS_OK;
+    k_topk_merge<<<ceil_div((long long)nq, 128), 128, 0, ctx->stream>>>(d_idx, d_dist, nlists, nq, k, d_out_idx, d_out_dist);
+    SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+
+}  // namespace ss

@@ -1,0 +1,91 @@
+// match.cuh — HBM-resident dictionary / query-batch handles shared by the DTW (dtw.cu) and cosine-ref (cosine.cu) matchers.
+#pragma once
+#include "common.cuh"
+
+namespace ss {
+
+// ---- layout constants of the DTW scan -----------------------------------------------------------------------------
+constexpr int kSlots = 16;        // floats per frame in the fp32 scan layouts (13 coefficient slots + norm slot + pad)
+constexpr int kNormSlot = 13;     // stream side: |b|^2 ; lane side: 1.0f
+constexpr int kLaneNaSlot = 14;   // lane side: |a|^2 (accumulator seed)
+constexpr int kStrip = 32;        // DP columns held in registers per strip
+constexpr int kTileFrames = 128;  // frames per TMA tile (8 KB)
+constexpr int kStages = 3;        // tile ring depth
+constexpr int kWarpsPerCta = 4;
+constexpr int kMaxKeep = 16;      // largest candidate list per query kept by the scan
+
+struct StripDesc {  // 16 B, read as int4
+    uint32_t frame_begin;  // first frame of the strip in the shard's frame stream
+    uint32_t seg;          // local segment index
+    uint32_t len_flags;    // bits 0..15 frames in strip (1..32), bit 16 first strip of its segment, bit 17 last
+    uint32_t seg_len;      // frames of the whole segment
+};
+struct TileDesc {  // 16 B, read as int4
+    uint32_t frame_begin, nframes, strip_begin, nstrips;
+};
+
+}  // namespace ss
+
+struct ss_dict {
+    ss_ctx* ctx = nullptr;
+    size_t nseg = 0;
+    int c = 0;
+    uint32_t index_base = 0;
+    uint64_t total_frames = 0;
+    uint32_t max_len = 0;
+    std::vector<uint64_t> h_off;  // nseg+1, frames
+    ss::DevBuf<double> d_mfcc;    // frames x c (f64, as given)
+    ss::DevBuf<uint64_t> d_off;   // nseg+1
+    // cosine-ref
+    ss::DevBuf<double> d_norm;  // per segment: norm(mfccs) (src/sound.rs:36-38)
+    // DTW scan
+    ss::DevBuf<float> d_stream;  // frames x kSlots
+    ss::DevBuf<int4> d_strips, d_tiles;
+    uint32_t nstrips = 0, ntiles = 0;
+    std::vector<uint32_t> h_tile_frames;    // frames per tile (slice balancing)
+    std::vector<uint8_t> h_tile_segstart;   // 1 if the tile begins at a segment boundary
+    ss::DevBuf<float> d_max_norm;           // [0] = max |b|^2 over the shard (error bound of the fp32 scan)
+    // per-call workspaces (grow-only)
+    ss::DevBuf<uint32_t> d_slice_tile;
+    ss::DevBuf<unsigned long long> d_partial;
+    ss::DevBuf<float> d_scratch;
+    ss::DevBuf<uint32_t> d_cand_idx;
+    ss::DevBuf<float> d_cand_adist;
+    ss::DevBuf<double> d_cand_exact;
+    ss::DevBuf<double> d_rescore_rows;
+    ss::DevBuf<unsigned long long> d_counters;  // [0] uncertified
+    std::vector<uint32_t> h_slice_tile;
+    uint64_t last_work = 0, last_uncertified = 0;
+};
+
+struct ss_queries {
+    ss_ctx* ctx = nullptr;
+    size_t nq = 0;
+    int c = 0;
+    uint64_t total_frames = 0;
+    uint32_t max_len = 0;
+    std::vector<uint64_t> h_off;
+    ss::DevBuf<double> d_mfcc;
+    ss::DevBuf<uint64_t> d_off;
+    ss::DevBuf<double> d_norm;  // cosine-ref: norm of every query
+    // lane layout: queries sorted by length (descending) into length-homogeneous groups of 32 lanes
+    uint32_t ngroups = 0;
+    uint64_t total_rows = 0;  // sum over groups of padded row counts
+    std::vector<uint32_t> h_group_len;
+    ss::DevBuf<uint32_t> d_group_len, d_group_rowbase, d_group_qid;  // qid: ngroups x 32, 0xFFFFFFFF = padding lane
+    ss::DevBuf<float4> d_lane;                                       // [row][4][32] float4 (DTW)
+    ss::DevBuf<float> d_max_norm;                                    // [0] = max |a|^2
+    ss::DevBuf<double> d_lane64;                                     // [row*c + e][32] f64 (cosine-ref), built on first use
+    bool cos_built = false;
+};
+
+namespace ss {
+int dtw_dict_build(ss_dict* d);       // builds the fp32 stream + strip / tile tables (dtw.cu)
+int dtw_queries_build(ss_queries* q); // builds the lane layout (dtw.cu)
+int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist);
+int cosine_dict_build(ss_dict* d);    // per-segment norms (cosine.cu)
+int cosine_queries_build(ss_queries* q);
+int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_t* d_out_idx, double* d_out_dist);
+int topk_merge_dev(ss_ctx* ctx, const uint32_t* d_idx, const double* d_dist, int nlists, size_t nq, int k,
+                   uint32_t* d_out_idx, double* d_out_dist);
+}  // namespace ss

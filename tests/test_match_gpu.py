@@ -1,0 +1,160 @@
+"""GPU parity tests of the matcher subsystem: CUDA path through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from soundsym_b200 import api, synth
+from soundsym_b200._lib import SS_COSINE_REF, SS_DTW, SoundsymError
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return api.Context(0)
+
+
+def cut(mfcc, seg_lens_samples, hop=256):
+    frames = (np.asarray(seg_lens_samples, dtype=np.uint64) // np.uint64(hop)).astype(np.uint64)
+    off = np.zeros(len(frames) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(frames)
+    return mfcc[: int(off[-1])], off
+
+
+def check_dtw(idx, dist, oidx, odist, k):
+    """indices bit-exact; distances are produced by the f64 refine kernel with the oracle's arithmetic -> 1e-12
+    (the north-star bar is 1e-4 relative)."""
+    assert idx.shape == oidx.shape
+    fin = np.isfinite(odist)
+    assert np.array_equal(np.isfinite(dist), fin)
+    assert np.allclose(dist[fin], odist[fin], rtol=1e-12, atol=0)
+    assert np.array_equal(idx, oidx)
+
+
+def test_dtw_synthetic_small_vs_oracle_and_golden(ctx, synthetic_small):
+    d, doff = synth.segments(600, 13, seed=1234)
+    q, qoff = synth.segments(48, 13, seed=5678)
+    dev = api.DeviceDictionary(ctx, d, doff)
+    for k in (1, 4, 8):
+        idx, dist = dev.match(q, qoff, SS_DTW, k)
+        oidx, odist = O.dtw_topk(d, doff, q, qoff, 13, k)
+        check_dtw(idx, dist, oidx, odist, k)
+        assert dev.last_uncertified == 0
+        assert dev.last_work == int(doff[-1]) * int(qoff[-1])
+    idx, dist = dev.match(q, qoff, SS_DTW, 4)
+    assert np.array_equal(idx, synthetic_small["dtw_idx"])
+    assert np.allclose(dist, synthetic_small["dtw_dist"], rtol=1e-12, atol=0)
+
+
+def test_dtw_config1_real_segments_long_strips(ctx, section71, sample_excerpt):
+    """config 1: queries = segments of sample.wav, dictionary = segments of Section_7_1.wav (C = 12, segments up to 83
+    frames -> multi-strip path, queries up to 385 frames)."""
+    d, doff = cut(section71["mfcc"], section71["splits_d3t4"])
+    q, qoff = cut(sample_excerpt["mfcc"], sample_excerpt["splits_d3t4"])
+    dev = api.DeviceDictionary(ctx, d, doff)
+    idx, dist = dev.match(q, qoff, SS_DTW, 4)
+    check_dtw(idx, dist, sample_excerpt["dtw_idx"], sample_excerpt["dtw_dist"], 4)
+
+
+def test_cosine_ref_config1_bit_exact(ctx, section71, sample_excerpt):
+    d, doff = cut(section71["mfcc"], section71["splits_d3t4"])
+    q, qoff = cut(sample_excerpt["mfcc"], sample_excerpt["splits_d3t4"])
+    dev = api.DeviceDictionary(ctx, d, doff)
+    idx, dist = dev.match(q, qoff, SS_COSINE_REF, 1)
+    assert np.array_equal(idx[:, 0], sample_excerpt["cos_idx"])
+    assert np.array_equal(dist[:, 0], sample_excerpt["cos_dist"])  # bit-exact f64
+
+
+def test_cosine_ref_synthetic_and_targets(ctx, synthetic_small):
+    d, doff = synth.segments(600, 13, seed=1234)
+    q, qoff = synth.segments(48, 13, seed=5678)
+    dev = api.DeviceDictionary(ctx, d, doff)
+    idx, dist = dev.match(q, qoff, SS_COSINE_REF, 1)
+    assert np.array_equal(idx[:, 0], synthetic_small["cos_idx"]) and np.array_equal(dist[:, 0], synthetic_small["cos_dist"])
+    targets = np.linspace(-1e-4, 1e-4, 48)  # at_distance(target != 1), src/sound.rs:351
+    idx, dist = dev.match(q, qoff, SS_COSINE_REF, 1, targets)
+    oidx, odist = O.cosine_match(d, doff, q, qoff, 13, targets)
+    assert np.array_equal(idx[:, 0], oidx) and np.array_equal(dist[:, 0], odist)
+    assert dev.last_work == sum(min(int(a), int(b)) for a in np.diff(qoff) for b in np.diff(doff)) * 13
+
+
+def test_ties_and_self_match(ctx):
+    d, doff = synth.segments(200, 12, seed=3)
+    # duplicate segment 17 at the end: a query equal to it must report 17 first (lowest index), then the copy
+    seg = d[int(doff[17]):int(doff[18])]
+    d2 = np.concatenate([d, seg])
+    doff2 = np.concatenate([doff, [doff[-1] + np.uint64(len(seg))]]).astype(np.uint64)
+    dev = api.DeviceDictionary(ctx, d2, doff2)
+    idx, dist = dev.match(seg, np.array([0, len(seg)], dtype=np.uint64), SS_DTW, 3)
+    assert list(idx[0, :2]) == [17, 200] and dist[0, 0] == 0.0 and dist[0, 1] == 0.0
+    oidx, odist = O.dtw_topk(d2, doff2, seg, np.array([0, len(seg)], dtype=np.uint64), 12, 3)
+    check_dtw(idx, dist, oidx, odist, 3)
+    cidx, cdist = dev.match(seg, np.array([0, len(seg)], dtype=np.uint64), SS_COSINE_REF, 1)
+    oc, od = O.cosine_match(d2, doff2, seg, np.array([0, len(seg)], dtype=np.uint64), 12)
+    assert cidx[0, 0] == oc[0] and cdist[0, 0] == od[0]
+
+
+def test_ragged_edge_cases(ctx):
+    rng = np.random.default_rng(11)
+    # lengths 1, 0 (empty), 33, 64, 65, 200 on both sides
+    lens = np.array([1, 0, 33, 64, 65, 200, 2, 31, 32], dtype=np.uint64)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    d = rng.normal(size=(int(off[-1]), 13)) * 5
+    q = rng.normal(size=(int(off[-1]), 13)) * 5
+    dev = api.DeviceDictionary(ctx, d, off)
+    idx, dist = dev.match(q, off, SS_DTW, 8)
+    oidx, odist = O.dtw_topk(d, off, q, off, 13, 8)
+    check_dtw(idx, dist, oidx, odist, 8)
+    assert np.all(idx[1] == 0xFFFFFFFF) and np.all(np.isinf(dist[1]))  # empty query matches nothing
+    cidx, cdist = dev.match(q, off, SS_COSINE_REF, 1)
+    oc, od = O.cosine_match(d, off, q, off, 13)
+    assert np.array_equal(cidx[:, 0], oc) and np.array_equal(cdist[:, 0], od)
+    # zero queries
+    idx, dist = dev.match(np.zeros((0, 13)), np.zeros(1, dtype=np.uint64), SS_DTW, 2)
+    assert idx.shape == (0, 2)
+
+
+def test_index_base_and_topk_merge_across_shards(ctx):
+    """dictionary split into 3 shards with global index bases; merged top-k must equal the single-shard answer
+    (results identical for 1/2/4/8 shards)."""
+    import ctypes as C
+    import torch
+    d, doff = synth.segments(900, 13, seed=21)
+    q, qoff = synth.segments(40, 13, seed=22)
+    k = 4
+    whole = api.DeviceDictionary(ctx, d, doff)
+    widx, wdist = whole.match(q, qoff, SS_DTW, k)
+    cuts = [0, 250, 610, 900]
+    li, ld = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sh = api.DeviceDictionary(ctx, d, doff[a:b + 1], index_base=a)
+        i, dd = sh.match(q, qoff, SS_DTW, k)
+        li.append(i)
+        ld.append(dd)
+    gi = torch.from_numpy(np.stack(li).astype(np.int64)).to(torch.uint32 if hasattr(torch, "uint32") else torch.int32).cuda()
+    gd = torch.from_numpy(np.stack(ld)).cuda()
+    oi = torch.empty((40, k), dtype=gi.dtype, device="cuda")
+    od = torch.empty((40, k), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.ss_topk_merge_dev(ctx.h, gi.data_ptr(), gd.data_ptr(), 3, 40, k, oi.data_ptr(), od.data_ptr()))
+    ctx.sync()
+    assert np.array_equal(oi.cpu().numpy().astype(np.uint32), widx) and np.array_equal(od.cpu().numpy(), wdist)
+
+
+def test_error_behaviour(ctx):
+    d, doff = synth.segments(10, 13, seed=1)
+    with pytest.raises(SoundsymError) as e:
+        api.DeviceDictionary(ctx, d, doff, ncoeffs=14)
+    assert e.value.code == -1
+    empty = api.DeviceDictionary(ctx, np.zeros((0, 13)), np.zeros(1, dtype=np.uint64))
+    with pytest.raises(SoundsymError) as e:  # the reference panics on sounds[0] of an empty dictionary (src/sound.rs:369)
+        empty.match(d, doff, SS_DTW, 1)
+    assert e.value.code == -5
+    dev = api.DeviceDictionary(ctx, d, doff)
+    with pytest.raises(SoundsymError):
+        dev.match(d, doff, SS_DTW, 9)
+    with pytest.raises(SoundsymError):
+        dev.match(d, doff, SS_COSINE_REF, 2)
+    with pytest.raises(SoundsymError):
+        dev.match(d, np.array([0, 5, 3], dtype=np.uint64), SS_DTW, 1)
