@@ -140,6 +140,12 @@ int ss_dict_match_dev(ss_dict* dict, ss_queries* q, int mode, const double* d_ta
                       double* d_out_dist);
 int ss_topk_merge_dev(ss_ctx* ctx, const uint32_t* d_idx, const double* d_dist, int nlists, size_t nq, int k,
                       uint32_t* d_out_idx, double* d_out_dist);
+/* drops the cached device layouts of a query batch so that the next match rebuilds them (bench.py calls this every
+ * step so that the layout kernels are inside the timed region) */
+int ss_queries_invalidate(ss_queries* q);
+/* device time of the dominant kernel (DTW scan / cosine scan) of the last ss_dict_match*(…), measured with CUDA events
+ * on the ctx stream; synchronises the stream. Returns a negative value if no match has run. */
+double ss_dict_last_scan_ms(ss_dict* dict);
 /* DP cells / similarity products the last ss_dict_match*(…) evaluated (sum over pairs of Lq*Ld, resp. of min(Kq,Kd)) */
 uint64_t ss_dict_last_work(const ss_dict* dict);
 /* SS_DTW only: number of queries of the last match whose exact top-k could not be certified from the fp32 scan's

@@ -148,20 +148,13 @@ uint64_t ss_dict_last_uncertified(const ss_dict* dc) {
     return v;
 }
 
-int ss_queries_create(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs, ss_queries** out) {
-    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
-    if (!out) return set_error(ctx, SS_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    if (ncoeffs < 1 || ncoeffs > SS_MAX_NCOEFFS) return set_error(ctx, SS_ERR_INVALID, "ncoeffs must be in 1..%d (got %d)", SS_MAX_NCOEFFS, ncoeffs);
-    if (nq > 0x7FFFFFF0ull) return set_error(ctx, SS_ERR_INVALID, "too many queries");
-    SS_TRY(check_offsets(ctx, q_frame_offsets, nq, "ss_queries_create"));
-    if (nq && q_frame_offsets[nq] > q_frame_offsets[0] && !q_mfcc) return set_error(ctx, SS_ERR_INVALID, "q_mfcc is NULL");
-    SS_CUDA(ctx, cudaSetDevice(ctx->device));
-    ss_queries* q = new (std::nothrow) ss_queries();
-    if (!q) return set_error(ctx, SS_ERR_NOMEM, "out of host memory");
-    q->ctx = ctx;
+// (re)fills a query batch in place: device buffers are grow-only, so a reused handle does no cudaMalloc / cudaFree
+static int queries_fill(ss_queries* q, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq) {
+    ss_ctx* ctx = q->ctx;
     q->nq = nq;
-    q->c = ncoeffs;
+    q->max_len = 0;
+    q->lane_built = false;
+    q->cos_built = false;
     q->h_off.resize(nq + 1);
     const uint64_t base = nq ? q_frame_offsets[0] : 0;
     q->h_off[0] = 0;
@@ -170,14 +163,54 @@ int ss_queries_create(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame
         q->max_len = std::max<uint32_t>(q->max_len, (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, q_frame_offsets[i + 1] - q_frame_offsets[i]));
     }
     q->total_frames = q->h_off[nq];
-    int rc = upload(ctx, q->d_mfcc, q_mfcc ? q_mfcc + base * ncoeffs : nullptr, (size_t)q->total_frames * ncoeffs);
-    if (rc == SS_OK) rc = upload(ctx, q->d_off, q->h_off.data(), nq + 1);
+    SS_TRY(upload(ctx, q->d_mfcc, q_mfcc ? q_mfcc + base * q->c : nullptr, (size_t)q->total_frames * q->c));
+    SS_TRY(upload(ctx, q->d_off, q->h_off.data(), nq + 1));
+    return SS_OK;
+}
+
+static int queries_check(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs) {
+    if (ncoeffs < 1 || ncoeffs > SS_MAX_NCOEFFS) return set_error(ctx, SS_ERR_INVALID, "ncoeffs must be in 1..%d (got %d)", SS_MAX_NCOEFFS, ncoeffs);
+    if (nq > 0x7FFFFFF0ull) return set_error(ctx, SS_ERR_INVALID, "too many queries");
+    SS_TRY(check_offsets(ctx, q_frame_offsets, nq, "queries"));
+    if (nq && q_frame_offsets[nq] > q_frame_offsets[0] && !q_mfcc) return set_error(ctx, SS_ERR_INVALID, "q_mfcc is NULL");
+    return SS_OK;
+}
+
+int ss_queries_create(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs, ss_queries** out) {
+    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
+    if (!out) return set_error(ctx, SS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    SS_TRY(queries_check(ctx, q_mfcc, q_frame_offsets, nq, ncoeffs));
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    ss_queries* q = new (std::nothrow) ss_queries();
+    if (!q) return set_error(ctx, SS_ERR_NOMEM, "out of host memory");
+    q->ctx = ctx;
+    q->c = ncoeffs;
+    const int rc = queries_fill(q, q_mfcc, q_frame_offsets, nq);
     if (rc != SS_OK) {
         delete q;
         return rc;
     }
     *out = q;
     return SS_OK;
+}
+
+int ss_queries_invalidate(ss_queries* q) {
+    if (!q) return set_error(nullptr, SS_ERR_INVALID, "queries is NULL");
+    SS_CUDA(q->ctx, cudaSetDevice(q->ctx->device));
+    SS_CUDA(q->ctx, cudaStreamSynchronize(q->ctx->stream));
+    q->lane_built = false;
+    q->cos_built = false;
+    return SS_OK;
+}
+
+double ss_dict_last_scan_ms(ss_dict* d) {
+    if (!d || !d->scan_timed) return -1.0;
+    cudaSetDevice(d->ctx->device);
+    if (cudaEventSynchronize(d->ev_scan1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, d->ev_scan0, d->ev_scan1) != cudaSuccess) return -1.0;
+    return (double)ms;
 }
 
 void ss_queries_destroy(ss_queries* q) {
@@ -210,26 +243,31 @@ int ss_dict_match(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offs
     if (d->nseg == 0) return set_error(ctx, SS_ERR_EMPTY_DICT, "match against an empty dictionary");
     if (k < 1 || k > SS_MAX_TOPK) return set_error(ctx, SS_ERR_INVALID, "k must be in 1..%d (got %d)", SS_MAX_TOPK, k);
     if (nq && (!out_idx || !out_dist)) return set_error(ctx, SS_ERR_INVALID, "output pointers are NULL");
-    ss_queries* q = nullptr;
-    SS_TRY(ss_queries_create(ctx, q_mfcc, q_frame_offsets, nq, d->c, &q));
-    DevBuf<uint32_t> d_idx;
-    DevBuf<double> d_dist, d_targets;
-    int rc = SS_OK;
+    SS_TRY(queries_check(ctx, q_mfcc, q_frame_offsets, nq, d->c));
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!d->scratch_q) {
+        d->scratch_q = new (std::nothrow) ss_queries();
+        if (!d->scratch_q) return set_error(ctx, SS_ERR_NOMEM, "out of host memory");
+        d->scratch_q->ctx = ctx;
+        d->scratch_q->c = d->c;
+    }
+    ss_queries* q = d->scratch_q;
     auto body = [&]() -> int {
-        SS_CUDA(ctx, d_idx.reserve(nq * (size_t)k));
-        SS_CUDA(ctx, d_dist.reserve(nq * (size_t)k));
-        if (targets && mode == SS_COSINE_REF) SS_TRY(upload(ctx, d_targets, targets, nq));
-        SS_TRY(ss_dict_match_dev(d, q, mode, (targets && mode == SS_COSINE_REF) ? d_targets.p : nullptr, k, d_idx.p, d_dist.p));
+        SS_TRY(queries_fill(q, q_mfcc, q_frame_offsets, nq));
+        SS_CUDA(ctx, d->d_res_idx.reserve(nq * (size_t)k));
+        SS_CUDA(ctx, d->d_res_dist.reserve(nq * (size_t)k));
+        const bool use_targets = targets && mode == SS_COSINE_REF;
+        if (use_targets) SS_TRY(upload(ctx, d->d_res_targets, targets, nq));
+        SS_TRY(ss_dict_match_dev(d, q, mode, use_targets ? d->d_res_targets.p : nullptr, k, d->d_res_idx.p, d->d_res_dist.p));
         if (nq) {
-            SS_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx.p, nq * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            SS_CUDA(ctx, cudaMemcpyAsync(out_dist, d_dist.p, nq * (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            SS_CUDA(ctx, cudaMemcpyAsync(out_idx, d->d_res_idx.p, nq * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            SS_CUDA(ctx, cudaMemcpyAsync(out_dist, d->d_res_dist.p, nq * (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
         SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return SS_OK;
     };
-    rc = body();
+    const int rc = body();
     if (rc != SS_OK) cudaStreamSynchronize(ctx->stream);
-    ss_queries_destroy(q);
     return rc;
 }
 

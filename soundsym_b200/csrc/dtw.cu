@@ -446,7 +446,7 @@ int dtw_dict_build(ss_dict* d) {
 
 int dtw_queries_build(ss_queries* q) {
     ss_ctx* ctx = q->ctx;
-    if (q->d_lane.p) return SS_OK;
+    if (q->lane_built) return SS_OK;
     // sort query ids by length, longest first (heavy CTAs are scheduled first); zero-length queries get no lane
     std::vector<uint32_t> order;
     order.reserve(q->nq);
@@ -487,6 +487,7 @@ int dtw_queries_build(ss_queries* q) {
         SS_LAUNCHED(ctx);
     }
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    q->lane_built = true;
     return SS_OK;
 }
 
@@ -513,7 +514,12 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
     const uint32_t nqb = (q->ngroups + kWarpsPerCta - 1) / kWarpsPerCta;
     uint32_t nslices = 1;
     if (nqb && d->ntiles) {
-        const uint32_t target_ctas = (uint32_t)ctx->sm_count * 4 * 4;  // ~4 waves at 4 CTAs / SM
+        static int waves = 0;
+        if (!waves) {
+            const char* e = getenv("SS_DTW_WAVES");
+            waves = e ? std::max(1, atoi(e)) : 4;
+        }
+        const uint32_t target_ctas = (uint32_t)ctx->sm_count * 4 * waves;  // ~`waves` waves at 4 CTAs / SM
         nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->ntiles, (target_ctas + nqb - 1) / nqb));
     }
     std::vector<uint32_t>& st = d->h_slice_tile;
@@ -560,9 +566,16 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
             SS_CUDA(ctx, d->d_scratch.reserve((size_t)grid * p.scratch_rows * 128));
             p.scratch = d->d_scratch.p;
         }
+        if (!d->ev_scan0) {
+            SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
+            SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
+        }
 #define SS_SCAN_CASE(RBV, KPV)                                       \
     if (g_scan_rb == RBV && kp == KPV) {                              \
+        SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));      \
         SS_TRY((launch_scan<RBV, KPV>(ctx, p, grid)));                \
+        SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));      \
+        d->scan_timed = true;                                         \
         k_dtw_merge<KPV><<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_partial.p, nslices, nslots, d->d_cand_idx.p, \
                                                                         d->d_cand_adist.p);                                \
         SS_LAUNCHED(ctx);                                             \

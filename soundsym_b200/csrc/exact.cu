@@ -193,10 +193,17 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     SS_TRY(upload(ctx, d->d_slice_tile, ss.data(), ss.size()));
     SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
+    if (!d->ev_scan0) {
+        SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
+        SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
+    }
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->d_norm.p, d->c, d->d_slice_tile.p, nslices,
                                                          q->d_lane64.p, q->d_group_len.p, q->d_group_rowbase.p, q->d_group_qid.p,
                                                          q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p);
     SS_LAUNCHED(ctx);
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
+    d->scan_timed = true;
     k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices, nslots,
                                                                   q->d_group_qid.p, d->index_base, d_out_idx, d_out_dist);
     SS_LAUNCHED(ctx);

@@ -56,6 +56,13 @@ struct ss_dict {
     ss::DevBuf<unsigned long long> d_counters;  // [0] uncertified
     std::vector<uint32_t> h_slice_tile;
     uint64_t last_work = 0, last_uncertified = 0;
+    cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;  // around the dominant kernel of the last match
+    bool scan_timed = false;
+    // host-buffer entry point (ss_dict_match): query batch + result buffers reused across calls (grow-only)
+    struct ss_queries* scratch_q = nullptr;
+    ss::DevBuf<uint32_t> d_res_idx;
+    ss::DevBuf<double> d_res_dist, d_res_targets;
+    ~ss_dict();
 };
 
 struct ss_queries {
@@ -77,7 +84,14 @@ struct ss_queries {
     ss::DevBuf<float> d_max_norm;                                    // [0] = max |a|^2
     ss::DevBuf<double> d_lane64;                                     // [row*c + e][32] f64 (cosine-ref), built on first use
     bool cos_built = false;
+    bool lane_built = false;
 };
+
+inline ss_dict::~ss_dict() {
+    if (ev_scan0) cudaEventDestroy(ev_scan0);
+    if (ev_scan1) cudaEventDestroy(ev_scan1);
+    delete scratch_q;
+}
 
 namespace ss {
 int dtw_dict_build(ss_dict* d);       // builds the fp32 stream + strip / tile tables (dtw.cu)
