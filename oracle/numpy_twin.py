@@ -162,11 +162,17 @@ def cast_votes(sym, depth):  # A7, pure-Python bookkeeping with Counters
             tot = sum(nxt[k].values())
             h.append(-sum((c / tot) * math.log(c / tot) for _, c in sorted(nxt[k].items())) if tot else 0.0)
         h = np.array(h, dtype=np.float64)
-        for arr, dst in ((f, zf), (h, zh)):
-            sd = arr.std()
-            z = (arr - arr.mean()) / sd if sd > 0 else np.zeros_like(arr)
-            for k, v in zip(keys, z):
-                dst[k] = float(v)
+        m = float(len(keys))
+        s1, s2 = sum(cnt[k] for k in keys), sum(cnt[k] * cnt[k] for k in keys)  # exact integers
+        mf = s1 / m
+        vf = s2 / m - mf * mf
+        sf = math.sqrt(vf) if vf > 0 else 0.0
+        for k, v in zip(keys, f):
+            zf[k] = (float(v) - mf) / sf if sf > 0 else 0.0
+        mh = float(sum(h.tolist())) / m if False else float(np.add.reduce(h)) / m
+        sd = math.sqrt(float(((h - mh) ** 2).sum()) / m)
+        for k, v in zip(keys, h):
+            zh[k] = (float(v) - mh) / sd if sd > 0 else 0.0
     for s in range(n - depth + 1):
         w = text[s:s + depth]
         best_p, best = 1, zh[w[:1]]

@@ -578,12 +578,22 @@ void orc_cast_votes(const uint8_t* text, size_t n, int depth, uint32_t* votes) {
             }
             h[i] = ent;
         }
-        double mf = 0, mh = 0;
-        for (size_t i = 0; i < keys.size(); i++) mf += f[i], mh += h[i];
-        mf /= m, mh /= m;
-        double vf = 0, vh = 0;
-        for (size_t i = 0; i < keys.size(); i++) vf += (f[i] - mf) * (f[i] - mf), vh += (h[i] - mh) * (h[i] - mh);
-        const double sf = std::sqrt(vf / m), sh = std::sqrt(vh / m);
+        // frequency statistics from exact integer sums (order-independent, so a parallel implementation reproduces them
+        // bit for bit): mean = S1/m, var = S2/m - mean^2. Entropy statistics are plain sequential f64 sums.
+        uint64_t s1 = 0, s2 = 0;
+        for (size_t i = 0; i < keys.size(); i++) {
+            const uint64_t c = (uint64_t)tab[len][keys[i]].count;
+            s1 += c;
+            s2 += c * c;
+        }
+        const double mf = (double)s1 / m;
+        const double vf = (double)s2 / m - mf * mf;
+        double mh = 0;
+        for (size_t i = 0; i < keys.size(); i++) mh += h[i];
+        mh /= m;
+        double vh = 0;
+        for (size_t i = 0; i < keys.size(); i++) vh += (h[i] - mh) * (h[i] - mh);
+        const double sf = vf > 0 ? std::sqrt(vf) : 0.0, sh = std::sqrt(vh / m);
         for (size_t i = 0; i < keys.size(); i++)
             zt[len][keys[i]] = Z{sf > 0 ? (f[i] - mf) / sf : 0.0, sh > 0 ? (h[i] - mh) / sh : 0.0};
     }

@@ -69,6 +69,8 @@ void ss_ctx_destroy(ss_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->sound_state && ctx->sound_state_free) ctx->sound_state_free(ctx->sound_state);
+    if (ctx->seg_state && ctx->seg_state_free) ctx->seg_state_free(ctx->seg_state);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

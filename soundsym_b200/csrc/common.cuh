@@ -17,6 +17,11 @@ struct ss_ctx {
     int sm_count = 148;
     std::string err;
     uint64_t launches = 0;
+    // per-subsystem state (tables, grow-only workspaces) owned by the ctx; created lazily by sound.cu / segment.cu
+    void* sound_state = nullptr;
+    void (*sound_state_free)(void*) = nullptr;
+    void* seg_state = nullptr;
+    void (*seg_state_free)(void*) = nullptr;
 };
 
 namespace ss {

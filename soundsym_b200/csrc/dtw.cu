@@ -517,7 +517,7 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
         static int waves = 0;
         if (!waves) {
             const char* e = getenv("SS_DTW_WAVES");
-            waves = e ? std::max(1, atoi(e)) : 4;
+            waves = e ? std::max(1, atoi(e)) : 8;
         }
         const uint32_t target_ctas = (uint32_t)ctx->sm_count * 4 * waves;  // ~`waves` waves at 4 CTAs / SM
         nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->ntiles, (target_ctas + nqb - 1) / nqb));

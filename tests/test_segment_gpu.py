@@ -1,0 +1,123 @@
+"""GPU parity tests of the segmentation subsystem and of the three example flows."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from soundsym_b200 import api, synth
+from soundsym_b200._lib import SS_COSINE_REF, SS_DTW, SoundsymError
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return api.Context(0)
+
+
+def model_of(g):
+    return (g["gmm_means"], g["gmm_covs"], g["gmm_weights"])
+
+
+def test_symbols_section71_bit_exact(ctx, section71):
+    sym, post = ctx.symbols(section71["mfcc"], model_of(section71), want_posteriors=True)
+    assert np.array_equal(sym, section71["symbols"])  # boundary of parity: given the model, symbols are exact
+    z, _, _ = O.standardize(section71["mfcc"])
+    ref = O.gmm_posteriors(z, *model_of(section71))
+    assert np.allclose(post, ref, rtol=1e-9, atol=1e-300)
+
+
+def test_symbols_other_sound_uses_its_own_statistics(ctx, section71, sample_excerpt):
+    """partition_other re-fits the Standardizer on the TARGET's MFCCs (src/lib.rs:57-58, reconstruction.rs:71-77);
+    the excerpt has ~1 800 digitally silent frames."""
+    sym = ctx.symbols(sample_excerpt["mfcc"], model_of(section71))
+    assert np.array_equal(sym, sample_excerpt["symbols"])
+
+
+def test_votes_and_splits_section71(ctx, section71):
+    for depth, thr in ((3, 4), (4, 3), (5, 4)):
+        votes, lens = ctx.vote_split(section71["symbols"], depth, thr)
+        assert np.array_equal(votes, section71["votes_d%d" % depth])
+        assert np.array_equal(lens, section71["splits_d%dt%d" % (depth, thr)])
+        assert int(lens.sum()) == 1978 * 256
+
+
+def test_vote_split_random_strings_and_edges(ctx):
+    rng = np.random.default_rng(3)
+    for n, alpha, depth, thr in ((5000, 26, 5, 4), (777, 4, 3, 2), (64, 2, 7, 1), (300, 26, 1, 1), (10, 3, 2, 0)):
+        sym = (65 + rng.integers(0, alpha, n)).astype(np.uint8)
+        votes, lens = ctx.vote_split(sym, depth, thr)
+        ov = O.cast_votes(sym, depth)
+        assert np.array_equal(votes, ov), (n, alpha, depth)
+        assert np.array_equal(lens, O.split(ov, n, thr) * np.uint64(256))
+    votes, lens = ctx.vote_split(np.array([65, 66], dtype=np.uint8), 3, 1)  # shorter than the window
+    assert list(votes) == [0, 0, 0] and list(lens) == [512]
+    votes, lens = ctx.vote_split(np.zeros(0, dtype=np.uint8), 3, 1)
+    assert len(lens) == 0
+    with pytest.raises(SoundsymError):
+        ctx.vote_split(np.zeros(10, dtype=np.uint8), 8, 1)
+
+
+def test_partition_errors_and_flow(ctx, section71):
+    with pytest.raises(SoundsymError) as e:  # CosError("Must first train model"), src/lib.rs:140-142
+        ctx.partition(section71["mfcc"], None, 3, 4)
+    assert e.value.code == -4 and "Must first train model" in e.value.message
+    with pytest.raises(SoundsymError) as e:
+        ctx.partition(section71["mfcc"][:1], model_of(section71), 3, 4)
+    assert e.value.code == -6
+    lens = ctx.partition(section71["mfcc"], model_of(section71), 4, 3)  # examples/partition.rs defaults
+    assert np.array_equal(lens, section71["splits_d4t3"])
+
+
+def test_partition_long_synthetic(ctx, section71):
+    """5 minutes of synthetic audio through MFCC -> symbols -> votes -> splits, GPU vs oracle end to end."""
+    s = synth.audio(300.0, seed=42)
+    m = ctx.mfcc(s)
+    om = O.mfcc(s)
+    assert np.all(np.abs(m - om) <= 1e-9 * np.maximum(np.abs(om), 1.0))
+    z, _, _ = O.standardize(om)
+    model = O.gmm_train(z, seed=1)
+    lens = ctx.partition(m, model, 3, 4)
+    olens, osym, _ = O.partition(om, model, 3, 4)
+    sym = ctx.symbols(m, model)
+    assert np.mean(sym != osym) < 1e-4  # MFCC inputs differ by ~1e-13: a symbol may flip only at a posterior tie
+    if np.array_equal(sym, osym):
+        assert np.array_equal(lens, olens)
+
+
+def test_reconstruction_flow_like_the_example(ctx, section71, sample_excerpt):
+    """examples/reconstruction.rs with tests/Section_7_1.wav as source and the sample.wav excerpt as target:
+    Sound::from_samples -> Partitioner(threshold 4, depth 3).partition -> SoundDictionary::from_segments ->
+    partition target with the source's model -> clone_from_dictionary -> to_sound."""
+    src = api.Sound.from_samples(O.decode_pcm(section71["pcm"].astype(np.int32), 16), 44100.0, ctx=ctx)
+    part = api.Partitioner(src, ctx).set_threshold(4).set_depth(3)
+    part.train(model_of(section71))
+    splits = part.partition()
+    assert np.array_equal(splits, section71["splits_d3t4"])
+    dictionary = api.SoundDictionary.from_segments(src, splits, ctx, SS_COSINE_REF)
+    tgt = api.Sound.from_samples(O.decode_pcm(sample_excerpt["pcm"], 24), 44100.0, ctx=ctx)
+    part.sound = tgt
+    tsplits = part.partition()
+    assert np.array_equal(tsplits, sample_excerpt["splits_d3t4"])
+    segs, spos, fpos = [], 0, 0
+    for sp in tsplits:  # reconstruction.rs:77-81
+        sp = int(sp)
+        segs.append(api.Sound(tgt.samples()[spos:spos + sp], 44100.0, tgt.mfcc_arrays()[fpos:fpos + sp // 256], None,
+                              tgt.mfcc_arrays()[fpos:fpos + sp // 256].mean(axis=0) if sp // 256 else np.full(12, np.nan), None, ctx))
+        spos += sp
+        fpos += sp // 256
+    seq = api.SoundSequence(segs, ctx)
+    idx, dist = dictionary.match_indices(segs)
+    assert np.array_equal(idx[:, 0], sample_excerpt["cos_idx"])  # MFCCs differ ~1e-13 from the oracle's: ties aside, same argmin
+    out = seq.clone_from_dictionary(dictionary).to_sound()
+    assert len(out.samples()) == int(sample_excerpt["resynth_len"])
+    assert np.array_equal(out.samples()[:65536], sample_excerpt["resynth_head"])
+    # matcher.rs flow: silent queries (max_power < 0.03) are gated out by the caller, the rest matched
+    loud = [s for s, p in zip(segs, sample_excerpt["q_max_power"]) if p >= 0.03]
+    assert len(loud) == int((sample_excerpt["q_max_power"] >= 0.03).sum())
+    m = dictionary.match_sound(loud[0])
+    assert m is dictionary.sounds[int(sample_excerpt["cos_idx"][list(sample_excerpt["q_max_power"] >= 0.03).index(True)])]
+    # the DTW extension on the same data
+    d2 = api.SoundDictionary.from_segments(src, splits, ctx, SS_DTW)
+    di, dd = d2.match_indices(segs, k=4)
+    assert np.array_equal(di, sample_excerpt["dtw_idx"])
+    assert np.allclose(dd, sample_excerpt["dtw_dist"], rtol=1e-9)

@@ -1,0 +1,123 @@
+"""GPU parity tests of the MFCC subsystem against the oracle and the golden fixtures."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from soundsym_b200 import api, synth
+from soundsym_b200._lib import SoundsymError
+
+pytestmark = pytest.mark.gpu
+
+# north-star bar: MFCC coefficients within 1e-4 relative. The kernel computes in f64, so the test holds it to
+# |delta| <= 1e-9 * max(|ref|, 1) — five orders tighter; the slack covers a different FFT factorisation only.
+MFCC_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return api.Context(0)
+
+
+def assert_mfcc_close(got, ref):
+    assert got.shape == ref.shape
+    assert np.all(np.abs(got - ref) <= MFCC_RTOL * np.maximum(np.abs(ref), 1.0)), float(np.max(np.abs(got - ref)))
+
+
+def test_decode_pcm_bit_exact(ctx, section71, sample_excerpt):
+    s16 = ctx.decode_pcm(section71["pcm"].astype(np.int32), 16)
+    assert np.array_equal(s16, O.decode_pcm(section71["pcm"].astype(np.int32), 16))
+    s24 = ctx.decode_pcm(sample_excerpt["pcm"], 24)
+    assert np.array_equal(s24, O.decode_pcm(sample_excerpt["pcm"], 24))
+    assert ctx.decode_pcm(np.array([8388607], dtype=np.int32), 24)[0] == 1.0
+
+
+def test_analyze_section71_vs_golden(ctx, section71):
+    s = O.decode_pcm(section71["pcm"].astype(np.int32), 16)
+    mfcc, mp, mean = ctx.analyze(s, float(section71["sample_rate"]), 12)
+    assert mfcc.shape == (1978, 12)
+    assert_mfcc_close(mfcc, section71["mfcc"])
+    assert mp == float(section71["max_power"])  # bit-exact: same fold, separate multiply / add
+    assert np.allclose(mean, section71["mean_mfccs"], rtol=1e-12, atol=1e-12)
+
+
+def test_analyze_sample_excerpt_with_digital_silence(ctx, sample_excerpt):
+    s = O.decode_pcm(sample_excerpt["pcm"], 24)
+    mfcc, mp, _ = ctx.analyze(s, 44100.0, 12)
+    assert np.all(np.isfinite(mfcc))  # silent frames hit the energy floor (A4), no -inf
+    assert_mfcc_close(mfcc, sample_excerpt["mfcc"])
+    assert mp == float(sample_excerpt["max_power"])
+
+
+def test_c13_and_synthetic_audio(ctx):
+    s = synth.audio(3.0, seed=5)
+    for c in (12, 13):
+        assert_mfcc_close(ctx.mfcc(s, 44100.0, c), O.mfcc(s, 44100.0, c))
+    assert ctx.max_power(s) == O.max_power(s)
+
+
+def test_frame_edge_cases(ctx):
+    assert ctx.mfcc(np.zeros(0)).shape == (0, 12)
+    assert ctx.mfcc(np.zeros(1023)).shape == (0, 12)
+    m = ctx.mfcc(np.zeros(5120))
+    assert m.shape == (17, 12)  # the reference's stale asserts expect 5 (src/sound.rs:618-631); the code gives 17
+    assert_mfcc_close(m, O.mfcc(np.zeros(5120)))  # silence: energy floor (A4) -> c0 = -240, others ~0
+    rng = np.random.default_rng(0)
+    for n in (1024, 1279, 1280, 4097):
+        s = rng.uniform(-1, 1, n)
+        assert_mfcc_close(ctx.mfcc(s), O.mfcc(s))
+        assert ctx.max_power(s) == O.max_power(s)
+    assert ctx.max_power(np.zeros(100)) == 0.0 and ctx.max_power(np.zeros(0)) == 0.0
+    _, _, mean = ctx.analyze(np.zeros(10))
+    assert np.all(np.isnan(mean))  # 0/0, as analyze_mean_mfccs on an empty sound
+    with pytest.raises(SoundsymError):
+        ctx.mfcc(np.zeros(4096), 8000.0)  # band edges beyond Nyquist bin range
+
+
+def test_push_samples_equals_batch(ctx):
+    """Sound::push_samples (src/sound.rs:145-164) re-analyses from initial_frames*HOP: same frames as one batch pass."""
+    s = synth.audio(1.0, seed=9)
+    whole = api.Sound.from_samples(s, 44100.0, ctx=ctx)
+    inc = api.Sound.from_samples(s[:10000], 44100.0, ctx=ctx)
+    inc.push_samples(s[10000:30000])
+    inc.push_samples(s[30000:])
+    assert inc.num_frames() == whole.num_frames()
+    assert np.array_equal(inc.mfcc_arrays(), whole.mfcc_arrays())
+    assert inc.max_power() == whole.max_power()
+    z = api.Sound.from_samples(np.zeros(0), 44100.0, ctx=ctx)
+    z.push_samples(np.zeros(4096 + 1024))
+    assert z.num_frames() == 17 and len(z.samples()) == 5120
+
+
+def test_mfcc_dev_large_matches_oracle_sample(ctx):
+    """device-resident entry on a longer signal; spot-check frames against the oracle."""
+    import torch
+    s = synth.audio(30.0, seed=11)
+    d = torch.from_numpy(s).cuda()
+    frames = O.frame_count(len(s))
+    out = torch.empty((frames, 12), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.ss_mfcc_dev(ctx.h, d.data_ptr(), len(s), 44100.0, 12, out.data_ptr()))
+    ctx.sync()
+    got = out.cpu().numpy()
+    for f0 in (0, 1234, frames - 40):
+        ref = O.mfcc(s[f0 * 256:f0 * 256 + 1024 + 39 * 256])
+        assert_mfcc_close(got[f0:f0 + 40], ref)
+
+
+def test_resynth_and_sequence_distances(ctx, section71, sample_excerpt):
+    ds = np.arange(10, dtype=np.float64)
+    out = ctx.resynth(ds, np.array([0, 4, 10], dtype=np.uint64), np.array([1, 0, 0]), np.array([3, 6, 4], dtype=np.uint64))
+    assert list(out) == [4, 5, 6, 0, 1, 2, 3, 0, 0, 0, 1, 2, 3]
+    s71 = O.decode_pcm(section71["pcm"].astype(np.int32), 16)
+    soff = np.zeros(len(section71["splits_d3t4"]) + 1, dtype=np.uint64)
+    soff[1:] = np.cumsum(section71["splits_d3t4"])
+    out = ctx.resynth(s71, soff, sample_excerpt["cos_idx"], sample_excerpt["splits_d3t4"])
+    ref = O.resynth(s71, soff, sample_excerpt["cos_idx"], sample_excerpt["splits_d3t4"])
+    assert np.array_equal(out, ref)
+    assert np.array_equal(out[:65536], sample_excerpt["resynth_head"]) and len(out) == int(sample_excerpt["resynth_len"])
+    rows = section71["mfcc"][:50]
+    got = ctx.sequence_distances(rows)
+    ref = np.array([O.cosine_sim_angular(rows[i], rows[i + 1]) for i in range(49)])
+    assert np.allclose(got, ref, rtol=0, atol=1e-15)
+    v = np.array([[0.1, 0.4, 0.2, 0.8] + [0.0] * 8] * 2)
+    assert ctx.sequence_distances(v)[0] == 0.0  # the reference's KAT, src/sound.rs:612-615
