@@ -1,0 +1,378 @@
+// soundsym.hpp — C++17 host mirror of the reference crate's public API for the hot path, on top of the C ABI
+// (soundsym_b200.h). The reference is compiled Rust and Rust is not installed in this image, so this header plays the
+// role of the `extern "C"` shim of INTEGRATION.md: same type names, method names, argument meaning and error behaviour
+// as src/lib.rs / src/sound.rs. Header-only; link with -lsoundsym_b200. All numerics run in the library on the GPU.
+//
+//   Sound            src/sound.rs:71-213      SoundDictionary  src/sound.rs:288-371
+//   SoundSequence    src/sound.rs:373-484     Partitioner      src/lib.rs:62-151      CosError  src/lib.rs:181-198
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "soundsym_b200.h"
+
+namespace soundsym {
+
+constexpr size_t NCOEFFS = SS_NCOEFFS, NCLUSTERS = SS_NCLUSTERS, HOP = SS_HOP, BIN = SS_BIN;  // src/lib.rs:22-25
+
+/// CosError (src/lib.rs:181-198): a message plus the C ABI status it came from.
+struct CosError : std::runtime_error {
+    int code;
+    CosError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+/// one ss_ctx per process and device (the crate is single-threaded; so is a context)
+class Context {
+   public:
+    explicit Context(int device = 0) {
+        const int rc = ss_ctx_create(device, &h_);
+        if (rc != SS_OK) throw CosError(rc, ss_last_error(nullptr));
+    }
+    ~Context() { ss_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    ss_ctx* get() const { return h_; }
+    void check(int rc) const {
+        if (rc != SS_OK) throw CosError(rc, ss_last_error(h_));
+    }
+    static Context& global() {
+        static Context ctx(0);
+        return ctx;
+    }
+
+   private:
+    ss_ctx* h_ = nullptr;
+};
+
+/// GaussianMixtureModel as train_model returns it (src/lib.rs:44-54)
+struct GaussianMixtureModel {
+    int ncomp = 0, ncoeffs = 0;
+    std::vector<double> means, covs, weights;
+    ss_gmm view() const { return ss_gmm{ncomp, ncoeffs, means.data(), covs.data(), weights.data()}; }
+    /// binary dump: i32 ncomp, i32 ncoeffs, then means, covs, weights as f64
+    static GaussianMixtureModel load(const std::string& path) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw CosError(SS_ERR_INVALID, "cannot open model file " + path);
+        GaussianMixtureModel m;
+        int32_t hdr[2];
+        f.read(reinterpret_cast<char*>(hdr), 8);
+        m.ncomp = hdr[0];
+        m.ncoeffs = hdr[1];
+        m.means.resize((size_t)m.ncomp * m.ncoeffs);
+        m.covs.resize((size_t)m.ncomp * m.ncoeffs * m.ncoeffs);
+        m.weights.resize(m.ncomp);
+        f.read(reinterpret_cast<char*>(m.means.data()), m.means.size() * 8);
+        f.read(reinterpret_cast<char*>(m.covs.data()), m.covs.size() * 8);
+        f.read(reinterpret_cast<char*>(m.weights.data()), m.weights.size() * 8);
+        if (!f) throw CosError(SS_ERR_INVALID, "short model file " + path);
+        return m;
+    }
+};
+
+class Sound {
+   public:
+    std::optional<std::string> name;
+
+    /// Sound::from_samples (src/sound.rs:92-112): MFCC + max_power + mean in one device pass
+    static Sound from_samples(std::vector<double> samples, double sample_rate, std::optional<std::vector<double>> mfccs = std::nullopt,
+                              std::optional<std::string> name = std::nullopt, Context& ctx = Context::global()) {
+        Sound s;
+        s.ctx_ = &ctx;
+        s.name = std::move(name);
+        s.sample_rate_ = sample_rate;
+        size_t frames = 0;
+        ss_frame_count(samples.size(), &frames);
+        std::vector<double> out(frames * NCOEFFS);
+        s.mean_mfccs_.assign(NCOEFFS, 0.0);
+        ctx.check(ss_sound_analyze(ctx.get(), samples.data(), samples.size(), sample_rate, (int)NCOEFFS, out.data(), &frames, &s.max_power_,
+                                   s.mean_mfccs_.data()));
+        if (mfccs) {  // the reference computes and discards its own analysis here (src/sound.rs:94)
+            s.mfccs_ = std::move(*mfccs);
+            s.mean_mfccs_ = mean_of(s.mfccs_);
+        } else {
+            s.mfccs_ = std::move(out);
+        }
+        s.samples_ = std::move(samples);
+        return s;
+    }
+
+    /// Sound::from_path (src/sound.rs:116-126): mono integer-PCM WAV; the int -> f64 conversion runs on the GPU
+    static Sound from_path(const std::string& path, Context& ctx = Context::global()) {
+        int bits = 0;
+        double sr = 0;
+        std::vector<int32_t> pcm = read_wav_pcm(path, &bits, &sr);
+        std::vector<double> samples(pcm.size());
+        ctx.check(ss_decode_pcm(ctx.get(), pcm.data(), pcm.size(), bits, samples.data()));
+        std::string stem = path.substr(path.find_last_of('/') == std::string::npos ? 0 : path.find_last_of('/') + 1);
+        stem = stem.substr(0, stem.find_last_of('.'));
+        return from_samples(std::move(samples), sr, std::nullopt, stem, ctx);
+    }
+
+    /// Sound::push_samples (src/sound.rs:145-164), including its `(old*n0 + new*n1) * 0.5` mean rule
+    void push_samples(const std::vector<double>& new_samples) {
+        const size_t initial = num_frames();
+        samples_.insert(samples_.end(), new_samples.begin(), new_samples.end());
+        const double* tail = samples_.data() + initial * HOP;
+        const size_t n = samples_.size() - initial * HOP;
+        size_t frames = 0;
+        ss_frame_count(n, &frames);
+        std::vector<double> out(frames * NCOEFFS), mean(NCOEFFS);
+        double mp = 0;
+        ctx_->check(ss_sound_analyze(ctx_->get(), tail, n, sample_rate_, (int)NCOEFFS, out.data(), &frames, &mp, mean.data()));
+        mfccs_.insert(mfccs_.end(), out.begin(), out.end());
+        const size_t nf = num_frames() - initial;
+        for (size_t k = 0; k < NCOEFFS; k++) mean_mfccs_[k] = (mean_mfccs_[k] * (double)initial + mean[k] * (double)nf) * 0.5;
+        max_power_ = std::fmax(max_power_, mp);
+    }
+
+    /// Sound::write_file (src/sound.rs:129-143): 32-bit integer PCM
+    void write_file(const std::string& path) const {
+        std::ofstream f(path, std::ios::binary);
+        const uint32_t bytes = (uint32_t)(samples_.size() * 4), sr = (uint32_t)sample_rate_;
+        auto u32 = [&](uint32_t v) { f.write(reinterpret_cast<const char*>(&v), 4); };
+        auto u16 = [&](uint16_t v) { f.write(reinterpret_cast<const char*>(&v), 2); };
+        f.write("RIFF", 4), u32(36 + bytes), f.write("WAVEfmt ", 8), u32(16), u16(1), u16(1), u32(sr), u32(sr * 4), u16(4), u16(32);
+        f.write("data", 4), u32(bytes);
+        for (double s : samples_) {
+            const double v = std::trunc(2147483647.0 * s);
+            const int32_t i = v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v);
+            f.write(reinterpret_cast<const char*>(&i), 4);
+        }
+    }
+
+    double max_power() const { return max_power_; }
+    const std::vector<double>& samples() const { return samples_; }
+    double sample_rate() const { return sample_rate_; }
+    const std::vector<double>& mfccs() const { return mfccs_; }
+    const std::vector<double>& mean_mfccs() const { return mean_mfccs_; }
+    size_t num_frames() const { return mfccs_.size() / NCOEFFS; }
+    Context& context() const { return *ctx_; }
+
+    /// a cut of a longer sound that carries the parent's MFCC rows (add_segments / reconstruction.rs:77-81):
+    /// Sound::from_samples(samp, sr, Some(mfccs), None) without re-running the discarded analysis
+    static Sound from_cut(std::vector<double> samples, double sample_rate, std::vector<double> mfccs, Context& ctx) {
+        Sound s;
+        s.ctx_ = &ctx;
+        s.sample_rate_ = sample_rate;
+        s.samples_ = std::move(samples);
+        s.mfccs_ = std::move(mfccs);
+        s.mean_mfccs_ = mean_of(s.mfccs_);
+        s.max_power_ = std::numeric_limits<double>::quiet_NaN();  // analysed on demand by callers that gate on it
+        return s;
+    }
+
+   private:
+    static std::vector<double> mean_of(const std::vector<double>& m) {  // analyze_mean_mfccs, src/sound.rs:271-286
+        std::vector<double> out(NCOEFFS, 0.0);
+        const size_t frames = m.size() / NCOEFFS;
+        for (size_t f = 0; f < frames; f++)
+            for (size_t k = 0; k < NCOEFFS; k++) out[k] += m[f * NCOEFFS + k];
+        for (size_t k = 0; k < NCOEFFS; k++) out[k] = out[k] / (double)frames;
+        return out;
+    }
+    static std::vector<int32_t> read_wav_pcm(const std::string& path, int* bits, double* sr) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw CosError(SS_ERR_INVALID, "cannot open " + path);
+        std::vector<char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        if (d.size() < 12 || memcmp(d.data(), "RIFF", 4) || memcmp(d.data() + 8, "WAVE", 4)) throw CosError(SS_ERR_INVALID, "not a WAVE file: " + path);
+        size_t pos = 12;
+        std::vector<int32_t> pcm;
+        while (pos + 8 <= d.size()) {
+            uint32_t size;
+            memcpy(&size, d.data() + pos + 4, 4);
+            const char* body = d.data() + pos + 8;
+            if (!memcmp(d.data() + pos, "fmt ", 4)) {
+                uint32_t rate;
+                uint16_t b;
+                memcpy(&rate, body + 4, 4);
+                memcpy(&b, body + 14, 2);
+                *sr = rate;
+                *bits = b;
+            } else if (!memcmp(d.data() + pos, "data", 4)) {
+                const size_t avail = std::min<size_t>(size, d.size() - pos - 8);
+                const int bytes = *bits / 8;
+                pcm.resize(avail / bytes);
+                for (size_t i = 0; i < pcm.size(); i++) {
+                    int32_t v = 0;
+                    memcpy(&v, body + i * bytes, bytes);
+                    if (bytes < 4) v = (v << (32 - *bits)) >> (32 - *bits);  // sign-extend
+                    pcm[i] = v;
+                }
+            }
+            pos += 8 + size + (size & 1);
+        }
+        return pcm;
+    }
+    Context* ctx_ = nullptr;
+    double max_power_ = 0, sample_rate_ = 44100;
+    std::vector<double> samples_, mfccs_, mean_mfccs_;
+};
+
+class SoundDictionary {
+   public:
+    std::vector<std::shared_ptr<Sound>> sounds;
+    int mode = SS_COSINE_REF;  // SS_DTW selects the DTW extension
+
+    explicit SoundDictionary(Context& ctx = Context::global()) : ctx_(&ctx) {}
+    ~SoundDictionary() { ss_dict_destroy(dev_); }
+    SoundDictionary(const SoundDictionary&) = delete;
+    SoundDictionary& operator=(const SoundDictionary&) = delete;
+
+    /// SoundDictionary::add_segments (src/sound.rs:330-343)
+    void add_segments(const Sound& sound, const std::vector<size_t>& segments) {
+        size_t spos = 0, fpos = 0;
+        for (size_t seg : segments) {
+            const size_t ns = std::min(seg, sound.samples().size() - std::min(spos, sound.samples().size()));
+            const size_t nv = std::min(seg / HOP * NCOEFFS, sound.mfccs().size() - std::min(fpos, sound.mfccs().size()));
+            std::vector<double> samp(sound.samples().begin() + spos, sound.samples().begin() + spos + ns);
+            std::vector<double> m(sound.mfccs().begin() + fpos, sound.mfccs().begin() + fpos + nv);
+            spos += ns;
+            fpos += nv;
+            sounds.push_back(std::make_shared<Sound>(Sound::from_cut(std::move(samp), sound.sample_rate(), std::move(m), *ctx_)));
+        }
+        ss_dict_destroy(dev_);
+        dev_ = nullptr;
+    }
+    static std::unique_ptr<SoundDictionary> from_segments(const Sound& sound, const std::vector<size_t>& segments, Context& ctx = Context::global()) {
+        auto d = std::make_unique<SoundDictionary>(ctx);
+        d->add_segments(sound, segments);
+        return d;
+    }
+
+    /// batched at_distance: (indices, distances) for every query; targets empty -> 1.0 (match_sound)
+    void match_indices(const std::vector<std::shared_ptr<Sound>>& queries, const std::vector<double>& targets, int k, std::vector<uint32_t>* idx,
+                       std::vector<double>* dist) {
+        ss_dict* d = device();
+        std::vector<uint64_t> off(queries.size() + 1, 0);
+        std::vector<double> flat;
+        for (size_t i = 0; i < queries.size(); i++) {
+            off[i + 1] = off[i] + queries[i]->num_frames();
+            flat.insert(flat.end(), queries[i]->mfccs().begin(), queries[i]->mfccs().end());
+        }
+        idx->assign(queries.size() * k, 0);
+        dist->assign(queries.size() * k, 0.0);
+        ctx_->check(ss_dict_match(d, flat.data(), off.data(), queries.size(), mode, targets.empty() ? nullptr : targets.data(), k, idx->data(),
+                                  dist->data()));
+    }
+    /// SoundDictionary::at_distance (src/sound.rs:351-370); always Some for a non-empty dictionary
+    std::shared_ptr<Sound> at_distance(double distance, const std::shared_ptr<Sound>& other) {
+        std::vector<uint32_t> idx;
+        std::vector<double> dist;
+        match_indices({other}, {distance}, 1, &idx, &dist);
+        return sounds[idx[0]];
+    }
+    /// SoundDictionary::match_sound (src/sound.rs:346-348)
+    std::shared_ptr<Sound> match_sound(const std::shared_ptr<Sound>& other) { return at_distance(1.0, other); }
+    Context& context() const { return *ctx_; }
+
+   private:
+    ss_dict* device() {
+        if (dev_) return dev_;
+        std::vector<uint64_t> off(sounds.size() + 1, 0);
+        std::vector<double> flat;
+        for (size_t i = 0; i < sounds.size(); i++) {
+            off[i + 1] = off[i] + sounds[i]->num_frames();
+            flat.insert(flat.end(), sounds[i]->mfccs().begin(), sounds[i]->mfccs().end());
+        }
+        ctx_->check(ss_dict_create(ctx_->get(), flat.data(), off.data(), sounds.size(), (int)NCOEFFS, 0, &dev_));
+        return dev_;
+    }
+    Context* ctx_;
+    ss_dict* dev_ = nullptr;
+};
+
+class SoundSequence {
+   public:
+    /// SoundSequence::new (src/sound.rs:392-401): consecutive angular distances of the mean MFCCs
+    explicit SoundSequence(std::vector<std::shared_ptr<Sound>> sounds, Context& ctx = Context::global()) : sounds_(std::move(sounds)), ctx_(&ctx) {
+        if (sounds_.size() >= 2) {
+            std::vector<double> rows;
+            for (auto& s : sounds_) rows.insert(rows.end(), s->mean_mfccs().begin(), s->mean_mfccs().end());
+            distances_.assign(sounds_.size() - 1, 0.0);
+            ctx.check(ss_sequence_distances(ctx.get(), rows.data(), sounds_.size(), (int)NCOEFFS, distances_.data()));
+        }
+    }
+    const std::vector<std::shared_ptr<Sound>>& sounds() const { return sounds_; }
+    const std::vector<double>& distances() const { return distances_; }
+
+    /// SoundSequence::clone_from_dictionary (src/sound.rs:451-472) + to_sound (:475-483): ONE batched match, then the
+    /// pad / truncate / concatenate on the GPU. Returns the assembled Sound.
+    Sound clone_from_dictionary_to_sound(SoundDictionary& dict, std::vector<uint32_t>* out_idx = nullptr) {
+        std::vector<uint32_t> idx;
+        std::vector<double> dist;
+        dict.match_indices(sounds_, {}, 1, &idx, &dist);
+        std::vector<uint64_t> doff(dict.sounds.size() + 1, 0), tlen(sounds_.size());
+        std::vector<double> dsamples;
+        for (size_t i = 0; i < dict.sounds.size(); i++) {
+            doff[i + 1] = doff[i] + dict.sounds[i]->samples().size();
+            dsamples.insert(dsamples.end(), dict.sounds[i]->samples().begin(), dict.sounds[i]->samples().end());
+        }
+        uint64_t total = 0;
+        for (size_t i = 0; i < sounds_.size(); i++) total += (tlen[i] = sounds_[i]->samples().size());
+        std::vector<double> out(total);
+        ctx_->check(ss_resynth(ctx_->get(), dsamples.data(), doff.data(), dict.sounds.size(), idx.data(), tlen.data(), sounds_.size(), out.data()));
+        if (out_idx) *out_idx = idx;
+        const double sr = sounds_.empty() ? 44100.0 : sounds_[0]->sample_rate();
+        return Sound::from_samples(std::move(out), sr, std::nullopt, std::nullopt, *ctx_);
+    }
+
+    /// SoundSequence::morph_to (src/sound.rs:440-449), batched
+    SoundSequence morph_to(const std::vector<double>& distances, SoundDictionary& dict) {
+        const size_t n = std::min(sounds_.size(), distances.size());
+        std::vector<std::shared_ptr<Sound>> q(sounds_.begin(), sounds_.begin() + n), out;
+        std::vector<uint32_t> idx;
+        std::vector<double> dist;
+        dict.match_indices(q, std::vector<double>(distances.begin(), distances.begin() + n), 1, &idx, &dist);
+        for (uint32_t i : idx) out.push_back(dict.sounds[i]);
+        return SoundSequence(std::move(out), *ctx_);
+    }
+    /// SoundSequence::from_distances (src/sound.rs:405-417): sequential chain of nq = 1 matches
+    static SoundSequence from_distances(const std::vector<double>& distances, std::shared_ptr<Sound> start, SoundDictionary& dict) {
+        std::vector<std::shared_ptr<Sound>> sounds{std::move(start)};
+        for (double d : distances) sounds.push_back(dict.at_distance(d, sounds.back()));
+        return SoundSequence(std::move(sounds), dict.context());
+    }
+
+   private:
+    std::vector<std::shared_ptr<Sound>> sounds_;
+    std::vector<double> distances_;
+    Context* ctx_;
+};
+
+class Partitioner {
+   public:
+    std::shared_ptr<Sound> sound;
+    size_t depth = 5, threshold = 4;  // Partitioner::new defaults, src/lib.rs:75-82
+    std::optional<GaussianMixtureModel> model;
+
+    explicit Partitioner(std::shared_ptr<Sound> s) : sound(std::move(s)) {}
+    Partitioner& set_depth(size_t d) { return depth = d, *this; }
+    Partitioner& set_threshold(size_t t) { return threshold = t, *this; }
+    /// Partitioner::train (src/lib.rs:101-107). EM training is not on the data-parallel path (the reference's is randomly
+    /// seeded, so parity is only defined GIVEN a model): the caller supplies one.
+    void train(GaussianMixtureModel m) { model = std::move(m); }
+
+    /// Partitioner::partition_other (src/lib.rs:112-144): segment lengths in samples
+    std::vector<size_t> partition_other(const Sound& other) const {
+        Context& ctx = other.context();
+        std::vector<uint64_t> lens(std::max<size_t>(other.num_frames(), 1));
+        size_t nseg = 0;
+        ss_gmm view{};
+        if (model) view = model->view();
+        ctx.check(ss_partition(ctx.get(), other.mfccs().data(), other.num_frames(), model ? &view : nullptr, (int)depth, (int)threshold, lens.data(), &nseg));
+        return std::vector<size_t>(lens.begin(), lens.begin() + nseg);
+    }
+    std::vector<size_t> partition() const { return partition_other(*sound); }
+};
+
+}  // namespace soundsym
