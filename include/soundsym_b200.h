@@ -151,6 +151,9 @@ uint64_t ss_dict_last_work(const ss_dict* dict);
 /* SS_DTW only: number of queries of the last match whose exact top-k could not be certified from the fp32 scan's
  * candidate list (see DESIGN.md "filter and refine"); 0 means every reported index is the f64 argmin. */
 uint64_t ss_dict_last_uncertified(const ss_dict* dict);
+/* SS_DTW only: number of queries of the last match that the tensor-core (fp16) scan could not certify and that were
+ * therefore re-run through the fp32 scan before the result was returned. */
+uint64_t ss_dict_last_tc_fallback(const ss_dict* dict);
 
 /* ss_resynth   SoundSequence::clone_from_dictionary sample assembly (src/sound.rs:451-472) + to_sound (:475-483):
  *              for target segment t copy min(len) samples of dictionary sound match_idx[t] and zero-pad to

@@ -196,6 +196,10 @@ class DeviceDictionary:
     def last_uncertified(self):
         return int(self.ctx.lib.ss_dict_last_uncertified(self.h))
 
+    @property
+    def last_tc_fallback(self):
+        return int(self.ctx.lib.ss_dict_last_tc_fallback(self.h))
+
 
 class DeviceQueries:
     """ss_queries: a prepared query batch resident in HBM."""

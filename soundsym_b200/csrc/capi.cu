@@ -121,6 +121,7 @@ int ss_dict_create(ss_ctx* ctx, const double* mfcc_flat, const uint64_t* frame_o
     if (rc == SS_OK) rc = upload(ctx, d->d_off, d->h_off.data(), nseg + 1);
     if (rc == SS_OK) rc = cosine_dict_build(d);
     if (rc == SS_OK) rc = dtw_dict_build(d);
+    if (rc == SS_OK) rc = dtw_tc_dict_build(d);
     if (rc == SS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_error(ctx, SS_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != SS_OK) {
         delete d;
@@ -138,6 +139,7 @@ void ss_dict_destroy(ss_dict* d) {
 }
 size_t ss_dict_len(const ss_dict* d) { return d ? d->nseg : 0; }
 uint64_t ss_dict_last_work(const ss_dict* d) { return d ? d->last_work : 0; }
+uint64_t ss_dict_last_tc_fallback(const ss_dict* d) { return d ? d->last_tc_fallback : 0; }
 
 uint64_t ss_dict_last_uncertified(const ss_dict* dc) {
     ss_dict* d = const_cast<ss_dict*>(dc);
@@ -157,6 +159,7 @@ static int queries_fill(ss_queries* q, const double* q_mfcc, const uint64_t* q_f
     q->max_len = 0;
     q->lane_built = false;
     q->cos_built = false;
+    q->tc_built = false;
     q->h_off.resize(nq + 1);
     const uint64_t base = nq ? q_frame_offsets[0] : 0;
     q->h_off[0] = 0;
@@ -203,6 +206,7 @@ int ss_queries_invalidate(ss_queries* q) {
     SS_CUDA(q->ctx, cudaStreamSynchronize(q->ctx->stream));
     q->lane_built = false;
     q->cos_built = false;
+    q->tc_built = false;
     return SS_OK;
 }
 

@@ -378,7 +378,10 @@ __global__ void k_dtw_merge(const unsigned long long* __restrict__ partial, uint
 
 // exact f64 kernels live in exact.cu (compiled with --fmad=false)
 namespace ss {
-int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, uint32_t* d_out_idx, double* d_out_dist);
+int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, double eps,
+                         const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
+                         bool fill, uint32_t* d_out_idx, double* d_out_dist);
+int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used);
 }
 
 namespace ss {
@@ -444,14 +447,19 @@ int dtw_dict_build(ss_dict* d) {
     return SS_OK;
 }
 
-int dtw_queries_build(ss_queries* q) {
+int dtw_queries_build(ss_queries* q, const std::vector<uint32_t>* subset) {
     ss_ctx* ctx = q->ctx;
-    if (q->lane_built) return SS_OK;
+    if (q->lane_built && !subset) return SS_OK;
     // sort query ids by length, longest first (heavy CTAs are scheduled first); zero-length queries get no lane
     std::vector<uint32_t> order;
     order.reserve(q->nq);
-    for (size_t i = 0; i < q->nq; i++)
-        if (q->h_off[i + 1] > q->h_off[i]) order.push_back((uint32_t)i);
+    if (subset) {
+        for (uint32_t i : *subset)
+            if (q->h_off[i + 1] > q->h_off[i]) order.push_back(i);
+    } else {
+        for (size_t i = 0; i < q->nq; i++)
+            if (q->h_off[i + 1] > q->h_off[i]) order.push_back((uint32_t)i);
+    }
     auto len_of = [&](uint32_t i) { return (uint32_t)(q->h_off[i + 1] - q->h_off[i]); };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len_of(x) > len_of(y); });
     std::vector<uint32_t> glen, gbase, gqid;
@@ -487,7 +495,7 @@ int dtw_queries_build(ss_queries* q) {
         SS_LAUNCHED(ctx);
     }
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    q->lane_built = true;
+    q->lane_built = !subset;  // a subset layout is transient
     return SS_OK;
 }
 
@@ -501,10 +509,32 @@ static int launch_scan(ss_ctx* ctx, const ScanParams& p, uint32_t grid) {
 
 static int g_scan_rb = 0;  // 0 = default; tools/tests may override through SS_DTW_RB
 
+static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset);
+
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
     if (k < 1 || k > SS_MAX_TOPK) return set_error(ctx, SS_ERR_INVALID, "k must be in 1..%d (got %d)", SS_MAX_TOPK, k);
-    SS_TRY(dtw_queries_build(q));
+    bool used = false;  // tensor-core scan (dtw_tc.cu) when the shapes allow it
+    SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
+    if (!used) return dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr);
+    // queries whose top-k the fp16 scan could not certify are re-run through the fp32 scan (rigorous bound 4e-6)
+    unsigned long long n_unc = 0;
+    SS_CUDA(ctx, cudaMemcpyAsync(&n_unc, d->d_counters.p, sizeof(n_unc), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    d->last_tc_fallback = n_unc;
+    if (n_unc == 0) return SS_OK;
+    std::vector<uint8_t> flags(q->nq);
+    SS_CUDA(ctx, cudaMemcpyAsync(flags.data(), q->d_uncert_flag.p, q->nq, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> subset;
+    for (size_t i = 0; i < q->nq; i++)
+        if (flags[i]) subset.push_back((uint32_t)i);
+    return dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, &subset);
+}
+
+static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset) {
+    ss_ctx* ctx = d->ctx;
+    SS_TRY(dtw_queries_build(q, subset));
     const int kp = k <= 2 ? 4 : (k <= 6 ? 8 : 16);  // candidates kept per query by the scan
     const uint32_t nslots = q->ngroups * 32;
     d->last_work = d->total_frames * q->total_frames;
@@ -591,7 +621,9 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
         SS_SCAN_CASE(1, 16)
 #undef SS_SCAN_CASE
     }
-    return dtw_rescore_finalize(d, q, k, kp, nslots, d_out_idx, d_out_dist);
+    // fp32 scan: |error| of a normalised distance <= 4e-6 (max|a|^2 + max|b|^2)  (14 roundings of 2^-24 on terms <= 2(|a|^2+|b|^2))
+    return dtw_rescore_finalize(d, q, k, kp, nslots, q->d_group_qid.p, 4e-6, q->d_max_norm.p, d->d_max_norm.p, nullptr, 0, nullptr,
+                                /*fill=*/subset == nullptr, d_out_idx, d_out_dist);
 }
 
 }  // namespace ss

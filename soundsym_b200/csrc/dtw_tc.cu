@@ -1,0 +1,649 @@
+// dtw_tc.cu — tensor-core variant of the DTW scan (filter stage only; merge / f64 refine / certification are shared
+// with dtw.cu + exact.cu). Used when every dictionary segment and every query has <= 32 frames; otherwise dtw.cu's fp32
+// scan runs.
+//
+// Idea: the local-cost matrix is a K = 13 contraction, c(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j. One tcgen05.mma per
+// (dictionary tile, query row i) computes, for the CTA's 128 queries at once, the costs of row i against the 128 columns
+// of the tile (4 segment slots x 32 columns):
+//     D[m, n] = sum_k A_i[m, k] * B[n, k],   A_i[m, :] = [-2 a^(m)_i (13), s, s, 0]   (fp16, K-major, no swizzle)
+//                                            B[n, :]   = [ b_n (13), (|b_n|^2/s)_hi, (|b_n|^2/s)_lo, 0 ]
+// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 128 columns, K = 16 = one MMA). TMEM lane m is
+// read back by the thread that owns query m (tcgen05.ld 32x32b), which adds |a_i|^2 and runs the DP recurrence for its
+// two segment slots with the row state in registers:  FADD + FMNMX3 + FADD per cell instead of 7 FFMA2 + 2 FADD + FMNMX3.
+// Both sides are centred on the dictionary's mean frame before the fp16 conversion (the cost is translation invariant).
+//
+// Warp roles (288 threads, 1 CTA / SM): warps 0-7 = DP (warp w owns TMEM lane quadrant w % 4 and column half w / 4);
+// warp 8 = TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and
+// the MMAs (4 TMEM slots of 128 columns, so the tensor core runs up to 4 rows ahead of the DP).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "match.cuh"
+
+namespace ss {
+
+int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, double eps,
+                         const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
+                         bool fill, uint32_t* d_out_idx, double* d_out_dist);
+
+constexpr int kTcM = 128;          // queries per CTA = MMA M = TMEM lanes
+constexpr int kTcN = 128;          // columns per tile = MMA N
+constexpr int kTcSlots = 4;        // segment slots per tile (32 columns each)
+constexpr int kTcK = 16;           // fp16 elements per row = one MMA K step
+constexpr int kTcTileBytes = kTcN * kTcK * 2;  // 4096
+constexpr int kTcStages = 4;       // B-tile ring
+constexpr int kTcTmemSlots = 4;    // 4 x 128 columns = 512
+constexpr int kTcMaxLen = 32;
+constexpr int kTcThreads = 288;
+
+// byte offset of element (row, k) inside a 128 x 16 fp16 K-major no-swizzle UMMA tile:
+// core matrix = 8 rows x 16 B; LBO (between the two K chunks) = 2048 B, SBO (between 8-row groups) = 128 B
+__host__ __device__ __forceinline__ int tc_tile_offset(int row, int k) { return ((k >> 3) * 16 + (row >> 3)) * 128 + (row & 7) * 16 + (k & 7) * 2; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count)); }
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory"); }
+// blocking wait: try_wait suspends the thread in hardware (up to the hint) instead of hot-spinning, and a failed
+// probe backs off with nanosleep — a spinning high-id warp otherwise starves the DP warps that share its scheduler
+// (measured: 33 issued instructions per cell with a plain try_wait loop).
+__device__ __forceinline__ void mb_wait(uint64_t* bar, unsigned parity) {
+    const uint32_t addr = s32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
+}
+__device__ __forceinline__ void tma_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
+                 "r"(bytes), "r"(s32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// D[tmem] = A[smem] * B[smem]^T (overwrite), kind::f16, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t tc_smem_desc(const void* p) {
+    // start >> 4 | LBO (2048 B) >> 4 << 16 | SBO (128 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
+    return (uint64_t)((s32(p) & 0x3FFFF) >> 4) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tc_min3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout builders
+// ---------------------------------------------------------------------------------------------------------------
+// per-coefficient sums of the dictionary frames -> mu (deterministic: one block, fixed order)
+__global__ void k_tc_mean(const double* __restrict__ mfcc, size_t frames, int c, double* __restrict__ mu) {
+    __shared__ double s[256];
+    const int col = threadIdx.x % 16, rl = threadIdx.x / 16;
+    double acc = 0.0;
+    if (col < c)
+        for (size_t r = rl; r < frames; r += 16) acc += mfcc[r * c + col];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && col < c) {
+        for (int j = 1; j < 16; j++) acc += s[j * 16 + col];
+        mu[col] = frames ? acc / (double)frames : 0.0;
+    }
+}
+// max over frames of |fp16(b - mu)|^2 (to pick the power-of-two scale of the norm columns) and max |fp16(b - mu)|
+__global__ void k_tc_dict_maxnorm(const double* __restrict__ mfcc, size_t frames, int c, const double* __restrict__ mu,
+                                  float* __restrict__ out /* [0] max norm, [1] max abs */) {
+    const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float nrm = 0.f, mx = 0.f;
+    if (f < frames) {
+        for (int k = 0; k < c; k++) {
+            const float v = __half2float(__float2half_rn((float)(mfcc[f * c + k] - mu[k])));
+            nrm += v * v;
+            mx = fmaxf(mx, fabsf(v));
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        nrm = fmaxf(nrm, __shfl_xor_sync(0xffffffffu, nrm, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nrm == nrm) atomicMax(reinterpret_cast<unsigned*>(out), __float_as_uint(nrm));
+        if (mx == mx) atomicMax(reinterpret_cast<unsigned*>(out + 1), __float_as_uint(mx));
+    }
+}
+// one thread per (tile, column n): writes row n of the tile's B operand
+__global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
+                                const int4* __restrict__ desc, uint32_t ntiles, float inv_scale, unsigned char* __restrict__ tiles) {
+    const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = 128
+    if (t >= ntiles) return;
+    const int4 segs = desc[2 * t], lens = desc[2 * t + 1];
+    const int slot = n >> 5, j = n & 31;
+    const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : segs.w;
+    const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : lens.w;
+    __half row[kTcK];
+#pragma unroll
+    for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
+    if (seg >= 0 && j < len) {
+        const double* src = mfcc + (off[seg] + j) * c;
+        float nrm = 0.f;
+        for (int k = 0; k < c; k++) {
+            const __half h = __float2half_rn((float)(src[k] - mu[k]));
+            row[k] = h;
+            const float v = __half2float(h);
+            nrm += v * v;
+        }
+        const float sn = nrm * inv_scale;
+        const __half hi = __float2half_rn(sn);
+        row[13] = hi;
+        row[14] = __float2half_rn(sn - __half2float(hi));
+    }
+    unsigned char* base = tiles + (size_t)t * kTcTileBytes;
+#pragma unroll
+    for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset((int)n, k)) = row[k];
+}
+// one thread per (group, row i, query m): A_i[m, :] and |a_i|^2
+__global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
+                                 const uint32_t* __restrict__ group_len, const uint64_t* __restrict__ group_off,
+                                 const uint32_t* __restrict__ qid, float scale, unsigned char* __restrict__ a_blocks,
+                                 float* __restrict__ max_norm, float* __restrict__ slot_max_na) {
+    const uint32_t g = blockIdx.x, m = threadIdx.x;  // blockDim = 128
+    const uint32_t L = group_len[g];
+    const uint32_t id = qid[g * kTcM + m];
+    unsigned char* blk = a_blocks + group_off[g];
+    float* na = reinterpret_cast<float*>(blk + (size_t)L * kTcTileBytes);
+    float mx = 0.f;
+    for (uint32_t i = 0; i < L; i++) {
+        __half row[kTcK];
+#pragma unroll
+        for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
+        float nrm = 0.f;
+        if (id != 0xFFFFFFFFu) {
+            const double* src = mfcc + (off[id] + i) * c;
+            for (int k = 0; k < c; k++) {
+                const __half h = __float2half_rn((float)(src[k] - mu[k]));
+                const float v = __half2float(h);
+                nrm += v * v;
+                row[k] = __float2half_rn(-2.f * v);  // exact
+            }
+            row[13] = __float2half_rn(scale);
+            row[14] = __float2half_rn(scale);
+        }
+        unsigned char* base = blk + (size_t)i * kTcTileBytes;
+#pragma unroll
+        for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset((int)m, k)) = row[k];
+        na[(size_t)i * kTcM + m] = nrm;
+        mx = fmaxf(mx, nrm);
+    }
+    slot_max_na[g * kTcM + m] = mx;
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((m & 31) == 0 && mx == mx) atomicMax(reinterpret_cast<unsigned*>(max_norm), __float_as_uint(mx));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the scan
+// ---------------------------------------------------------------------------------------------------------------
+struct TcParams {
+    const unsigned char* a_blocks;
+    const uint64_t* group_off;
+    const uint32_t* group_len;
+    uint32_t ngroups;
+    const unsigned char* tiles;
+    const int4* desc;
+    const uint32_t* slice_tile;  // nslices + 1
+    uint32_t nslices;
+    unsigned long long* partial;  // [nslices * 2 halves][ngroups * 128][KP]
+    uint32_t max_len;
+};
+
+__host__ __device__ __forceinline__ uint32_t tc_f2ord(float f) {
+    uint32_t b;
+#ifdef __CUDA_ARCH__
+    b = __float_as_uint(f);
+#else
+    memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// per-thread candidate list kept in shared memory as packed (ord(dist) << 32 | idx) keys, ascending; only the worst kept
+// key lives in a register for the per-pair test, so the hot loop pays two registers for the list
+template <int KP>
+__device__ __forceinline__ void tc_insert(unsigned long long* list, unsigned long long& worst, float dist, uint32_t idx) {
+    const unsigned long long key = ((unsigned long long)tc_f2ord(dist) << 32) | idx;
+    if (key < worst && dist == dist) {
+        int s = KP - 1;
+        while (s > 0 && list[(s - 1) * 256] > key) {
+            list[s * 256] = list[(s - 1) * 256];
+            s--;
+        }
+        list[s * 256] = key;
+        worst = list[(KP - 1) * 256];
+    }
+}
+
+// one DP row for the thread's two segment slots at once (independent chains, interleaved for ILP). The row state is
+// updated IN PLACE: t = min(up, diag) of the next column is taken before the current column is overwritten, so the
+// recurrence needs no register copies: per cell FADD (cost + |a|^2), FMNMX (pairwise), FMNMX (with left), FADD.
+// Columns run in groups of 4 behind one uniform guard. LAST (the query's final row) also captures D(L-1, len-1).
+template <bool LAST>
+__device__ __forceinline__ void tc_dp_rows(const float (&tm0)[32], const float (&tm1)[32], float (&d0)[32], float (&d1)[32], float na, int len0,
+                                           int len1, bool first_row, float& r0, float& r1) {
+    const float INF = __int_as_float(0x7f800000);
+    const int lenm = len0 > len1 ? len0 : len1;
+    const float corner = first_row ? 0.f : INF;  // D(i-1, -1)
+    float left0 = INF, left1 = INF;
+    float t0 = fminf(d0[0], corner), t1 = fminf(d1[0], corner);
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+        if (j0 < lenm) {
+#pragma unroll
+            for (int j = j0; j < j0 + 4; j++) {
+                float tn0 = INF, tn1 = INF;
+                if (j + 1 < 32) {
+                    tn0 = fminf(d0[j + 1], d0[j]);
+                    tn1 = fminf(d1[j + 1], d1[j]);
+                }
+                const float c0 = (tm0[j] + na) + fminf(left0, t0);
+                const float c1 = (tm1[j] + na) + fminf(left1, t1);
+                d0[j] = c0;
+                d1[j] = c1;
+                left0 = c0;
+                left1 = c1;
+                t0 = tn0;
+                t1 = tn1;
+                if (LAST) {
+                    if (j == len0 - 1) r0 = c0;
+                    if (j == len1 - 1) r1 = c1;
+                }
+            }
+        }
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // [A tiles: max_len x 4 KB][|a|^2: max_len x 512 B][B ring: 4 x 4 KB][barriers], 128-byte aligned
+    unsigned char* smem = smem_raw + ((128u - (s32(smem_raw) & 127u)) & 127u);
+    unsigned char* sA = smem;
+    float* sNa = reinterpret_cast<float*>(smem + (size_t)p.max_len * kTcTileBytes);
+    unsigned char* sB = smem + (size_t)p.max_len * (kTcTileBytes + kTcM * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcTileBytes);
+    uint64_t* a_full = bars;
+    uint64_t* b_full = bars + 1;
+    uint64_t* b_empty = b_full + kTcStages;
+    uint64_t* t_full = b_empty + kTcStages;
+    uint64_t* t_empty = t_full + kTcTmemSlots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kTcTmemSlots);
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
+    const uint32_t L = p.group_len[g];
+    const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
+    const uint32_t ntiles = t1 - t0;
+
+    if (threadIdx.x == 0) {
+        mb_init(a_full, 1);
+        for (int s = 0; s < kTcStages; s++) mb_init(&b_full[s], 1), mb_init(&b_empty[s], 1);
+        for (int s = 0; s < kTcTmemSlots; s++) mb_init(&t_full[s], 1), mb_init(&t_empty[s], 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0 && ntiles) {
+            // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------
+            const unsigned a_bytes = L * (kTcTileBytes + kTcM * 4);
+            mb_expect_tx(a_full, a_bytes);
+            const unsigned char* ablk = p.a_blocks + p.group_off[g];
+            // tiles and |a|^2 are contiguous in global memory but land in two smem regions
+            tma_g2s(sA, ablk, L * kTcTileBytes, a_full);
+            tma_g2s(sNa, ablk + (size_t)L * kTcTileBytes, L * kTcM * 4, a_full);
+            for (uint32_t n = 0; n < ntiles && n < (uint32_t)kTcStages; n++) {
+                mb_expect_tx(&b_full[n], kTcTileBytes);
+                tma_g2s(sB + n * kTcTileBytes, p.tiles + (size_t)(t0 + n) * kTcTileBytes, kTcTileBytes, &b_full[n]);
+            }
+            mb_wait(a_full, 0);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);  // f16 x f16 -> f32, K-major
+            uint32_t cnt = 0;
+            for (uint32_t n = 0; n < ntiles; n++) {
+                const int stage = n % kTcStages;
+                mb_wait(&b_full[stage], (n / kTcStages) & 1);
+                const uint64_t bdesc = tc_smem_desc(sB + stage * kTcTileBytes);
+                for (uint32_t i = 0; i < L; i++, cnt++) {
+                    const int slot = cnt % kTcTmemSlots;
+                    if (cnt >= (uint32_t)kTcTmemSlots) mb_wait(&t_empty[slot], ((cnt / kTcTmemSlots) - 1) & 1);
+                    tc_fence_after();
+                    tc_mma_f16(tmem_base + slot * kTcN, tc_smem_desc(sA + (size_t)i * kTcTileBytes), bdesc, idesc);
+                    tc_commit(&t_full[slot]);
+                }
+                tc_commit(&b_empty[stage]);
+                if (n + kTcStages < ntiles) {  // refill this stage once its MMAs have completed
+                    mb_wait(&b_empty[stage], (n / kTcStages) & 1);
+                    mb_expect_tx(&b_full[stage], kTcTileBytes);
+                    tma_g2s(sB + stage * kTcTileBytes, p.tiles + (size_t)(t0 + n + kTcStages) * kTcTileBytes, kTcTileBytes, &b_full[stage]);
+                }
+            }
+        }
+    } else {
+        // ---- DP warps ---------------------------------------------------------------------------------------------------
+        const int q = warp & 3, h = warp >> 2;
+        const int m = q * 32 + lane;
+        const float INF = __int_as_float(0x7f800000);
+        unsigned long long* list = topk + threadIdx.x;  // [KP][256] keys, this thread's column
+#pragma unroll
+        for (int s = 0; s < KP; s++) list[s * 256] = 0xFFFFFFFFFFFFFFFFull;
+        unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
+        if (ntiles) mb_wait(a_full, 0);  // |a|^2 block
+        uint32_t cnt = 0;
+        for (uint32_t n = 0; n < ntiles; n++) {
+            const int4 segs = __ldg(&p.desc[2 * (t0 + n)]), lens = __ldg(&p.desc[2 * (t0 + n) + 1]);
+            const int seg0 = h ? segs.z : segs.x, seg1 = h ? segs.w : segs.y;
+            const int len0 = h ? lens.z : lens.x, len1 = h ? lens.w : lens.y;
+            float d0[32], d1[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) d0[j] = INF, d1[j] = INF;
+            float r0 = INF, r1 = INF;
+            for (uint32_t i = 0; i < L; i++, cnt++) {
+                const int slot = cnt % kTcTmemSlots;
+                mb_wait(&t_full[slot], (cnt / kTcTmemSlots) & 1);
+                tc_fence_after();
+                float tm0[32], tm1[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * kTcN + h * 64;
+                const float na = sNa[i * kTcM + m];
+                tc_ld32(taddr, tm0);
+                tc_ld32(taddr + 32, tm1);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mb_arrive(&t_empty[slot]);  // the costs are in registers: hand the TMEM slot back
+                if (i + 1 == L) tc_dp_rows<true>(tm0, tm1, d0, d1, na, len0, len1, i == 0, r0, r1);
+                else tc_dp_rows<false>(tm0, tm1, d0, d1, na, len0, len1, i == 0, r0, r1);
+            }
+            // results: D(L-1, len-1) / (L + len)
+            if (seg0 >= 0) tc_insert<KP>(list, worst, r0 * (1.0f / (float)(L + (uint32_t)len0)), (uint32_t)seg0);
+            if (seg1 >= 0) tc_insert<KP>(list, worst, r1 * (1.0f / (float)(L + (uint32_t)len1)), (uint32_t)seg1);
+        }
+        unsigned long long* out = p.partial + (((size_t)slice * 2 + h) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
+#pragma unroll
+        for (int s = 0; s < KP; s++) out[s] = list[s * 256];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// per query slot: merge the (slice, half) candidate lists by packed (ord(dist), idx) key
+template <int KP>
+__global__ void k_tc_merge(const unsigned long long* __restrict__ partial, uint32_t nlists, uint32_t nslots, uint32_t* __restrict__ cand_idx,
+                           float* __restrict__ cand_adist) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    unsigned long long best[KP];
+#pragma unroll
+    for (int s = 0; s < KP; s++) best[s] = 0xFFFFFFFFFFFFFFFFull;
+    for (uint32_t l = 0; l < nlists; l++) {
+        const unsigned long long* src = partial + ((size_t)l * nslots + slot) * KP;
+#pragma unroll
+        for (int s = 0; s < KP; s++) {
+            const unsigned long long key = src[s];
+            if (key < best[KP - 1]) {
+                best[KP - 1] = key;
+#pragma unroll
+                for (int s2 = KP - 1; s2 > 0; s2--)
+                    if (best[s2] < best[s2 - 1]) {
+                        const unsigned long long tmp = best[s2];
+                        best[s2] = best[s2 - 1];
+                        best[s2 - 1] = tmp;
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < KP; s++) {
+        const bool empty = best[s] == 0xFFFFFFFFFFFFFFFFull;
+        cand_idx[(size_t)slot * KP + s] = empty ? 0xFFFFFFFFu : (uint32_t)best[s];
+        const uint32_t o = (uint32_t)(best[s] >> 32);
+        const uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        cand_adist[(size_t)slot * KP + s] = empty ? __int_as_float(0x7f800000) : __uint_as_float(b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+int dtw_tc_dict_build(ss_dict* d) {
+    ss_ctx* ctx = d->ctx;
+    d->tc_ready = false;
+    if (d->max_len > (uint32_t)kTcMaxLen || d->total_frames == 0) return SS_OK;  // dtw.cu's fp32 scan handles these
+    // segments sorted by length (longest first) so that the 4 slots of a tile, and hence both column halves, carry equal work
+    std::vector<uint32_t> order;
+    order.reserve(d->nseg);
+    for (size_t s = 0; s < d->nseg; s++)
+        if (d->h_off[s + 1] > d->h_off[s]) order.push_back((uint32_t)s);
+    auto len_of = [&](uint32_t s) { return (int)(d->h_off[s + 1] - d->h_off[s]); };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
+    const uint32_t ntiles = (uint32_t)((order.size() + kTcSlots - 1) / kTcSlots);
+    std::vector<int4> desc(2 * (size_t)ntiles);
+    d->h_tc_tile_frames.assign(ntiles, 0);
+    for (uint32_t t = 0; t < ntiles; t++) {
+        int sg[4], ln[4];
+        for (int s = 0; s < 4; s++) {
+            const size_t o = (size_t)t * 4 + s;
+            sg[s] = o < order.size() ? (int)order[o] : -1;
+            ln[s] = o < order.size() ? len_of(order[o]) : 0;
+            d->h_tc_tile_frames[t] += (uint32_t)ln[s];
+        }
+        // slots 0,1 feed column half 0 and slots 2,3 half 1: interleave so both halves get (longer, shorter) pairs
+        desc[2 * t] = make_int4(sg[0], sg[3], sg[1], sg[2]);
+        desc[2 * t + 1] = make_int4(ln[0], ln[3], ln[1], ln[2]);
+    }
+    d->tc_ntiles = ntiles;
+    SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
+    SS_CUDA(ctx, d->d_mu.reserve(16));
+    SS_CUDA(ctx, cudaMemsetAsync(d->d_mu.p, 0, 16 * sizeof(double), ctx->stream));
+    k_tc_mean<<<1, 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_mu.p);
+    SS_LAUNCHED(ctx);
+    DevBuf<float>& d_mx = d->d_tc_max_norm;
+    SS_CUDA(ctx, d_mx.reserve(2));
+    SS_CUDA(ctx, cudaMemsetAsync(d_mx.p, 0, 2 * sizeof(float), ctx->stream));
+    k_tc_dict_maxnorm<<<ceil_div((long long)d->total_frames, 256), 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_mu.p, d_mx.p);
+    SS_LAUNCHED(ctx);
+    float mx[2] = {0, 0};
+    SS_CUDA(ctx, cudaMemcpyAsync(mx, d_mx.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!(mx[1] < 3.0e4f) || !(mx[0] < 1.0e9f)) return SS_OK;  // values outside a safe fp16 range: keep the fp32 scan
+    float scale = 1.f;
+    while (mx[0] / scale > 16384.f) scale *= 2.f;  // |b|^2 / s must fit fp16 comfortably; s <= 2^16 is exact in fp16
+    if (scale > 32768.f) return SS_OK;
+    d->tc_nb_scale = scale;
+    SS_CUDA(ctx, d->d_tc_tiles.reserve((size_t)ntiles * kTcTileBytes / 2));
+    k_tc_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_tc_desc.p, ntiles, 1.0f / scale,
+                                                     reinterpret_cast<unsigned char*>(d->d_tc_tiles.p));
+    SS_LAUNCHED(ctx);
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    d->tc_ready = true;
+    return SS_OK;
+}
+
+static int tc_queries_build(ss_dict* d, ss_queries* q) {
+    ss_ctx* ctx = q->ctx;
+    if (q->tc_built) return SS_OK;
+    std::vector<uint32_t> order;
+    order.reserve(q->nq);
+    for (size_t i = 0; i < q->nq; i++)
+        if (q->h_off[i + 1] > q->h_off[i]) order.push_back((uint32_t)i);
+    auto len_of = [&](uint32_t i) { return (uint32_t)(q->h_off[i + 1] - q->h_off[i]); };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
+    std::vector<uint32_t> glen, gqid;
+    std::vector<uint64_t> goff;
+    uint64_t bytes = 0;
+    size_t pos = 0;
+    while (pos < order.size()) {
+        const uint32_t L = len_of(order[pos]);
+        size_t end = pos;
+        while (end < order.size() && len_of(order[end]) == L) end++;
+        for (size_t b = pos; b < end; b += kTcM) {
+            glen.push_back(L);
+            goff.push_back(bytes);
+            for (size_t l = 0; l < (size_t)kTcM; l++) gqid.push_back(b + l < end ? order[b + l] : 0xFFFFFFFFu);
+            bytes += (uint64_t)L * (kTcTileBytes + kTcM * 4);
+        }
+        pos = end;
+    }
+    q->tc_ngroups = (uint32_t)glen.size();
+    q->h_tc_group_len = glen;
+    SS_TRY(upload(ctx, q->d_tc_group_len, glen.data(), glen.size()));
+    SS_TRY(upload(ctx, q->d_tc_group_off, goff.data(), goff.size()));
+    SS_TRY(upload(ctx, q->d_tc_qid, gqid.data(), gqid.size()));
+    SS_CUDA(ctx, q->d_tc_a.reserve(std::max<uint64_t>(bytes, 16)));
+    SS_CUDA(ctx, q->d_tc_slot_max_na.reserve(std::max<size_t>((size_t)q->tc_ngroups * kTcM, 1)));
+    SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
+    SS_CUDA(ctx, q->d_tc_max_norm.reserve(1));
+    SS_CUDA(ctx, cudaMemsetAsync(q->d_tc_max_norm.p, 0, sizeof(float), ctx->stream));
+    if (q->tc_ngroups) {
+        k_tc_query_tiles<<<q->tc_ngroups, kTcM, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, d->d_mu.p, q->d_tc_group_len.p,
+                                                                 q->d_tc_group_off.p, q->d_tc_qid.p, d->tc_nb_scale, q->d_tc_a.p,
+                                                                 q->d_tc_max_norm.p, q->d_tc_slot_max_na.p);
+        SS_LAUNCHED(ctx);
+    }
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    q->tc_built = true;
+    return SS_OK;
+}
+
+template <int KP>
+static int tc_launch(ss_ctx* ctx, const TcParams& p, uint32_t grid, size_t smem, uint32_t nlists, uint32_t nslots, ss_dict* d) {
+    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
+    k_dtw_scan_tc<KP><<<grid, kTcThreads, smem, ctx->stream>>>(p);
+    SS_LAUNCHED(ctx);
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
+    d->scan_timed = true;
+    k_tc_merge<KP><<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_tc_partial.p, nlists, nslots, d->d_cand_idx.p, d->d_cand_adist.p);
+    SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+
+int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used) {
+    ss_ctx* ctx = d->ctx;
+    *used = false;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SS_DTW_TC");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
+    SS_TRY(tc_queries_build(d, q));
+    if (!q->tc_ngroups) return SS_OK;
+    const int kp = k <= 2 ? 8 : 16;  // fp16 products are noisier than the fp32 scan: keep a longer candidate list
+    const uint32_t nslots = q->tc_ngroups * kTcM;
+    d->last_work = d->total_frames * q->total_frames;
+    d->last_uncertified = 0;
+    // slices: contiguous tile ranges balanced by frames; ~2 CTAs per SM in flight order (1 resident per SM)
+    static int waves = 0;
+    if (!waves) {
+        const char* e = getenv("SS_DTW_TC_WAVES");
+        waves = e ? std::max(1, atoi(e)) : 4;
+    }
+    uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->tc_ntiles, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups));
+    std::vector<uint32_t>& st = d->h_slice_tile;
+    st.clear();
+    st.push_back(0);
+    {
+        uint64_t total = 0, acc = 0;
+        for (uint32_t f : d->h_tc_tile_frames) total += f;
+        const uint64_t per = (total + nslices - 1) / nslices;
+        for (uint32_t t = 0; t < d->tc_ntiles; t++) {
+            if (t > 0 && st.size() < nslices && acc >= (uint64_t)st.size() * per) st.push_back(t);
+            acc += d->h_tc_tile_frames[t];
+        }
+    }
+    st.push_back(d->tc_ntiles);
+    nslices = (uint32_t)st.size() - 1;
+    SS_TRY(upload(ctx, d->d_slice_tile, st.data(), st.size()));
+    const uint32_t nlists = nslices * 2;
+    SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nlists * nslots * kp));
+    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
+    SS_CUDA(ctx, d->d_cand_adist.reserve((size_t)nslots * kp));
+    if (!d->ev_scan0) {
+        SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
+        SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
+    }
+    TcParams p;
+    p.a_blocks = q->d_tc_a.p;
+    p.group_off = q->d_tc_group_off.p;
+    p.group_len = q->d_tc_group_len.p;
+    p.ngroups = q->tc_ngroups;
+    p.tiles = reinterpret_cast<const unsigned char*>(d->d_tc_tiles.p);
+    p.desc = d->d_tc_desc.p;
+    p.slice_tile = d->d_slice_tile.p;
+    p.nslices = nslices;
+    p.partial = d->d_tc_partial.p;
+    p.max_len = q->max_len;
+    const size_t smem = (size_t)q->max_len * (kTcTileBytes + kTcM * 4) + kTcStages * kTcTileBytes + 32 * 8 + (size_t)kp * 256 * 8 + 1024;
+    const uint32_t grid = q->tc_ngroups * nslices;
+    if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, grid, smem, nlists, nslots, d));
+    else SS_TRY(tc_launch<16>(ctx, p, grid, smem, nlists, nslots, d));
+    // certification bound for fp16 inputs: see k_dtw_finalize (bound_mode 1)
+    SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
+    SS_TRY(dtw_rescore_finalize(d, q, k, kp, nslots, q->d_tc_qid.p, 0.0, q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 1,
+                                q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
+    *used = true;
+    return SS_OK;
+}
+
+}  // namespace ss

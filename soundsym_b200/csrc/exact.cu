@@ -263,7 +263,8 @@ __global__ void k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* 
 
 __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
                                const double* __restrict__ exact, const uint32_t* __restrict__ group_qid, uint32_t nslots, int kp,
-                               int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb,
+                               int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb, double eps,
+                               const float* __restrict__ slot_max_na, int bound_mode, uint8_t* __restrict__ uncert_flag,
                                uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, unsigned long long* __restrict__ counters) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= nslots) return;
@@ -290,19 +291,38 @@ __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const floa
         out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
         out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
     }
-    // certification: every pair outside the candidate list has scan distance >= the list's worst entry; the scan's
-    // absolute error on a normalised distance is bounded by E, so such a pair's exact distance is > worst - E.
+    // certification: every pair X outside the candidate list has scan distance >= the list's worst entry w, and
+    //   bound_mode 0 (fp32 scan):  |scan - exact| <= E = eps (max|a|^2 + max|b|^2)            => exact(X) >= w - E
+    //   bound_mode 1 (fp16 scan):  the scan is the DTW of the fp16-ROUNDED frames (products of fp16 values are exact in
+    //     fp32), and for every cell sqrt(c) >= sqrt(c~) - delta with delta = |a - a~| + |b - b~| <= 2^-11 (|a| + |b|)
+    //     (triangle inequality). Summing along the exact optimum and using Cauchy-Schwarz over its <= Lq+Ld cells:
+    //                              exact(X) >= w - 2 delta sqrt(w) - E32,   E32 = fp32 accumulation slack
+    // If that lower bound exceeds the exact k-th distance found among the candidates, the reported top-k is THE f64 top-k.
     const float worst = cand_adist[(size_t)slot * kp + kp - 1];
+    bool uncertified = false;
     if (worst < __int_as_float(0x7f800000)) {
-        const double E = 4e-6 * ((double)max_na[0] + (double)max_nb[0]);
         const double kth = n >= k ? dv[k - 1] : kInf;
-        if (!((double)worst - E > kth)) atomicAdd(&counters[0], 1ull);
+        const double na = slot_max_na ? (double)slot_max_na[slot] : (double)max_na[0];
+        const double nb = (double)max_nb[0];
+        double lower;
+        if (bound_mode == 0) {
+            lower = (double)worst - eps * (na + nb);
+        } else {
+            const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
+            const double w = worst > 0.f ? (double)worst : 0.0;
+            lower = w - 2.0 * delta * sqrt(w) - 8e-6 * (na + nb);
+        }
+        uncertified = !(lower > kth);
+        if (uncertified) atomicAdd(&counters[0], 1ull);
     }
+    if (uncert_flag) uncert_flag[qid] = uncertified ? 1 : 0;
 }
 
-int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, uint32_t* d_out_idx, double* d_out_dist) {
+int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, double eps,
+                         const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
+                         bool fill, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
-    if (q->nq) {
+    if (q->nq && fill) {
         k_fill_result<<<ceil_div((long long)q->nq * k, 256), 256, 0, ctx->stream>>>(d_out_idx, d_out_dist, q->nq * (size_t)k,
                                                                                    0xFFFFFFFFu, kInf);
         SS_LAUNCHED(ctx);
@@ -319,13 +339,14 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     for (uint32_t pb = 0; pb < npairs; pb += batch) {
         const uint32_t pe = std::min<uint32_t>(npairs, pb + batch);
         k_dtw_rescore<<<ceil_div(pe - pb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
-                                                                     q->d_group_qid.p, d->d_cand_idx.p, pb, pe, kp,
+                                                                     d_slot_qid, d->d_cand_idx.p, pb, pe, kp,
                                                                      d->d_rescore_rows.p, batch, d->d_cand_exact.p);
         SS_LAUNCHED(ctx);
     }
     k_dtw_finalize<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_idx.p, d->d_cand_adist.p, d->d_cand_exact.p,
-                                                                  q->d_group_qid.p, nslots, kp, k, d->index_base, q->d_max_norm.p,
-                                                                  d->d_max_norm.p, d_out_idx, d_out_dist, d->d_counters.p);
+                                                                  d_slot_qid, nslots, kp, k, d->index_base, d_max_na, d_max_nb, eps,
+                                                                  d_slot_max_na, bound_mode, d_uncert_flag, d_out_idx, d_out_dist,
+                                                                  d->d_counters.p);
     SS_LAUNCHED(ctx);
     return SS_OK;
 }

@@ -56,8 +56,19 @@ struct ss_dict {
     ss::DevBuf<unsigned long long> d_counters;  // [0] uncertified
     std::vector<uint32_t> h_slice_tile;
     uint64_t last_work = 0, last_uncertified = 0;
+    uint64_t last_tc_fallback = 0;  // queries of the last match that the tensor-core scan handed to the fp32 scan
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;  // around the dominant kernel of the last match
     bool scan_timed = false;
+    // tensor-core scan (dtw_tc.cu): fp16 UMMA tiles of 4 segment slots x 32 columns, segments sorted by length
+    bool tc_ready = false;
+    uint32_t tc_ntiles = 0;
+    float tc_nb_scale = 1.f;                 // power of two s: the |b|^2 columns hold |b|^2 / s
+    ss::DevBuf<double> d_mu;                 // per-coefficient mean of the dictionary frames (both sides are centred on it)
+    ss::DevBuf<uint16_t> d_tc_tiles;         // ntiles x 4 KB
+    ss::DevBuf<int4> d_tc_desc;              // ntiles x 2: {seg[4]}, {len[4]}
+    std::vector<uint32_t> h_tc_tile_frames;  // sum of the 4 lengths (slice balancing)
+    ss::DevBuf<unsigned long long> d_tc_partial;
+    ss::DevBuf<float> d_tc_max_norm;         // [0] = max |fp16(b - mu)|^2
     // host-buffer entry point (ss_dict_match): query batch + result buffers reused across calls (grow-only)
     struct ss_queries* scratch_q = nullptr;
     ss::DevBuf<uint32_t> d_res_idx;
@@ -85,6 +96,16 @@ struct ss_queries {
     ss::DevBuf<double> d_lane64;                                     // [row*c + e][32] f64 (cosine-ref), built on first use
     bool cos_built = false;
     bool lane_built = false;
+    // tensor-core scan: groups of 128 equal-length queries
+    bool tc_built = false;
+    uint32_t tc_ngroups = 0;
+    std::vector<uint32_t> h_tc_group_len;
+    ss::DevBuf<uint32_t> d_tc_group_len, d_tc_qid;  // qid: ngroups x 128
+    ss::DevBuf<uint64_t> d_tc_group_off;            // byte offset of each group's [L x 4 KB tiles][L x 128 floats |a|^2] block
+    ss::DevBuf<unsigned char> d_tc_a;
+    ss::DevBuf<float> d_tc_max_norm;                // [0] = max |fp16(a - mu)|^2
+    ss::DevBuf<float> d_tc_slot_max_na;             // per query slot: max over its rows of |fp16(a - mu)|^2
+    ss::DevBuf<uint8_t> d_uncert_flag;              // per query: 1 if the tensor-core scan could not certify its top-k
 };
 
 inline ss_dict::~ss_dict() {
@@ -95,7 +116,8 @@ inline ss_dict::~ss_dict() {
 
 namespace ss {
 int dtw_dict_build(ss_dict* d);       // builds the fp32 stream + strip / tile tables (dtw.cu)
-int dtw_queries_build(ss_queries* q); // builds the lane layout (dtw.cu)
+int dtw_tc_dict_build(ss_dict* d);    // builds the fp16 UMMA tiles (dtw_tc.cu)
+int dtw_queries_build(ss_queries* q, const std::vector<uint32_t>* subset = nullptr); // builds the lane layout (dtw.cu)
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist);
 int cosine_dict_build(ss_dict* d);    // per-segment norms (cosine.cu)
 int cosine_queries_build(ss_queries* q);
