@@ -290,6 +290,7 @@ def main():
         ms_step, _ = timed(step_resident, args.steps)
         launches = ctx.launches - launches0
         scan_ms = float(ctx.lib.ss_dict_last_scan_ms(shard.h))
+        tc_fallback = shard.last_tc_fallback
         clocks = sampler.stop() if rank == 0 else None
         uncert = shard.last_uncertified
         for _ in range(2):
@@ -317,10 +318,12 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg = algorithmic_bytes(doff, qoff, s0, s1)
         achieved = alg / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
+        scan_kernel = "k_dtw_scan_tc (tcgen05 fp16 cost + CUDA-core DP)" if os.environ.get("SS_DTW_TC", "1") != "0" else "k_dtw_scan (fp32)"
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dtw_scan_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("tc" if "tc" in scan_kernel else "fp32", {}).get("dram_bytes_per_launch") if world == 1 else None
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import oracle as O
@@ -332,7 +335,7 @@ def main():
         line = {
             "metric": "dtw_cell_updates_per_s", "value": total_cells / (ms_step * 1e-3), "unit": "cells/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 scan + f64 refine", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core cost + f32 DP scan, f64 refine", "data": "synthetic",
             "config": {"workload": "synthetic 100k-segment dictionary x 10k queries, C=13, L~U{4..32}, DTW top-1 (config 4)",
                        "nd": args.nd, "nq": args.nq, "ncoeffs": C, "k": K, "parallelism": "dictionary sharded x%d, NCCL all-gather top-k merge" % world,
                        "l2": "flushed: a 256 MB buffer is overwritten at the start of every timed step (dictionary resident: %.0f MB fp32 stream + %.0f MB f64)" % (
@@ -343,14 +346,21 @@ def main():
                     "queries_per_s": nq / (ms_e2e * 1e-3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_dtw_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": alg,
-                         "note": "effective bandwidth of the pairwise-streaming model (SURVEY.md §8d); the kernel is FP32-issue bound, "
-                                 "compulsory DRAM traffic is ~0.1 GB",
+                         "note": "EFFECTIVE bandwidth of the pairwise-streaming model of SURVEY.md §8d (bytes the CPU path streams per pair); "
+                                 "operands stay on chip (one dictionary tile serves 128 queries), so compulsory DRAM traffic is ~0.1 GB and "
+                                 "frac can exceed 1. The kernel is bound by CUDA-core issue of the DP recurrence (DESIGN.md §3.1), not by HBM "
+                                 "or the tensor pipe",
+                         "issue_bound": {"cells_per_clk_per_sm": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) / 148.0
+                                         / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) if scan_ms > 0 else None,
+                                         "ceiling_cells_per_clk_per_sm": 32.0,
+                                         "ceiling_note": "4 issue slots per cell (FADD, FMNMX3, FADD, MOV) on 128 lanes / clk / SM"},
                          "cells_per_s_kernel": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) if scan_ms > 0 else None},
             "cpu_baseline": cpu,
             "uncertified_queries": int(uncert),
+            "tc_fallback_queries": int(tc_fallback),
             "oracle_probe_ok": ok,
         }
         print(json.dumps(line), flush=True)

@@ -118,19 +118,26 @@ __device__ __forceinline__ float tc_min3(float a, float b, float c) {
 // ---------------------------------------------------------------------------------------------------------------
 // layout builders
 // ---------------------------------------------------------------------------------------------------------------
-// per-coefficient sums of the dictionary frames -> mu (deterministic: one block, fixed order)
-__global__ void k_tc_mean(const double* __restrict__ mfcc, size_t frames, int c, double* __restrict__ mu) {
+// per-coefficient mean of the dictionary frames -> mu, in two deterministic stages (fixed summation order)
+__global__ void k_tc_mean_partial(const double* __restrict__ mfcc, size_t frames, int c, double* __restrict__ partial) {
     __shared__ double s[256];
     const int col = threadIdx.x % 16, rl = threadIdx.x / 16;
     double acc = 0.0;
     if (col < c)
-        for (size_t r = rl; r < frames; r += 16) acc += mfcc[r * c + col];
+        for (size_t r = (size_t)blockIdx.x * 16 + rl; r < frames; r += (size_t)gridDim.x * 16) acc += mfcc[r * c + col];
     s[threadIdx.x] = acc;
     __syncthreads();
-    if (rl == 0 && col < c) {
+    if (rl == 0) {
         for (int j = 1; j < 16; j++) acc += s[j * 16 + col];
-        mu[col] = frames ? acc / (double)frames : 0.0;
+        partial[(size_t)blockIdx.x * 16 + col] = acc;
     }
+}
+__global__ void k_tc_mean_final(const double* __restrict__ partial, int nblocks, size_t frames, int c, double* __restrict__ mu) {
+    const int col = threadIdx.x;
+    if (col >= c) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; b++) acc += partial[(size_t)b * 16 + col];
+    mu[col] = frames ? acc / (double)frames : 0.0;
 }
 // max over frames of |fp16(b - mu)|^2 (to pick the power-of-two scale of the norm columns) and max |fp16(b - mu)|
 __global__ void k_tc_dict_maxnorm(const double* __restrict__ mfcc, size_t frames, int c, const double* __restrict__ mu,
@@ -495,8 +502,14 @@ int dtw_tc_dict_build(ss_dict* d) {
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
     SS_CUDA(ctx, d->d_mu.reserve(16));
     SS_CUDA(ctx, cudaMemsetAsync(d->d_mu.p, 0, 16 * sizeof(double), ctx->stream));
-    k_tc_mean<<<1, 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_mu.p);
-    SS_LAUNCHED(ctx);
+    {
+        const int nb = (int)std::min<size_t>(std::max<size_t>(d->total_frames / 256, 1), 512);
+        SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)nb * 16));  // scratch
+        k_tc_mean_partial<<<nb, 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_rescore_rows.p);
+        SS_LAUNCHED(ctx);
+        k_tc_mean_final<<<1, 32, 0, ctx->stream>>>(d->d_rescore_rows.p, nb, d->total_frames, d->c, d->d_mu.p);
+        SS_LAUNCHED(ctx);
+    }
     DevBuf<float>& d_mx = d->d_tc_max_norm;
     SS_CUDA(ctx, d_mx.reserve(2));
     SS_CUDA(ctx, cudaMemsetAsync(d_mx.p, 0, 2 * sizeof(float), ctx->stream));
