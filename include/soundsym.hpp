@@ -361,6 +361,25 @@ class Partitioner {
     /// Partitioner::train (src/lib.rs:101-107). EM training is not on the data-parallel path (the reference's is randomly
     /// seeded, so parity is only defined GIVEN a model): the caller supplies one.
     void train(GaussianMixtureModel m) { model = std::move(m); }
+    /// the same on the GPU (ss_gmm_train): 26 components, 5 EM rounds, Regularized(0.1); seeded instead of thread_rng,
+    /// retried with the next seed when a component collapses (the reference's `while let Err` loop, src/lib.rs:50-52)
+    void train(uint64_t seed = 0) {
+        Context& ctx = sound->context();
+        GaussianMixtureModel m;
+        m.ncomp = (int)NCLUSTERS;
+        m.ncoeffs = (int)NCOEFFS;
+        m.means.resize(NCLUSTERS * NCOEFFS);
+        m.covs.resize(NCLUSTERS * NCOEFFS * NCOEFFS);
+        m.weights.resize(NCLUSTERS);
+        int rc = SS_OK;
+        for (int attempt = 0; attempt < 64; attempt++) {
+            rc = ss_gmm_train(ctx.get(), sound->mfccs().data(), sound->num_frames(), m.ncoeffs, m.ncomp, 5, 0.1, seed + attempt,
+                              m.means.data(), m.covs.data(), m.weights.data());
+            if (rc != SS_ERR_INVALID) break;
+        }
+        ctx.check(rc);
+        model = std::move(m);
+    }
 
     /// Partitioner::partition_other (src/lib.rs:112-144): segment lengths in samples
     std::vector<size_t> partition_other(const Sound& other) const {

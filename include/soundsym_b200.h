@@ -105,6 +105,14 @@ int ss_mfcc_dev(ss_ctx* ctx, const double* d_samples, size_t n, double sample_ra
  */
 int ss_symbols(ss_ctx* ctx, const double* mfcc, size_t frames, const ss_gmm* model, uint8_t* out_symbols,
                double* out_posteriors);
+/* ss_gmm_train   train_model (src/lib.rs:44-54): Standardizer on the input, then `iters` EM rounds for `ncomp`
+ *                full-covariance Gaussians with CovOption::Regularized(reg) (reference: ncomp 26, iters 5, reg 0.1).
+ *                Initial means are `ncomp` distinct rows drawn with a seeded mt19937_64 (the reference draws from
+ *                thread_rng, so its model differs from run to run; parity is defined GIVEN a model). On a collapsed
+ *                component / singular covariance returns SS_ERR_INVALID — retry with another seed, as the reference's
+ *                `while let Err` loop does. Outputs: means ncomp x ncoeffs, covs ncomp x ncoeffs x ncoeffs, weights ncomp. */
+int ss_gmm_train(ss_ctx* ctx, const double* mfcc, size_t frames, int ncoeffs, int ncomp, int iters, double reg, uint64_t seed,
+                 double* out_means, double* out_covs, double* out_weights);
 int ss_vote_split(ss_ctx* ctx, const uint8_t* symbols, size_t n, int depth, int threshold, uint32_t* out_votes,
                   uint64_t* out_seg_lens, size_t* out_nseg);
 int ss_partition(ss_ctx* ctx, const double* mfcc, size_t frames, const ss_gmm* model, int depth, int threshold,

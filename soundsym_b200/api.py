@@ -114,6 +114,22 @@ class Context:
         self.check(self.lib.ss_symbols(self.h, _ptr(mfcc), mfcc.shape[0], C.byref(g) if g else None, _ptr(out), _ptr(post)))
         return (out, post) if want_posteriors else out
 
+    def gmm_train(self, mfcc, ncomp=NCLUSTERS, iters=5, reg=0.1, seed=0):
+        """train_model (src/lib.rs:44-54) on the GPU; retries with seed+1, ... like the reference's `while let Err` loop."""
+        mfcc = np.ascontiguousarray(mfcc, dtype=np.float64)
+        c = mfcc.shape[1]
+        means, covs, weights = np.empty((ncomp, c)), np.empty((ncomp, c, c)), np.empty(ncomp)
+        err = None
+        for attempt in range(64):
+            rc = self.lib.ss_gmm_train(self.h, _ptr(mfcc), mfcc.shape[0], c, int(ncomp), int(iters), float(reg), int(seed) + attempt,
+                                       _ptr(means), _ptr(covs), _ptr(weights))
+            if rc == 0:
+                return means, covs, weights
+            err = SoundsymError(rc, self.lib.ss_last_error(self.h).decode())
+            if rc != _lib.SS_ERR_INVALID or "EM failed" not in err.message:
+                break
+        raise err
+
     def vote_split(self, symbols, depth, threshold):
         symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
         n = symbols.shape[0]
@@ -491,10 +507,11 @@ class Partitioner:
         self.threshold = int(threshold)
         return self
 
-    def train(self, model):
-        """Partitioner::train (src/lib.rs:101-107). EM training is not on the data-parallel path (SURVEY.md §8f-1:
-        the reference's is randomly seeded, so parity is only defined GIVEN a model); the caller supplies one."""
-        self.model = model
+    def train(self, model=None, seed=0):
+        """Partitioner::train (src/lib.rs:101-107): 26 full-covariance Gaussians, 5 EM rounds, Regularized(0.1), on the
+        GPU (ss_gmm_train). The reference seeds its means from thread_rng, so its model differs from run to run; here
+        the draw is seeded. A ready model (means, covs, weights) may be supplied instead."""
+        self.model = model if model is not None else self._ctx.gmm_train(self.sound.mfcc_arrays(), NCLUSTERS, 5, 0.1, seed)
 
     def partition_other(self, sound):
         """src/lib.rs:112-144: segment lengths in samples; error "Must first train model" without a model."""

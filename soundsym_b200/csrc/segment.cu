@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <random>
 
 #include "sound.cuh"
 
@@ -427,6 +428,100 @@ static int symbols_dev(ss_ctx* ctx, SegState* st, const double* d_mfcc, size_t f
     return SS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GMM training (train_model, src/lib.rs:44-54; EM of rusty-machine 0.5.4 [RECALL], restated in the oracle's orc_gmm_train)
+// ---------------------------------------------------------------------------------------------------------------
+// weighted moments of one component in two deterministic stages. Block (b, j) walks rows b, b+gridDim.x, ... in tiles of
+// 32 staged in shared memory; thread t < c*c owns covariance element (t / c, t % c), threads c*c .. c*c+c-1 own the
+// weighted sums of z, thread c*c+c owns the weight sum.  mode 0: w = post[r][j], centre = 0 (first pass: sums for the
+// means); mode 1: w = post[r][j], centre = means[j] (second pass: covariance); mode 2: w = 1, centre = centre0 (initial
+// data covariance).
+__global__ void __launch_bounds__(256)
+k_gmm_moments(const double* __restrict__ z, size_t rows, int c, int ncomp, const double* __restrict__ post, const double* __restrict__ centre,
+              int mode, double* __restrict__ partial) {
+    __shared__ double sz[32][SS_MAX_NCOEFFS];
+    __shared__ double sw[32];
+    const int j = blockIdx.y, t = threadIdx.x;
+    const int nout = c * c + c + 1;
+    const int a = t / c, b2 = t % c;
+    double mu_a = 0.0, mu_b = 0.0;
+    if (mode != 0 && t < c * c) {
+        const double* mu = centre + (mode == 1 ? (size_t)j * c : 0);
+        mu_a = mu[a];
+        mu_b = mu[b2];
+    }
+    double acc = 0.0;
+    for (size_t r0 = (size_t)blockIdx.x * 32; r0 < rows; r0 += (size_t)gridDim.x * 32) {
+        __syncthreads();
+        for (int i = t; i < 32 * c; i += blockDim.x) {
+            const size_t r = r0 + i / c;
+            sz[i / c][i % c] = r < rows ? z[r * c + i % c] : 0.0;
+        }
+        if (t < 32) {
+            const size_t r = r0 + t;
+            sw[t] = r < rows ? (mode == 2 ? 1.0 : post[r * ncomp + j]) : 0.0;
+        }
+        __syncthreads();
+        if (t < c * c) {
+            for (int i = 0; i < 32; i++) acc += ((sz[i][a] - mu_a) * sw[i]) * (sz[i][b2] - mu_b);
+        } else if (t < c * c + c) {
+            const int k = t - c * c;
+            for (int i = 0; i < 32; i++) acc += sw[i] * sz[i][k];
+        } else if (t == c * c + c) {
+            for (int i = 0; i < 32; i++) acc += sw[i];
+        }
+    }
+    if (t < nout) partial[((size_t)j * gridDim.x + blockIdx.x) * nout + t] = acc;
+}
+// sums the per-block partials in block order -> out[j][nout]
+__global__ void k_gmm_moments_final(const double* __restrict__ partial, int nblocks, int nout, double* __restrict__ out) {
+    const int j = blockIdx.x, t = threadIdx.x;
+    if (t >= nout) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; b++) acc += partial[((size_t)j * nblocks + b) * nout + t];
+    out[(size_t)j * nout + t] = acc;
+}
+// M-step, part 1: weights and means from the first-pass moments
+__global__ void k_gmm_update_means(const double* __restrict__ mom, int c, int ncomp, size_t rows, double* __restrict__ means,
+                                   double* __restrict__ weights, int* __restrict__ status) {
+    const int j = blockIdx.x, k = threadIdx.x;
+    const int nout = c * c + c + 1;
+    const double sumw = mom[(size_t)j * nout + c * c + c];
+    if (k == 0) {
+        weights[j] = sumw / (double)rows;
+        if (!(sumw > 0.0)) atomicMin(status, -1000 - j);
+    }
+    if (k < c) means[(size_t)j * c + k] = mom[(size_t)j * nout + c * c + k] / sumw;
+}
+// M-step, part 2: cov = (sum_i w (z - mu)(z - mu)^T + reg I) / sum w   (Regularized(reg), [RECALL])
+__global__ void k_gmm_update_covs(const double* __restrict__ mom, int c, double reg, double* __restrict__ covs) {
+    const int j = blockIdx.x, t = threadIdx.x;
+    const int nout = c * c + c + 1;
+    if (t >= c * c) return;
+    const double sumw = mom[(size_t)j * nout + c * c + c];
+    double v = mom[(size_t)j * nout + t];
+    if (t / c == t % c) v += reg;
+    covs[(size_t)j * c * c + t] = v / sumw;
+}
+// initial covariance for every component: data covariance / (n - 1) + reg I
+__global__ void k_gmm_init_covs(const double* __restrict__ mom, int c, int ncomp, size_t rows, double reg, double* __restrict__ covs) {
+    const int j = blockIdx.x, t = threadIdx.x;
+    if (t >= c * c) return;
+    double v = mom[t] * (1.0 / (double)(rows - 1));
+    if (t / c == t % c) v += reg;
+    covs[(size_t)j * c * c + t] = v;
+}
+__global__ void k_gmm_init_means(const double* __restrict__ z, int c, const uint64_t* __restrict__ pick, double* __restrict__ means,
+                                 double* __restrict__ weights, int ncomp) {
+    const int j = blockIdx.x, k = threadIdx.x;
+    if (k < c) means[(size_t)j * c + k] = z[pick[j] * c + k];
+    if (k == 0) weights[j] = 1.0 / (double)ncomp;
+}
+__global__ void k_gmm_check_det(const double* __restrict__ sqrt_det, int ncomp, int* __restrict__ status) {
+    const int j = threadIdx.x;
+    if (j < ncomp && !(sqrt_det[j] > 0.0)) atomicMin(status, -2000 - j);  // sqrt of a non-positive determinant is NaN / 0
+}
+
 static int check_model(ss_ctx* ctx, const ss_gmm* model) {
     if (!model) return set_error(ctx, SS_ERR_NOT_TRAINED, "Must first train model");  // src/lib.rs:141
     if (model->ncomp < 1 || model->ncomp > kMaxComp) return set_error(ctx, SS_ERR_INVALID, "ncomp must be in 1..%d", kMaxComp);
@@ -609,6 +704,113 @@ int ss_sequence_distances(ss_ctx* ctx, const double* mean_mfccs, size_t nrows, i
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaMemcpyAsync(out_dist, st->d_z.p, (nrows - 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+int ss_gmm_train(ss_ctx* ctx, const double* mfcc, size_t frames, int ncoeffs, int ncomp, int iters, double reg, uint64_t seed,
+                 double* out_means, double* out_covs, double* out_weights) {
+    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
+    if (ncoeffs < 1 || ncoeffs > SS_MAX_NCOEFFS) return set_error(ctx, SS_ERR_INVALID, "ncoeffs must be in 1..%d", SS_MAX_NCOEFFS);
+    if (ncomp < 1 || ncomp > kMaxComp) return set_error(ctx, SS_ERR_INVALID, "ncomp must be in 1..%d", kMaxComp);
+    if (iters < 0) return set_error(ctx, SS_ERR_INVALID, "iters must be >= 0");
+    if (frames < 2 || frames < (size_t)ncomp) return set_error(ctx, SS_ERR_TOO_FEW_ROWS, "training needs >= max(2, ncomp) rows (got %zu)", frames);
+    if (!mfcc || !out_means || !out_covs || !out_weights) return set_error(ctx, SS_ERR_INVALID, "NULL buffer");
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SegState* st = seg_state(ctx);
+    const int c = ncoeffs, nout = c * c + c + 1;
+    SS_TRY(upload(ctx, st->d_mfcc, mfcc, frames * (size_t)c));
+    // Standardizer (A5)
+    const int nb = (int)std::min<size_t>(std::max<size_t>(frames / 64, 1), 1024);
+    SS_CUDA(ctx, st->d_partial.reserve(std::max<size_t>((size_t)nb * 16, (size_t)ncomp * 256 * nout)));
+    SS_CUDA(ctx, st->d_stats.reserve(48));
+    double* d_mean = st->d_stats.p;
+    double* d_var = d_mean + 16;
+    double* d_sd = d_mean + 32;
+    k_col_partial<<<nb, 256, 0, ctx->stream>>>(st->d_mfcc.p, frames, c, nullptr, 0, st->d_partial.p);
+    SS_LAUNCHED(ctx);
+    k_col_final<<<1, 32, 0, ctx->stream>>>(st->d_partial.p, nb, c, (double)frames, d_mean, nullptr);
+    SS_LAUNCHED(ctx);
+    k_col_partial<<<nb, 256, 0, ctx->stream>>>(st->d_mfcc.p, frames, c, d_mean, 1, st->d_partial.p);
+    SS_LAUNCHED(ctx);
+    k_col_final<<<1, 32, 0, ctx->stream>>>(st->d_partial.p, nb, c, (double)(frames - 1), d_var, d_sd);
+    SS_LAUNCHED(ctx);
+    SS_CUDA(ctx, st->d_z.reserve(frames * (size_t)c));
+    k_standardize<<<ceil_div((long long)(frames * c), 256), 256, 0, ctx->stream>>>(st->d_mfcc.p, frames, c, d_mean, d_sd, st->d_z.p);
+    SS_LAUNCHED(ctx);
+    // model buffers: means | covs | weights, moments, inverse covariances
+    const size_t msz = (size_t)ncomp * c + (size_t)ncomp * c * c + ncomp;
+    SS_CUDA(ctx, st->d_model.reserve(msz));
+    double* d_means = st->d_model.p;
+    double* d_covs = d_means + (size_t)ncomp * c;
+    double* d_w = d_covs + (size_t)ncomp * c * c;
+    SS_CUDA(ctx, st->d_inv.reserve((size_t)ncomp * c * c));
+    SS_CUDA(ctx, st->d_sqrt_det.reserve(ncomp));
+    SS_CUDA(ctx, st->d_status.reserve(1));
+    SS_CUDA(ctx, cudaMemsetAsync(st->d_status.p, 0, sizeof(int), ctx->stream));
+    SS_CUDA(ctx, st->d_post.reserve(frames * (size_t)ncomp));
+    SS_CUDA(ctx, st->d_sym.reserve(frames));
+    SS_CUDA(ctx, st->d_h.reserve((size_t)ncomp * nout + 64));  // moments
+    double* d_mom = st->d_h.p;
+    const int mb = (int)std::min<size_t>((frames + 31) / 32, 256);
+    // initial covariance: column means of z, then centred second moments (mode 2)
+    k_col_partial<<<nb, 256, 0, ctx->stream>>>(st->d_z.p, frames, c, nullptr, 0, st->d_partial.p);
+    SS_LAUNCHED(ctx);
+    k_col_final<<<1, 32, 0, ctx->stream>>>(st->d_partial.p, nb, c, (double)frames, d_var, nullptr);  // d_var reused: mean of z
+    SS_LAUNCHED(ctx);
+    k_gmm_moments<<<dim3(mb, 1), 256, 0, ctx->stream>>>(st->d_z.p, frames, c, ncomp, nullptr, d_var, 2, st->d_partial.p);
+    SS_LAUNCHED(ctx);
+    k_gmm_moments_final<<<1, 256, 0, ctx->stream>>>(st->d_partial.p, mb, nout, d_mom);
+    SS_LAUNCHED(ctx);
+    k_gmm_init_covs<<<ncomp, 256, 0, ctx->stream>>>(d_mom, c, ncomp, frames, reg, d_covs);
+    SS_LAUNCHED(ctx);
+    // initial means: `ncomp` distinct rows, partial Fisher-Yates with a seeded mt19937_64 (the reference uses thread_rng)
+    std::vector<uint64_t> pick(ncomp);
+    {
+        std::mt19937_64 rng(seed);
+        std::vector<size_t> idx(frames);
+        for (size_t i = 0; i < frames; i++) idx[i] = i;
+        for (int j = 0; j < ncomp; j++) {
+            std::uniform_int_distribution<size_t> dist(j, frames - 1);
+            std::swap(idx[j], idx[dist(rng)]);
+            pick[j] = idx[j];
+        }
+    }
+    SS_TRY(upload(ctx, st->d_lens, pick.data(), (size_t)ncomp));
+    k_gmm_init_means<<<ncomp, 32, 0, ctx->stream>>>(st->d_z.p, c, st->d_lens.p, d_means, d_w, ncomp);
+    SS_LAUNCHED(ctx);
+    const size_t smem = sizeof(double) * ((size_t)ncomp * c * c + (size_t)ncomp * c + 2 * (size_t)ncomp);
+    SS_CUDA(ctx, cudaFuncSetAttribute(k_gmm_symbols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int it = 0; it < iters; it++) {
+        k_gmm_prepare<<<1, 32, 0, ctx->stream>>>(d_covs, ncomp, c, st->d_inv.p, st->d_sqrt_det.p, st->d_status.p);
+        SS_LAUNCHED(ctx);
+        k_gmm_symbols<<<ceil_div((long long)frames, 128), 128, smem, ctx->stream>>>(st->d_z.p, frames, c, ncomp, d_means, st->d_inv.p,
+                                                                                  st->d_sqrt_det.p, d_w, st->d_sym.p, st->d_post.p);
+        SS_LAUNCHED(ctx);
+        k_gmm_moments<<<dim3(mb, ncomp), 256, 0, ctx->stream>>>(st->d_z.p, frames, c, ncomp, st->d_post.p, nullptr, 0, st->d_partial.p);
+        SS_LAUNCHED(ctx);
+        k_gmm_moments_final<<<ncomp, 256, 0, ctx->stream>>>(st->d_partial.p, mb, nout, d_mom);
+        SS_LAUNCHED(ctx);
+        k_gmm_update_means<<<ncomp, 32, 0, ctx->stream>>>(d_mom, c, ncomp, frames, d_means, d_w, st->d_status.p);
+        SS_LAUNCHED(ctx);
+        k_gmm_moments<<<dim3(mb, ncomp), 256, 0, ctx->stream>>>(st->d_z.p, frames, c, ncomp, st->d_post.p, d_means, 1, st->d_partial.p);
+        SS_LAUNCHED(ctx);
+        k_gmm_moments_final<<<ncomp, 256, 0, ctx->stream>>>(st->d_partial.p, mb, nout, d_mom);
+        SS_LAUNCHED(ctx);
+        k_gmm_update_covs<<<ncomp, 256, 0, ctx->stream>>>(d_mom, c, reg, d_covs);
+        SS_LAUNCHED(ctx);
+    }
+    k_gmm_prepare<<<1, 32, 0, ctx->stream>>>(d_covs, ncomp, c, st->d_inv.p, st->d_sqrt_det.p, st->d_status.p);  // predict must work
+    SS_LAUNCHED(ctx);
+    k_gmm_check_det<<<1, 32, 0, ctx->stream>>>(st->d_sqrt_det.p, ncomp, st->d_status.p);
+    SS_LAUNCHED(ctx);
+    int status = 0;
+    SS_CUDA(ctx, cudaMemcpyAsync(&status, st->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaMemcpyAsync(out_means, d_means, sizeof(double) * ncomp * c, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaMemcpyAsync(out_covs, d_covs, sizeof(double) * ncomp * c * c, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaMemcpyAsync(out_weights, d_w, sizeof(double) * ncomp, cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (status != 0)  // the reference retries with a fresh random draw (`while let Err`, src/lib.rs:50-52); the caller does the same with seed + 1
+        return set_error(ctx, SS_ERR_INVALID, "EM failed (status %d): a component collapsed or a covariance became singular", status);
     return SS_OK;
 }
 

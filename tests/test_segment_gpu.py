@@ -121,3 +121,29 @@ def test_reconstruction_flow_like_the_example(ctx, section71, sample_excerpt):
     di, dd = d2.match_indices(segs, k=4)
     assert np.array_equal(di, sample_excerpt["dtw_idx"])
     assert np.allclose(dd, sample_excerpt["dtw_dist"], rtol=1e-9)
+
+
+def test_gmm_train_on_device_matches_seeded_oracle(ctx, section71):
+    """train_model (src/lib.rs:44-54) on the GPU vs the oracle's seeded EM: same initial rows (same mt19937_64 draw), so
+    the models agree to summation-order noise; the reference itself is randomly seeded, so this is the strongest parity
+    that exists for training."""
+    m = section71["mfcc"]
+    means, covs, weights = ctx.gmm_train(m, 26, 5, 0.1, seed=0)
+    assert np.allclose(means, section71["gmm_means"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(covs, section71["gmm_covs"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(weights, section71["gmm_weights"], rtol=1e-9) and abs(weights.sum() - 1.0) < 1e-12
+    sym = ctx.symbols(m, (means, covs, weights))
+    assert np.mean(sym != section71["symbols"]) < 2e-3  # a frame may flip only where two posteriors tie to ~1e-9
+    z, _, _ = O.standardize(m)
+    for seed, iters in ((3, 1), (7, 0)):
+        gm = ctx.gmm_train(m, 26, iters, 0.1, seed=seed)
+        om = O.gmm_train(z, 26, iters, 0.1, seed=seed)
+        for a, b in zip(gm, om):
+            assert np.allclose(a, b, rtol=1e-8, atol=1e-10)
+    with pytest.raises(SoundsymError) as e:
+        ctx.gmm_train(m[:10], 26)
+    assert e.value.code == -6
+    p = api.Partitioner(api.Sound(np.zeros(0), 44100.0, m, 0.0, m.mean(axis=0), None, ctx), ctx).set_depth(3).set_threshold(4)
+    p.train(seed=0)  # Partitioner::train without a supplied model
+    lens = p.partition()
+    assert int(lens.sum()) == 1978 * 256 and len(lens) > 50
