@@ -162,6 +162,9 @@ uint64_t ss_dict_last_uncertified(const ss_dict* dict);
 /* SS_DTW only: number of queries of the last match that the tensor-core (fp16) scan could not certify and that were
  * therefore re-run through the fp32 scan before the result was returned. */
 uint64_t ss_dict_last_tc_fallback(const ss_dict* dict);
+/* SS_DTW only: number of queries of the last match that neither scan could certify (e.g. many near-identical dictionary
+ * entries) and that were therefore matched by exhaustive f64 DTW against every segment. */
+uint64_t ss_dict_last_exhaustive(const ss_dict* dict);
 
 /* ss_resynth   SoundSequence::clone_from_dictionary sample assembly (src/sound.rs:451-472) + to_sound (:475-483):
  *              for target segment t copy min(len) samples of dictionary sound match_idx[t] and zero-pad to

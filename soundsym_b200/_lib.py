@@ -19,7 +19,7 @@ SYMBOLS = [
     "ss_ctx_launch_count", "ss_frame_count", "ss_decode_pcm", "ss_sound_analyze", "ss_mfcc", "ss_max_power", "ss_mfcc_dev",
     "ss_symbols", "ss_gmm_train", "ss_vote_split", "ss_partition", "ss_dict_create", "ss_dict_destroy", "ss_dict_len", "ss_dict_match",
     "ss_queries_create", "ss_queries_destroy", "ss_dict_match_dev", "ss_topk_merge_dev", "ss_dict_last_work",
-    "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances",
+    "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_dict_last_exhaustive", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances",
 ]
 
 
@@ -80,6 +80,8 @@ def load():
     L.ss_dict_last_uncertified.restype = u64
     L.ss_dict_last_tc_fallback.argtypes = [vp]
     L.ss_dict_last_tc_fallback.restype = u64
+    L.ss_dict_last_exhaustive.argtypes = [vp]
+    L.ss_dict_last_exhaustive.restype = u64
     L.ss_queries_invalidate.argtypes = [vp]
     L.ss_dict_last_scan_ms.argtypes = [vp]
     L.ss_dict_last_scan_ms.restype = dbl

@@ -216,6 +216,10 @@ class DeviceDictionary:
     def last_tc_fallback(self):
         return int(self.ctx.lib.ss_dict_last_tc_fallback(self.h))
 
+    @property
+    def last_exhaustive(self):
+        return int(self.ctx.lib.ss_dict_last_exhaustive(self.h))
+
 
 class DeviceQueries:
     """ss_queries: a prepared query batch resident in HBM."""

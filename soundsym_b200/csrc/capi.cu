@@ -140,6 +140,7 @@ void ss_dict_destroy(ss_dict* d) {
 size_t ss_dict_len(const ss_dict* d) { return d ? d->nseg : 0; }
 uint64_t ss_dict_last_work(const ss_dict* d) { return d ? d->last_work : 0; }
 uint64_t ss_dict_last_tc_fallback(const ss_dict* d) { return d ? d->last_tc_fallback : 0; }
+uint64_t ss_dict_last_exhaustive(const ss_dict* d) { return d ? d->last_exhaustive : 0; }
 
 uint64_t ss_dict_last_uncertified(const ss_dict* dc) {
     ss_dict* d = const_cast<ss_dict*>(dc);

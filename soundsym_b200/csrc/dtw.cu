@@ -382,6 +382,7 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used);
+int dtw_exhaustive_match(ss_dict* d, ss_queries* q, int k, const std::vector<uint32_t>& subset, uint32_t* d_out_idx, double* d_out_dist);
 }
 
 namespace ss {
@@ -511,25 +512,50 @@ static int g_scan_rb = 0;  // 0 = default; tools/tests may override through SS_D
 
 static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset);
 
-int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist) {
+// reads back which queries the last stage could not certify
+static int uncertified_subset(ss_dict* d, ss_queries* q, std::vector<uint32_t>* subset) {
     ss_ctx* ctx = d->ctx;
-    if (k < 1 || k > SS_MAX_TOPK) return set_error(ctx, SS_ERR_INVALID, "k must be in 1..%d (got %d)", SS_MAX_TOPK, k);
-    bool used = false;  // tensor-core scan (dtw_tc.cu) when the shapes allow it
-    SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
-    if (!used) return dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr);
-    // queries whose top-k the fp16 scan could not certify are re-run through the fp32 scan (rigorous bound 4e-6)
+    subset->clear();
     unsigned long long n_unc = 0;
     SS_CUDA(ctx, cudaMemcpyAsync(&n_unc, d->d_counters.p, sizeof(n_unc), cudaMemcpyDeviceToHost, ctx->stream));
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    d->last_tc_fallback = n_unc;
     if (n_unc == 0) return SS_OK;
     std::vector<uint8_t> flags(q->nq);
     SS_CUDA(ctx, cudaMemcpyAsync(flags.data(), q->d_uncert_flag.p, q->nq, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<uint32_t> subset;
     for (size_t i = 0; i < q->nq; i++)
-        if (flags[i]) subset.push_back((uint32_t)i);
-    return dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, &subset);
+        if (flags[i]) subset->push_back((uint32_t)i);
+    return SS_OK;
+}
+
+// Three stages, each only for the queries the previous one could not certify:
+//   1. tensor-core scan (fp16 products)          dtw_tc.cu     bound: triangle inequality on the rounded frames
+//   2. fp32 scan                                 k_dtw_scan    bound: 4e-6 (max|a|^2 + max|b|^2)
+//   3. exhaustive f64 DTW against every segment  exact.cu      exact by construction
+// Stage 3 only triggers when more than KP segments are closer to each other than the fp32 scan can resolve (e.g. many
+// near-identical dictionary entries); it guarantees that what ss_dict_match returns is THE f64 top-k.
+int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist) {
+    ss_ctx* ctx = d->ctx;
+    if (k < 1 || k > SS_MAX_TOPK) return set_error(ctx, SS_ERR_INVALID, "k must be in 1..%d (got %d)", SS_MAX_TOPK, k);
+    SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
+    SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
+    d->last_tc_fallback = 0;
+    d->last_exhaustive = 0;
+    bool used = false;
+    SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
+    std::vector<uint32_t> subset;
+    if (used) {
+        SS_TRY(uncertified_subset(d, q, &subset));
+        d->last_tc_fallback = subset.size();
+        if (subset.empty()) return SS_OK;
+        SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, &subset));
+    } else {
+        SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr));
+    }
+    SS_TRY(uncertified_subset(d, q, &subset));
+    d->last_exhaustive = subset.size();
+    if (subset.empty()) return SS_OK;
+    return dtw_exhaustive_match(d, q, k, subset, d_out_idx, d_out_dist);
 }
 
 static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset) {
@@ -622,7 +648,7 @@ static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx,
 #undef SS_SCAN_CASE
     }
     // fp32 scan: |error| of a normalised distance <= 4e-6 (max|a|^2 + max|b|^2)  (14 roundings of 2^-24 on terms <= 2(|a|^2+|b|^2))
-    return dtw_rescore_finalize(d, q, k, kp, nslots, q->d_group_qid.p, 4e-6, q->d_max_norm.p, d->d_max_norm.p, nullptr, 0, nullptr,
+    return dtw_rescore_finalize(d, q, k, kp, nslots, q->d_group_qid.p, 4e-6, q->d_max_norm.p, d->d_max_norm.p, nullptr, 0, q->d_uncert_flag.p,
                                 /*fill=*/subset == nullptr, d_out_idx, d_out_dist);
 }
 

@@ -652,7 +652,6 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, grid, smem, nlists, nslots, d));
     else SS_TRY(tc_launch<16>(ctx, p, grid, smem, nlists, nslots, d));
     // certification bound for fp16 inputs: see k_dtw_finalize (bound_mode 1)
-    SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
     SS_TRY(dtw_rescore_finalize(d, q, k, kp, nslots, q->d_tc_qid.p, 0.0, q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 1,
                                 q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
     *used = true;

@@ -352,6 +352,115 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// exhaustive f64 DTW: (uncertified query u, every dictionary segment). One thread per pair, DP row in a [column][pair]
+// global scratch; then one block per query selects its top-k by (distance, index).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_dtw_pairs_exact(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                                  const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ qids, uint32_t nu, uint32_t seg_begin,
+                                  uint32_t seg_count, double* __restrict__ rows, uint32_t row_pairs, double* __restrict__ exact, uint32_t nseg) {
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= nu * seg_count) return;
+    const uint32_t u = local / seg_count, sidx = seg_begin + local % seg_count;
+    const uint32_t qid = qids[u];
+    const double* a = qmfcc + qoff[qid] * c;
+    const double* b = dmfcc + doff[sidx] * c;
+    const uint32_t la = (uint32_t)(qoff[qid + 1] - qoff[qid]), lb = (uint32_t)(doff[sidx + 1] - doff[sidx]);
+    double* row = rows + local;
+    double last = kInf;
+    for (uint32_t i = 0; i < la; i++) {
+        double ar[SS_MAX_NCOEFFS];
+#pragma unroll
+        for (int k = 0; k < SS_MAX_NCOEFFS; k++) ar[k] = k < c ? a[(size_t)i * c + k] : 0.0;
+        double left = kInf, diag = kInf;
+        for (uint32_t j = 0; j < lb; j++) {
+            double cost = 0.0;
+#pragma unroll
+            for (int k = 0; k < SS_MAX_NCOEFFS; k++)
+                if (k < c) {
+                    const double dlt = ar[k] - b[(size_t)j * c + k];
+                    cost = cost + dlt * dlt;
+                }
+            const double up = i ? row[(size_t)j * row_pairs] : kInf;
+            const double m = (i == 0 && j == 0) ? 0.0 : fmin(fmin(up, left), diag);
+            const double cur = cost + m;
+            row[(size_t)j * row_pairs] = cur;
+            diag = up;
+            left = cur;
+        }
+        last = left;
+    }
+    exact[(size_t)u * nseg + sidx] = (la && lb) ? last / (double)(la + lb) : kInf;
+}
+
+__global__ void __launch_bounds__(256)
+k_dtw_select_exact(const double* __restrict__ exact, uint32_t nseg, int k, const uint32_t* __restrict__ qids, uint32_t index_base,
+                   uint32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    __shared__ double sd[256 * SS_MAX_TOPK];
+    __shared__ uint32_t si[256 * SS_MAX_TOPK];
+    const uint32_t u = blockIdx.x, t = threadIdx.x;
+    double dv[SS_MAX_TOPK];
+    uint32_t iv[SS_MAX_TOPK];
+    int n = 0;
+    auto push = [&](double dd, uint32_t ii) {
+        if (!(dd < kInf)) return;
+        if (n == k && !(dd < dv[k - 1] || (dd == dv[k - 1] && ii < iv[k - 1]))) return;
+        int pos = n < k ? n : k - 1;
+        while (pos > 0 && (dd < dv[pos - 1] || (dd == dv[pos - 1] && ii < iv[pos - 1]))) {
+            dv[pos] = dv[pos - 1];
+            iv[pos] = iv[pos - 1];
+            pos--;
+        }
+        dv[pos] = dd;
+        iv[pos] = ii;
+        if (n < k) n++;
+    };
+    for (uint32_t s = t; s < nseg; s += 256) push(exact[(size_t)u * nseg + s], s);
+    for (int s = 0; s < k; s++) {
+        sd[t * SS_MAX_TOPK + s] = s < n ? dv[s] : kInf;
+        si[t * SS_MAX_TOPK + s] = s < n ? iv[s] : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (t == 0) {
+        n = 0;
+        for (int w = 0; w < 256; w++)
+            for (int s = 0; s < k; s++)
+                if (si[w * SS_MAX_TOPK + s] != 0xFFFFFFFFu) push(sd[w * SS_MAX_TOPK + s], si[w * SS_MAX_TOPK + s]);
+        const uint32_t qid = qids[u];
+        for (int s = 0; s < k; s++) {
+            out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
+            out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
+        }
+    }
+}
+
+int dtw_exhaustive_match(ss_dict* d, ss_queries* q, int k, const std::vector<uint32_t>& subset, uint32_t* d_out_idx, double* d_out_dist) {
+    ss_ctx* ctx = d->ctx;
+    const uint32_t nseg = (uint32_t)d->nseg, max_ld = std::max<uint32_t>(d->max_len, 1);
+    const uint64_t budget = 32ull << 20;  // doubles of DP-row scratch and of the distance table (256 MB each)
+    const uint32_t ubatch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(subset.size(), budget / std::max<uint32_t>(nseg, 1)));
+    SS_CUDA(ctx, d->d_exh_qid.reserve(subset.size()));
+    SS_CUDA(ctx, cudaMemcpyAsync(d->d_exh_qid.p, subset.data(), subset.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SS_CUDA(ctx, d->d_exh_dist.reserve((size_t)ubatch * nseg));
+    for (size_t u0 = 0; u0 < subset.size(); u0 += ubatch) {
+        const uint32_t nu = (uint32_t)std::min<size_t>(ubatch, subset.size() - u0);
+        const uint32_t seg_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nseg, budget / ((uint64_t)max_ld * nu)));
+        SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)seg_batch * nu * max_ld));
+        for (uint32_t s0 = 0; s0 < nseg; s0 += seg_batch) {
+            const uint32_t sc = std::min<uint32_t>(seg_batch, nseg - s0);
+            k_dtw_pairs_exact<<<ceil_div((long long)nu * sc, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
+                                                                                         d->d_exh_qid.p + u0, nu, s0, sc, d->d_rescore_rows.p,
+                                                                                         nu * sc, d->d_exh_dist.p, nseg);
+            SS_LAUNCHED(ctx);
+        }
+        k_dtw_select_exact<<<nu, 256, 0, ctx->stream>>>(d->d_exh_dist.p, nseg, k, d->d_exh_qid.p + u0, d->index_base, d_out_idx, d_out_dist);
+        SS_LAUNCHED(ctx);
+    }
+    SS_CUDA(ctx, cudaMemsetAsync(d->d_counters.p, 0, sizeof(unsigned long long), ctx->stream));  // everything is exact now
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `subset` is read by the async copy above
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // merge of per-shard top-k lists, list-major [nlists][nq][k] -> [nq][k]; (distance, index) lexicographic
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_topk_merge(const uint32_t* __restrict__ idx, const double* __restrict__ dist, int nlists, size_t nq, int k,

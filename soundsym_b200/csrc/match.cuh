@@ -57,6 +57,9 @@ struct ss_dict {
     std::vector<uint32_t> h_slice_tile;
     uint64_t last_work = 0, last_uncertified = 0;
     uint64_t last_tc_fallback = 0;  // queries of the last match that the tensor-core scan handed to the fp32 scan
+    uint64_t last_exhaustive = 0;   // queries that neither scan could certify and that were matched exhaustively in f64
+    ss::DevBuf<double> d_exh_dist;
+    ss::DevBuf<uint32_t> d_exh_qid;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;  // around the dominant kernel of the last match
     bool scan_timed = false;
     // tensor-core scan (dtw_tc.cu): fp16 UMMA tiles of 4 segment slots x 32 columns, segments sorted by length

@@ -158,3 +158,41 @@ def test_error_behaviour(ctx):
         dev.match(d, doff, SS_COSINE_REF, 2)
     with pytest.raises(SoundsymError):
         dev.match(d, np.array([0, 5, 3], dtype=np.uint64), SS_DTW, 1)
+
+
+def test_tensor_core_scan_fallback_on_near_duplicates(ctx):
+    """A dictionary with many near-identical segments: more than KP candidates sit inside the fp16 scan's error bound,
+    so the certification must refuse them and the fp32 scan must re-run those queries; results stay exact and ties still
+    resolve to the lowest index."""
+    rng = np.random.default_rng(5)
+    base, boff = synth.segments(64, 13, seed=9)
+    seg = base[int(boff[3]):int(boff[4])]
+    L = len(seg)
+    copies = [seg + rng.normal(size=seg.shape) * 1e-4 for _ in range(40)] + [seg.copy(), seg.copy()]
+    d = np.concatenate([base] + copies)
+    doff = np.concatenate([boff, boff[-1] + np.uint64(L) * np.arange(1, len(copies) + 1, dtype=np.uint64)]).astype(np.uint64)
+    q = np.concatenate([seg, base[int(boff[10]):int(boff[11])]])
+    qoff = np.array([0, L, L + int(boff[11] - boff[10])], dtype=np.uint64)
+    dev = api.DeviceDictionary(ctx, d, doff)
+    idx, dist = dev.match(q, qoff, SS_DTW, 4)
+    oidx, odist = O.dtw_topk(d, doff, q, qoff, 13, 4)
+    check_dtw(idx, dist, oidx, odist, 4)
+    assert list(idx[0, :3]) == [3, 104, 105] and dist[0, 0] == 0.0  # the original and its two exact copies, lowest index first
+    # 43 segments within 1e-7 of each other: neither scan can certify query 0 -> exhaustive f64 stage; nothing stays uncertified
+    assert dev.last_tc_fallback >= 1 and dev.last_exhaustive >= 1 and dev.last_uncertified == 0
+
+
+def test_fp32_scan_forced_matches_tensor_core_scan(ctx):
+    """SS_DTW_TC=0 is read once per process, so the fp32 scan is exercised here through shapes the tensor-core scan
+    declines (a 33-frame segment in the dictionary) on otherwise identical data."""
+    d, doff = synth.segments(300, 13, seed=31)
+    q, qoff = synth.segments(70, 13, seed=32)
+    tc = api.DeviceDictionary(ctx, d, doff)
+    i1, d1 = tc.match(q, qoff, SS_DTW, 4)
+    long_seg = np.random.default_rng(1).normal(size=(33, 13)) * 50 + 500  # far from everything: never a candidate
+    d2 = np.concatenate([d, long_seg])
+    doff2 = np.concatenate([doff, [doff[-1] + np.uint64(33)]]).astype(np.uint64)
+    fp = api.DeviceDictionary(ctx, d2, doff2)
+    i2, dd2 = fp.match(q, qoff, SS_DTW, 4)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, dd2)
+    assert fp.last_tc_fallback == 0
