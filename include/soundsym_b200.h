@@ -89,6 +89,12 @@ int ss_frame_count(size_t n, size_t* out_frames);
 int ss_decode_pcm(ss_ctx* ctx, const int32_t* pcm, size_t n, int bits_per_sample, double* out_samples);
 int ss_sound_analyze(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc,
                      size_t* out_frames, double* out_max_power, double* out_mean_mfccs);
+/* ss_sound_analyze_pcm   Sound::from_path in one call: integer PCM in (bits 16 -> an int16_t buffer,
+ *                        24 / 32 -> an int32_t buffer), so the host->device copy is 2 or 4 bytes per sample instead of 8;
+ *                        the s / (i32::MAX >> (32 - bits)) conversion (src/sound.rs:118-120) runs on the device, then the
+ *                        three analyses. out_samples (n doubles, the Sound's `samples` Vec) may be NULL. */
+int ss_sound_analyze_pcm(ss_ctx* ctx, const void* pcm, size_t n, int bits_per_sample, double sample_rate, int ncoeffs,
+                         double* out_samples, double* out_mfcc, size_t* out_frames, double* out_max_power, double* out_mean_mfccs);
 int ss_mfcc(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc,
             size_t* out_frames);
 int ss_max_power(ss_ctx* ctx, const double* samples, size_t n, double* out);

@@ -83,6 +83,21 @@ class Context:
                                              C.byref(frames), C.byref(mp), _ptr(mean)))
         return mfcc, float(mp.value), mean
 
+    def analyze_pcm(self, pcm, bits, sample_rate=44100.0, ncoeffs=NCOEFFS):
+        """Sound::from_path's decode + the three analyses with integer PCM crossing PCIe (2 or 4 bytes per sample)
+        -> (samples f64, mfcc, max_power, mean_mfccs)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16 if bits == 16 else np.int32)
+        n = pcm.shape[0]
+        frames = C.c_size_t()
+        self.check(self.lib.ss_frame_count(n, C.byref(frames)))
+        samples = np.empty(n, dtype=np.float64)
+        mfcc = np.empty((frames.value, ncoeffs), dtype=np.float64)
+        mean = np.empty(ncoeffs, dtype=np.float64)
+        mp = C.c_double()
+        self.check(self.lib.ss_sound_analyze_pcm(self.h, _ptr(pcm), n, int(bits), float(sample_rate), int(ncoeffs), _ptr(samples), _ptr(mfcc),
+                                                 C.byref(frames), C.byref(mp), _ptr(mean)))
+        return samples, mfcc, float(mp.value), mean
+
     def mfcc(self, samples, sample_rate=44100.0, ncoeffs=NCOEFFS):
         samples = np.ascontiguousarray(samples, dtype=np.float64)
         frames = C.c_size_t()
@@ -291,8 +306,8 @@ class Sound:
         import os
         ctx = ctx or default_context()
         pcm, sr, bits = _read_wav_pcm(path)
-        samples = ctx.decode_pcm(pcm, bits)
-        return cls.from_samples(samples, sr, None, os.path.splitext(os.path.basename(path))[0], ctx)
+        samples, m, mp, mean = ctx.analyze_pcm(pcm, bits, sr, NCOEFFS)
+        return cls(samples, sr, m, mp, mean, os.path.splitext(os.path.basename(path))[0], ctx)
 
     def push_samples(self, new_samples):
         """Sound::push_samples (src/sound.rs:145-164), including its running-mean rule `(old*n0 + new*n1) * 0.5`."""

@@ -105,6 +105,10 @@ __global__ void k_decode_pcm(const int32_t* __restrict__ pcm, size_t n, double d
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __ddiv_rn((double)pcm[i], denom);
 }
+__global__ void k_decode_pcm16(const int16_t* __restrict__ pcm, size_t n, double denom, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __ddiv_rn((double)pcm[i], denom);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 struct cplx {
@@ -338,17 +342,12 @@ int ss_mfcc_dev(ss_ctx* ctx, const double* d_samples, size_t n, double sample_ra
     return mfcc_launch(ctx, d_samples, n, sample_rate, ncoeffs, d_out_mfcc, frames);
 }
 
-int ss_sound_analyze(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc,
-                     size_t* out_frames, double* out_max_power, double* out_mean_mfccs) {
-    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
-    SS_TRY(check_c(ctx, ncoeffs));
-    if (n && !samples) return set_error(ctx, SS_ERR_INVALID, "samples is NULL");
-    SS_CUDA(ctx, cudaSetDevice(ctx->device));
-    SoundState* st = sound_state(ctx);
+// the three analyses on samples already in st->d_samples; stream-synchronised on return
+static int analyze_resident(ss_ctx* ctx, SoundState* st, size_t n, double sample_rate, int ncoeffs, double* out_mfcc, size_t* out_frames,
+                            double* out_max_power, double* out_mean_mfccs) {
     size_t frames = 0;
     ss_frame_count(n, &frames);
     if (out_frames) *out_frames = frames;
-    SS_TRY(upload(ctx, st->d_samples, samples, n));
     const bool want_mfcc = out_mfcc || out_mean_mfccs;
     if (want_mfcc && frames) {
         SS_CUDA(ctx, st->d_mfcc.reserve(frames * (size_t)ncoeffs));
@@ -380,6 +379,44 @@ int ss_sound_analyze(ss_ctx* ctx, const double* samples, size_t n, double sample
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (out_max_power) memcpy(out_max_power, &bits, sizeof(double));
     return SS_OK;
+}
+
+int ss_sound_analyze(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc,
+                     size_t* out_frames, double* out_max_power, double* out_mean_mfccs) {
+    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
+    SS_TRY(check_c(ctx, ncoeffs));
+    if (n && !samples) return set_error(ctx, SS_ERR_INVALID, "samples is NULL");
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SoundState* st = sound_state(ctx);
+    SS_TRY(upload(ctx, st->d_samples, samples, n));
+    return analyze_resident(ctx, st, n, sample_rate, ncoeffs, out_mfcc, out_frames, out_max_power, out_mean_mfccs);
+}
+
+int ss_sound_analyze_pcm(ss_ctx* ctx, const void* pcm, size_t n, int bits_per_sample, double sample_rate, int ncoeffs, double* out_samples,
+                         double* out_mfcc, size_t* out_frames, double* out_max_power, double* out_mean_mfccs) {
+    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
+    SS_TRY(check_c(ctx, ncoeffs));
+    if (bits_per_sample != 16 && bits_per_sample != 24 && bits_per_sample != 32)
+        return set_error(ctx, SS_ERR_INVALID, "bits_per_sample must be 16 (int16 buffer), 24 or 32 (int32 buffer); got %d", bits_per_sample);
+    if (n && !pcm) return set_error(ctx, SS_ERR_INVALID, "pcm is NULL");
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SoundState* st = sound_state(ctx);
+    SS_CUDA(ctx, st->d_samples.reserve(n));
+    const double denom = (double)(INT32_MAX >> (32 - bits_per_sample));  // src/sound.rs:118-120
+    if (n) {
+        if (bits_per_sample == 16) {
+            SS_CUDA(ctx, st->d_pcm.reserve((n + 1) / 2));  // int16 samples packed in the int32 staging buffer
+            SS_CUDA(ctx, cudaMemcpyAsync(st->d_pcm.p, pcm, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+            k_decode_pcm16<<<ceil_div((long long)n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const int16_t*>(st->d_pcm.p), n, denom,
+                                                                               st->d_samples.p);
+        } else {
+            SS_TRY(upload(ctx, st->d_pcm, static_cast<const int32_t*>(pcm), n));
+            k_decode_pcm<<<ceil_div((long long)n, 256), 256, 0, ctx->stream>>>(st->d_pcm.p, n, denom, st->d_samples.p);
+        }
+        SS_LAUNCHED(ctx);
+        if (out_samples) SS_CUDA(ctx, cudaMemcpyAsync(out_samples, st->d_samples.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return analyze_resident(ctx, st, n, sample_rate, ncoeffs, out_mfcc, out_frames, out_max_power, out_mean_mfccs);
 }
 
 int ss_mfcc(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc, size_t* out_frames) {

@@ -121,3 +121,26 @@ def test_resynth_and_sequence_distances(ctx, section71, sample_excerpt):
     assert np.allclose(got, ref, rtol=0, atol=1e-15)
     v = np.array([[0.1, 0.4, 0.2, 0.8] + [0.0] * 8] * 2)
     assert ctx.sequence_distances(v)[0] == 0.0  # the reference's KAT, src/sound.rs:612-615
+
+
+def test_pcm_ingest_equals_decode_then_analyze(ctx, section71, sample_excerpt, tmp_path):
+    """ss_sound_analyze_pcm: int16 / int24 PCM crosses PCIe, conversion on the device (src/sound.rs:118-120)."""
+    s16 = O.decode_pcm(section71["pcm"].astype(np.int32), 16)
+    samples, mfcc, mp, mean = ctx.analyze_pcm(section71["pcm"], 16)
+    assert np.array_equal(samples, s16)
+    m2, mp2, mean2 = ctx.analyze(s16)
+    assert np.array_equal(mfcc, m2) and mp == mp2 and np.array_equal(mean, mean2)
+    samples, mfcc, mp, _ = ctx.analyze_pcm(sample_excerpt["pcm"], 24)
+    assert np.array_equal(samples, O.decode_pcm(sample_excerpt["pcm"], 24)) and mp == float(sample_excerpt["max_power"])
+    assert_mfcc_close(mfcc, sample_excerpt["mfcc"])
+    # Sound::from_path through a real WAV file
+    import struct
+    body = section71["pcm"].astype("<i2").tobytes()
+    p = tmp_path / "s.wav"
+    p.write_bytes(b"RIFF" + struct.pack("<I", 36 + len(body)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 44100, 88200, 2, 16) + b"data"
+                  + struct.pack("<I", len(body)) + body)
+    snd = api.Sound.from_path(str(p), ctx)
+    assert snd.name == "s" and snd.num_frames() == 1978 and snd.max_power() == float(section71["max_power"])
+    assert np.array_equal(snd.samples(), s16)
+    with pytest.raises(SoundsymError):
+        ctx.analyze_pcm(section71["pcm"], 8)
