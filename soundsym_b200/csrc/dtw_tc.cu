@@ -3,18 +3,21 @@
 // scan runs.
 //
 // Idea: the local-cost matrix is a K = 13 contraction, c(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j. One tcgen05.mma per
-// (dictionary tile, query row i) computes, for the CTA's 128 queries at once, the costs of row i against the 128 columns
-// of the tile (4 segment slots x 32 columns):
+// (dictionary tile, query row i) computes, for the CTA's 128 queries at once, the costs of row i against the 96 columns
+// of the tile (3 segment slots x 32 columns):
 //     D[m, n] = sum_k A_i[m, k] * B[n, k],   A_i[m, :] = [-2 a^(m)_i (13), s, s, 0]   (fp16, K-major, no swizzle)
 //                                            B[n, :]   = [ b_n (13), (|b_n|^2/s)_hi, (|b_n|^2/s)_lo, 0 ]
-// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 128 columns, K = 16 = one MMA). TMEM lane m is
-// read back by the thread that owns query m (tcgen05.ld 32x32b), which adds |a_i|^2 and runs the DP recurrence for its
-// two segment slots with the row state in registers:  FADD + FMNMX3 + FADD per cell instead of 7 FFMA2 + 2 FADD + FMNMX3.
-// Both sides are centred on the dictionary's mean frame before the fp16 conversion (the cost is translation invariant).
+// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 96 columns, K = 16 = one MMA). TMEM lane m is
+// read back by the threads that own query m (tcgen05.ld 32x32b), which add |a_i|^2 and run the DP recurrence for one
+// segment slot each with the row state in registers:  FADD + FMNMX3 + FADD per cell instead of the fp32 scan's
+// 7 FFMA2 + 2 FADD + FMNMX3. Both sides are centred on the dictionary's mean frame before the fp16 conversion (the cost
+// is translation invariant).
 //
-// Warp roles (288 threads, 1 CTA / SM): warps 0-7 = DP (warp w owns TMEM lane quadrant w % 4 and column half w / 4);
-// warp 8 = TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and
-// the MMAs (4 TMEM slots of 128 columns, so the tensor core runs up to 4 rows ahead of the DP).
+// Warp roles (416 threads, 1 CTA / SM): warps 0-11 = DP (warp w owns TMEM lane quadrant w % 4 and segment slot w / 4);
+// warp 12 = TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and
+// the MMAs. A pipeline step is TWO query rows (two MMAs, one commit) into one of two 192-column TMEM buffers, so the DP
+// warps pay one mbarrier round trip per two rows and ping-pong their row state between two register arrays (row i reads
+// dA and writes dB, row i+1 reads dB and writes dA), which removes every register copy from the recurrence.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -28,18 +31,24 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 
 constexpr int kTcM = 128;          // queries per CTA = MMA M = TMEM lanes
-constexpr int kTcN = 128;          // columns per tile = MMA N
-constexpr int kTcSlots = 4;        // segment slots per tile (32 columns each)
+constexpr int kTcSlots = 3;        // segment slots per tile (32 columns each)
+constexpr int kTcN = kTcSlots * 32;  // columns per tile = MMA N = 96
 constexpr int kTcK = 16;           // fp16 elements per row = one MMA K step
-constexpr int kTcTileBytes = kTcN * kTcK * 2;  // 4096
+constexpr int kTcATileBytes = kTcM * kTcK * 2;  // 4096: one query row of the CTA's 128 queries
+constexpr int kTcBTileBytes = kTcN * kTcK * 2;  // 3072: one dictionary tile
 constexpr int kTcStages = 4;       // B-tile ring
-constexpr int kTcTmemSlots = 4;    // 4 x 128 columns = 512
+constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows = 192 TMEM columns; two buffers
 constexpr int kTcMaxLen = 32;
-constexpr int kTcThreads = 288;
+constexpr int kTcDpWarps = 4 * kTcSlots;             // 12
+constexpr int kTcThreads = (kTcDpWarps + 1) * 32;    // 416
+constexpr int kTcDpThreads = kTcDpWarps * 32;        // 384
 
-// byte offset of element (row, k) inside a 128 x 16 fp16 K-major no-swizzle UMMA tile:
-// core matrix = 8 rows x 16 B; LBO (between the two K chunks) = 2048 B, SBO (between 8-row groups) = 128 B
-__host__ __device__ __forceinline__ int tc_tile_offset(int row, int k) { return ((k >> 3) * 16 + (row >> 3)) * 128 + (row & 7) * 16 + (k & 7) * 2; }
+// byte offset of element (row, k) inside a ROWS x 16 fp16 K-major no-swizzle UMMA tile: core matrix = 8 rows x 16 B;
+// SBO (between 8-row groups) = 128 B, LBO (between the two K chunks) = ROWS / 8 * 128 B
+template <int ROWS>
+__host__ __device__ __forceinline__ int tc_tile_offset(int row, int k) {
+    return ((k >> 3) * (ROWS / 8) + (row >> 3)) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -91,9 +100,10 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u)
         : "memory");
 }
+template <int ROWS>
 __device__ __forceinline__ uint64_t tc_smem_desc(const void* p) {
-    // start >> 4 | LBO (2048 B) >> 4 << 16 | SBO (128 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
-    return (uint64_t)((s32(p) & 0x3FFFF) >> 4) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+    // start >> 4 | LBO >> 4 << 16 | SBO (128 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
+    return (uint64_t)((s32(p) & 0x3FFFF) >> 4) | ((uint64_t)((ROWS / 8 * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
@@ -107,6 +117,45 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
+}
+// loads the 8*w8 columns of the thread's segment slot (w8 = slot width / 8, tile-uniform) with at most two tcgen05.ld.
+// TMEM reads are the scarce resource of this kernel (measured: ~21 cycles per tcgen05.ld plus ~10.6 cycles per KB, SM-wide),
+// so segments are sorted by length, every tile gets the narrowest slot width that fits its three segments, and only
+// those columns are read.
+__device__ __forceinline__ void tc_ld_cols(uint32_t taddr, float (&tm)[32], int w8) {
+    if (w8 >= 4) {
+        tc_ld32(taddr, tm);
+    } else if (w8 == 3) {
+        tc_ld16(taddr, tm);
+        tc_ld8(taddr + 16, tm + 16);
+    } else if (w8 == 2) {
+        tc_ld16(taddr, tm);
+    } else {
+        tc_ld8(taddr, tm);
+    }
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tc_min3(float a, float b, float c) {
@@ -163,12 +212,13 @@ __global__ void k_tc_dict_maxnorm(const double* __restrict__ mfcc, size_t frames
 // one thread per (tile, column n): writes row n of the tile's B operand
 __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
                                 const int4* __restrict__ desc, uint32_t ntiles, float inv_scale, unsigned char* __restrict__ tiles) {
-    const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = 128
+    const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = kTcN
     if (t >= ntiles) return;
     const int4 segs = desc[2 * t], lens = desc[2 * t + 1];
-    const int slot = n >> 5, j = n & 31;
-    const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : segs.w;
-    const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : lens.w;
+    const int W = 32;  // slot width
+    const int slot = (int)n / W, j = (int)n % W;
+    const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : -1;
+    const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : 0;
     __half row[kTcK];
 #pragma unroll
     for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
@@ -186,9 +236,9 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
         row[13] = hi;
         row[14] = __float2half_rn(sn - __half2float(hi));
     }
-    unsigned char* base = tiles + (size_t)t * kTcTileBytes;
+    unsigned char* base = tiles + (size_t)t * kTcBTileBytes;
 #pragma unroll
-    for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset((int)n, k)) = row[k];
+    for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcN>((int)n, k)) = row[k];
 }
 // one thread per (group, row i, query m): A_i[m, :] and |a_i|^2
 __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
@@ -199,7 +249,7 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
     const uint32_t L = group_len[g];
     const uint32_t id = qid[g * kTcM + m];
     unsigned char* blk = a_blocks + group_off[g];
-    float* na = reinterpret_cast<float*>(blk + (size_t)L * kTcTileBytes);
+    float* na = reinterpret_cast<float*>(blk + (size_t)L * kTcATileBytes);
     float mx = 0.f;
     for (uint32_t i = 0; i < L; i++) {
         __half row[kTcK];
@@ -217,9 +267,9 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
             row[13] = __float2half_rn(scale);
             row[14] = __float2half_rn(scale);
         }
-        unsigned char* base = blk + (size_t)i * kTcTileBytes;
+        unsigned char* base = blk + (size_t)i * kTcATileBytes;
 #pragma unroll
-        for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset((int)m, k)) = row[k];
+        for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcM>((int)m, k)) = row[k];
         na[(size_t)i * kTcM + m] = nrm;
         mx = fmaxf(mx, nrm);
     }
@@ -240,7 +290,7 @@ struct TcParams {
     const int4* desc;
     const uint32_t* slice_tile;  // nslices + 1
     uint32_t nslices;
-    unsigned long long* partial;  // [nslices * 2 halves][ngroups * 128][KP]
+    unsigned long long* partial;  // [nslices * 3 slots][ngroups * 128][KP]
     uint32_t max_len;
 };
 
@@ -261,84 +311,98 @@ __device__ __forceinline__ void tc_insert(unsigned long long* list, unsigned lon
     const unsigned long long key = ((unsigned long long)tc_f2ord(dist) << 32) | idx;
     if (key < worst && dist == dist) {
         int s = KP - 1;
-        while (s > 0 && list[(s - 1) * 256] > key) {
-            list[s * 256] = list[(s - 1) * 256];
+        while (s > 0 && list[(s - 1) * kTcDpThreads] > key) {
+            list[s * kTcDpThreads] = list[(s - 1) * kTcDpThreads];
             s--;
         }
-        list[s * 256] = key;
-        worst = list[(KP - 1) * 256];
+        list[s * kTcDpThreads] = key;
+        worst = list[(KP - 1) * kTcDpThreads];
     }
 }
 
-// one DP row for the thread's two segment slots at once (independent chains, interleaved for ILP). The row state is
-// updated IN PLACE: t = min(up, diag) of the next column is taken before the current column is overwritten, so the
-// recurrence needs no register copies: per cell FADD (cost + |a|^2), FMNMX (pairwise), FMNMX (with left), FADD.
-// Columns run in groups of 4 behind one uniform guard. LAST (the query's final row) also captures D(L-1, len-1).
+// one DP row of one 32-column segment slot: reads the previous row `din`, writes `dout` (ping-pong, so no register
+// copies): per cell FADD (cost + |a|^2), FMNMX3, FADD. Columns run in groups of 4 behind one uniform guard.
+// LAST (the query's final row) also captures D(L-1, len-1).
 template <bool LAST>
-__device__ __forceinline__ void tc_dp_rows(const float (&tm0)[32], const float (&tm1)[32], float (&d0)[32], float (&d1)[32], float na, int len0,
-                                           int len1, bool first_row, float& r0, float& r1) {
+__device__ __forceinline__ void tc_dp_row(const float (&tm)[32], const float (&din)[32], float (&dout)[32], float na, int len, bool first_row,
+                                          float& res) {
     const float INF = __int_as_float(0x7f800000);
-    const int lenm = len0 > len1 ? len0 : len1;
-    const float corner = first_row ? 0.f : INF;  // D(i-1, -1)
-    float left0 = INF, left1 = INF;
-    float t0 = fminf(d0[0], corner), t1 = fminf(d1[0], corner);
+    float left = INF, diag = first_row ? 0.f : INF;  // D(i, j-1), D(i-1, j-1)
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += 4) {
-        if (j0 < lenm) {
+        if (j0 < len) {
 #pragma unroll
             for (int j = j0; j < j0 + 4; j++) {
-                float tn0 = INF, tn1 = INF;
-                if (j + 1 < 32) {
-                    tn0 = fminf(d0[j + 1], d0[j]);
-                    tn1 = fminf(d1[j + 1], d1[j]);
-                }
-                const float c0 = (tm0[j] + na) + fminf(left0, t0);
-                const float c1 = (tm1[j] + na) + fminf(left1, t1);
-                d0[j] = c0;
-                d1[j] = c1;
-                left0 = c0;
-                left1 = c1;
-                t0 = tn0;
-                t1 = tn1;
-                if (LAST) {
-                    if (j == len0 - 1) r0 = c0;
-                    if (j == len1 - 1) r1 = c1;
-                }
+                const float up = din[j];
+                const float cur = (tm[j] + na) + tc_min3(left, up, diag);
+                dout[j] = cur;
+                left = cur;
+                diag = up;
+                if (LAST && j == len - 1) res = cur;
             }
         }
+    }
+}
+
+// the same row with the number of 4-column groups as a compile-time constant: straight-line code, no guards (the
+// per-group uniform branches of the generic version cost a branch-resolve bubble every 4 cells of the dependent chain)
+template <int NG>
+__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[32], const float (&din)[32], float (&dout)[32], float na, bool first_row) {
+    const float INF = __int_as_float(0x7f800000);
+    float left = INF, diag = first_row ? 0.f : INF;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const float up = din[j];
+        const float cur = (tm[j] + na) + tc_min3(left, up, diag);
+        dout[j] = cur;
+        left = cur;
+        diag = up;
+    }
+}
+__device__ __forceinline__ void tc_dp_row_fast(const float (&tm)[32], const float (&din)[32], float (&dout)[32], float na, int ng, bool first_row) {
+    switch (ng) {
+        case 1: tc_dp_row_ng<1>(tm, din, dout, na, first_row); break;
+        case 2: tc_dp_row_ng<2>(tm, din, dout, na, first_row); break;
+        case 3: tc_dp_row_ng<3>(tm, din, dout, na, first_row); break;
+        case 4: tc_dp_row_ng<4>(tm, din, dout, na, first_row); break;
+        case 5: tc_dp_row_ng<5>(tm, din, dout, na, first_row); break;
+        case 6: tc_dp_row_ng<6>(tm, din, dout, na, first_row); break;
+        case 7: tc_dp_row_ng<7>(tm, din, dout, na, first_row); break;
+        default: tc_dp_row_ng<8>(tm, din, dout, na, first_row); break;
     }
 }
 
 template <int KP>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    // [A tiles: max_len x 4 KB][|a|^2: max_len x 512 B][B ring: 4 x 4 KB][barriers], 128-byte aligned
+    // [A tiles: max_len x 4 KB][|a|^2: max_len x 512 B][B ring: 4 x 3 KB][barriers][candidate lists], 128-byte aligned
     unsigned char* smem = smem_raw + ((128u - (s32(smem_raw) & 127u)) & 127u);
     unsigned char* sA = smem;
-    float* sNa = reinterpret_cast<float*>(smem + (size_t)p.max_len * kTcTileBytes);
-    unsigned char* sB = smem + (size_t)p.max_len * (kTcTileBytes + kTcM * 4);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcTileBytes);
+    float* sNa = reinterpret_cast<float*>(smem + (size_t)p.max_len * kTcATileBytes);
+    unsigned char* sB = smem + (size_t)p.max_len * (kTcATileBytes + kTcM * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcBTileBytes);
     uint64_t* a_full = bars;
     uint64_t* b_full = bars + 1;
     uint64_t* b_empty = b_full + kTcStages;
     uint64_t* t_full = b_empty + kTcStages;
-    uint64_t* t_empty = t_full + kTcTmemSlots;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kTcTmemSlots);
-    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][256]
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][384]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
     const uint32_t L = p.group_len[g];
+    const uint32_t nsteps = (L + 1) / 2;  // pipeline steps (two rows each) per tile
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
     const uint32_t ntiles = t1 - t0;
 
     if (threadIdx.x == 0) {
         mb_init(a_full, 1);
         for (int s = 0; s < kTcStages; s++) mb_init(&b_full[s], 1), mb_init(&b_empty[s], 1);
-        for (int s = 0; s < kTcTmemSlots; s++) mb_init(&t_full[s], 1), mb_init(&t_empty[s], 8);
+        for (int s = 0; s < 2; s++) mb_init(&t_full[s], 1), mb_init(&t_empty[s], kTcDpWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kTcDpWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -347,18 +411,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kTcDpWarps) {
         if (lane == 0 && ntiles) {
             // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------
-            const unsigned a_bytes = L * (kTcTileBytes + kTcM * 4);
+            const unsigned a_bytes = L * (kTcATileBytes + kTcM * 4);
             mb_expect_tx(a_full, a_bytes);
             const unsigned char* ablk = p.a_blocks + p.group_off[g];
             // tiles and |a|^2 are contiguous in global memory but land in two smem regions
-            tma_g2s(sA, ablk, L * kTcTileBytes, a_full);
-            tma_g2s(sNa, ablk + (size_t)L * kTcTileBytes, L * kTcM * 4, a_full);
+            tma_g2s(sA, ablk, L * kTcATileBytes, a_full);
+            tma_g2s(sNa, ablk + (size_t)L * kTcATileBytes, L * kTcM * 4, a_full);
             for (uint32_t n = 0; n < ntiles && n < (uint32_t)kTcStages; n++) {
-                mb_expect_tx(&b_full[n], kTcTileBytes);
-                tma_g2s(sB + n * kTcTileBytes, p.tiles + (size_t)(t0 + n) * kTcTileBytes, kTcTileBytes, &b_full[n]);
+                mb_expect_tx(&b_full[n], kTcBTileBytes);
+                tma_g2s(sB + n * kTcBTileBytes, p.tiles + (size_t)(t0 + n) * kTcBTileBytes, kTcBTileBytes, &b_full[n]);
             }
             mb_wait(a_full, 0);
             const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);  // f16 x f16 -> f32, K-major
@@ -366,68 +430,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
             for (uint32_t n = 0; n < ntiles; n++) {
                 const int stage = n % kTcStages;
                 mb_wait(&b_full[stage], (n / kTcStages) & 1);
-                const uint64_t bdesc = tc_smem_desc(sB + stage * kTcTileBytes);
-                for (uint32_t i = 0; i < L; i++, cnt++) {
-                    const int slot = cnt % kTcTmemSlots;
-                    if (cnt >= (uint32_t)kTcTmemSlots) mb_wait(&t_empty[slot], ((cnt / kTcTmemSlots) - 1) & 1);
+                const uint64_t bdesc = tc_smem_desc<kTcN>(sB + stage * kTcBTileBytes);
+                for (uint32_t st = 0; st < nsteps; st++, cnt++) {
+                    const uint32_t buf = cnt & 1;
+                    if (cnt >= 2) mb_wait(&t_empty[buf], ((cnt >> 1) - 1) & 1);
                     tc_fence_after();
-                    tc_mma_f16(tmem_base + slot * kTcN, tc_smem_desc(sA + (size_t)i * kTcTileBytes), bdesc, idesc);
-                    tc_commit(&t_full[slot]);
+                    tc_mma_f16(tmem_base + buf * kTcBufCols, tc_smem_desc<kTcM>(sA + (size_t)(2 * st) * kTcATileBytes), bdesc, idesc);
+                    if (2 * st + 1 < L)
+                        tc_mma_f16(tmem_base + buf * kTcBufCols + kTcN, tc_smem_desc<kTcM>(sA + (size_t)(2 * st + 1) * kTcATileBytes), bdesc, idesc);
+                    tc_commit(&t_full[buf]);
                 }
                 tc_commit(&b_empty[stage]);
                 if (n + kTcStages < ntiles) {  // refill this stage once its MMAs have completed
                     mb_wait(&b_empty[stage], (n / kTcStages) & 1);
-                    mb_expect_tx(&b_full[stage], kTcTileBytes);
-                    tma_g2s(sB + stage * kTcTileBytes, p.tiles + (size_t)(t0 + n + kTcStages) * kTcTileBytes, kTcTileBytes, &b_full[stage]);
+                    mb_expect_tx(&b_full[stage], kTcBTileBytes);
+                    tma_g2s(sB + stage * kTcBTileBytes, p.tiles + (size_t)(t0 + n + kTcStages) * kTcBTileBytes, kTcBTileBytes, &b_full[stage]);
                 }
             }
         }
     } else {
         // ---- DP warps ---------------------------------------------------------------------------------------------------
-        const int q = warp & 3, h = warp >> 2;
+        const int q = warp & 3, slot = warp >> 2;
         const int m = q * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
-        unsigned long long* list = topk + threadIdx.x;  // [KP][256] keys, this thread's column
+        unsigned long long* list = topk + threadIdx.x;  // [KP][384] keys, this thread's column
 #pragma unroll
-        for (int s = 0; s < KP; s++) list[s * 256] = 0xFFFFFFFFFFFFFFFFull;
+        for (int s = 0; s < KP; s++) list[s * kTcDpThreads] = 0xFFFFFFFFFFFFFFFFull;
         unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
         if (ntiles) mb_wait(a_full, 0);  // |a|^2 block
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t cnt = 0;
         for (uint32_t n = 0; n < ntiles; n++) {
             const int4 segs = __ldg(&p.desc[2 * (t0 + n)]), lens = __ldg(&p.desc[2 * (t0 + n) + 1]);
-            const int seg0 = h ? segs.z : segs.x, seg1 = h ? segs.w : segs.y;
-            const int len0 = h ? lens.z : lens.x, len1 = h ? lens.w : lens.y;
-            float d0[32], d1[32];
+            const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : segs.z;
+            const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : lens.z;
+            const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
+            const uint32_t lane_addr = lane_base + slot * 32;
+            float dA[32], dB[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) d0[j] = INF, d1[j] = INF;
-            float r0 = INF, r1 = INF;
-            for (uint32_t i = 0; i < L; i++, cnt++) {
-                const int slot = cnt % kTcTmemSlots;
-                mb_wait(&t_full[slot], (cnt / kTcTmemSlots) & 1);
+            for (int j = 0; j < 32; j++) dA[j] = INF;
+            float res = INF;
+            for (uint32_t st = 0; st < nsteps; st++, cnt++) {
+                const uint32_t buf = cnt & 1;
+                const uint32_t i = 2 * st;
+                const bool two = i + 1 < L;
+                mb_wait(&t_full[buf], (cnt >> 1) & 1);
                 tc_fence_after();
-                float tm0[32], tm1[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * kTcN + h * 64;
-                const float na = sNa[i * kTcM + m];
-                tc_ld32(taddr, tm0);
-                tc_ld32(taddr + 32, tm1);
+                float tm[32];
+                const uint32_t taddr = lane_addr + buf * kTcBufCols;
+                tc_ld32(taddr, tm);
                 tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mb_arrive(&t_empty[slot]);  // the costs are in registers: hand the TMEM slot back
-                if (i + 1 == L) tc_dp_rows<true>(tm0, tm1, d0, d1, na, len0, len1, i == 0, r0, r1);
-                else tc_dp_rows<false>(tm0, tm1, d0, d1, na, len0, len1, i == 0, r0, r1);
+                if (!two) {  // odd L: the last step carries one row
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(&t_empty[buf]);
+                    tc_dp_row<true>(tm, dA, dB, sNa[i * kTcM + m], len, i == 0, res);
+                } else {
+                    tc_dp_row_fast(tm, dA, dB, sNa[i * kTcM + m], ng, i == 0);
+                    tc_ld32(taddr + kTcN, tm);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(&t_empty[buf]);  // both rows are in registers: hand the TMEM buffer back
+                    if (i + 2 == L) tc_dp_row<true>(tm, dB, dA, sNa[(i + 1) * kTcM + m], len, false, res);
+                    else tc_dp_row_fast(tm, dB, dA, sNa[(i + 1) * kTcM + m], ng, false);
+                }
             }
-            // results: D(L-1, len-1) / (L + len)
-            if (seg0 >= 0) tc_insert<KP>(list, worst, r0 * (1.0f / (float)(L + (uint32_t)len0)), (uint32_t)seg0);
-            if (seg1 >= 0) tc_insert<KP>(list, worst, r1 * (1.0f / (float)(L + (uint32_t)len1)), (uint32_t)seg1);
+            // result: D(L-1, len-1) / (L + len)
+            if (seg >= 0) tc_insert<KP>(list, worst, res * (1.0f / (float)(L + (uint32_t)len)), (uint32_t)seg);
         }
-        unsigned long long* out = p.partial + (((size_t)slice * 2 + h) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
+        unsigned long long* out = p.partial + (((size_t)slice * kTcSlots + slot) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
 #pragma unroll
-        for (int s = 0; s < KP; s++) out[s] = list[s * 256];
+        for (int s = 0; s < KP; s++) out[s] = list[s * kTcDpThreads];
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kTcDpWarps) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -487,16 +565,16 @@ int dtw_tc_dict_build(ss_dict* d) {
     std::vector<int4> desc(2 * (size_t)ntiles);
     d->h_tc_tile_frames.assign(ntiles, 0);
     for (uint32_t t = 0; t < ntiles; t++) {
-        int sg[4], ln[4];
-        for (int s = 0; s < 4; s++) {
-            const size_t o = (size_t)t * 4 + s;
+        int sg[kTcSlots], ln[kTcSlots];
+        for (int s = 0; s < kTcSlots; s++) {
+            const size_t o = (size_t)t * kTcSlots + s;
             sg[s] = o < order.size() ? (int)order[o] : -1;
             ln[s] = o < order.size() ? len_of(order[o]) : 0;
             d->h_tc_tile_frames[t] += (uint32_t)ln[s];
         }
-        // slots 0,1 feed column half 0 and slots 2,3 half 1: interleave so both halves get (longer, shorter) pairs
-        desc[2 * t] = make_int4(sg[0], sg[3], sg[1], sg[2]);
-        desc[2 * t + 1] = make_int4(ln[0], ln[3], ln[1], ln[2]);
+        const int W = 32;
+        desc[2 * t] = make_int4(sg[0], sg[1], sg[2], -1);
+        desc[2 * t + 1] = make_int4(ln[0], ln[1], ln[2], W);
     }
     d->tc_ntiles = ntiles;
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
@@ -523,7 +601,7 @@ int dtw_tc_dict_build(ss_dict* d) {
     while (mx[0] / scale > 16384.f) scale *= 2.f;  // |b|^2 / s must fit fp16 comfortably; s <= 2^16 is exact in fp16
     if (scale > 32768.f) return SS_OK;
     d->tc_nb_scale = scale;
-    SS_CUDA(ctx, d->d_tc_tiles.reserve((size_t)ntiles * kTcTileBytes / 2));
+    SS_CUDA(ctx, d->d_tc_tiles.reserve((size_t)ntiles * kTcBTileBytes / 2));
     k_tc_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_tc_desc.p, ntiles, 1.0f / scale,
                                                      reinterpret_cast<unsigned char*>(d->d_tc_tiles.p));
     SS_LAUNCHED(ctx);
@@ -553,7 +631,7 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
             glen.push_back(L);
             goff.push_back(bytes);
             for (size_t l = 0; l < (size_t)kTcM; l++) gqid.push_back(b + l < end ? order[b + l] : 0xFFFFFFFFu);
-            bytes += (uint64_t)L * (kTcTileBytes + kTcM * 4);
+            bytes += (uint64_t)L * (kTcATileBytes + kTcM * 4);
         }
         pos = end;
     }
@@ -628,7 +706,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     st.push_back(d->tc_ntiles);
     nslices = (uint32_t)st.size() - 1;
     SS_TRY(upload(ctx, d->d_slice_tile, st.data(), st.size()));
-    const uint32_t nlists = nslices * 2;
+    const uint32_t nlists = nslices * kTcSlots;
     SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nlists * nslots * kp));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
     SS_CUDA(ctx, d->d_cand_adist.reserve((size_t)nslots * kp));
@@ -647,7 +725,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     p.nslices = nslices;
     p.partial = d->d_tc_partial.p;
     p.max_len = q->max_len;
-    const size_t smem = (size_t)q->max_len * (kTcTileBytes + kTcM * 4) + kTcStages * kTcTileBytes + 32 * 8 + (size_t)kp * 256 * 8 + 1024;
+    const size_t smem = (size_t)q->max_len * (kTcATileBytes + kTcM * 4) + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kTcDpThreads * 8 + 1024;
     const uint32_t grid = q->tc_ngroups * nslices;
     if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, grid, smem, nlists, nslots, d));
     else SS_TRY(tc_launch<16>(ctx, p, grid, smem, nlists, nslots, d));
