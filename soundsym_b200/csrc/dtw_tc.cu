@@ -372,6 +372,79 @@ __device__ __forceinline__ void tc_dp_row_fast(const float (&tm)[32], const floa
     }
 }
 
+// TWO rows (i, i+1) of one segment slot in column-major order, row state updated in place: cell (i, j) reads d[j]
+// (row i-1) and feeds cell (i+1, j), which overwrites d[j]. Two independent dependency chains per thread (ILP 2), no
+// register copies, no guards: per cell FADD (cost + |a|^2), FMNMX3, FADD.
+template <int NG>
+__device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, bool first_row) {
+    const float INF = __int_as_float(0x7f800000);
+    float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const float up0 = d[j];
+        const float c0 = (tm0[j] + na0) + tc_min3(left0, up0, diag0);
+        const float c1 = (tm1[j] + na1) + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
+        diag0 = up0;
+        left0 = c0;
+        left1 = c1;
+        d[j] = c1;
+    }
+}
+__device__ __forceinline__ void tc_dp_band_fast(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, int ng,
+                                                bool first_row) {
+    switch (ng) {
+        case 1: tc_dp_band_ng<1>(tm0, tm1, d, na0, na1, first_row); break;
+        case 2: tc_dp_band_ng<2>(tm0, tm1, d, na0, na1, first_row); break;
+        case 3: tc_dp_band_ng<3>(tm0, tm1, d, na0, na1, first_row); break;
+        case 4: tc_dp_band_ng<4>(tm0, tm1, d, na0, na1, first_row); break;
+        case 5: tc_dp_band_ng<5>(tm0, tm1, d, na0, na1, first_row); break;
+        case 6: tc_dp_band_ng<6>(tm0, tm1, d, na0, na1, first_row); break;
+        case 7: tc_dp_band_ng<7>(tm0, tm1, d, na0, na1, first_row); break;
+        default: tc_dp_band_ng<8>(tm0, tm1, d, na0, na1, first_row); break;
+    }
+}
+// the band that contains the query's last row (generic, guarded; runs once per tile): captures D(L-1, len-1)
+__device__ __forceinline__ void tc_dp_band_last(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, int len,
+                                                bool first_row, float& res) {
+    const float INF = __int_as_float(0x7f800000);
+    float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+        if (j0 < len) {
+#pragma unroll
+            for (int j = j0; j < j0 + 4; j++) {
+                const float up0 = d[j];
+                const float c0 = (tm0[j] + na0) + tc_min3(left0, up0, diag0);
+                const float c1 = (tm1[j] + na1) + tc_min3(left1, c0, left0);
+                diag0 = up0;
+                left0 = c0;
+                left1 = c1;
+                d[j] = c1;
+                if (j == len - 1) res = c1;
+            }
+        }
+    }
+}
+// a single trailing row (odd query length), in place; captures D(L-1, len-1)
+__device__ __forceinline__ void tc_dp_row_last(const float (&tm)[32], float (&d)[32], float na, int len, bool first_row, float& res) {
+    const float INF = __int_as_float(0x7f800000);
+    float left = INF, diag = first_row ? 0.f : INF;
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+        if (j0 < len) {
+#pragma unroll
+            for (int j = j0; j < j0 + 4; j++) {
+                const float up = d[j];
+                const float cur = (tm[j] + na) + tc_min3(left, up, diag);
+                diag = up;
+                left = cur;
+                d[j] = cur;
+                if (j == len - 1) res = cur;
+            }
+        }
+    }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -466,9 +539,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
             const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : lens.z;
             const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
             const uint32_t lane_addr = lane_base + slot * 32;
-            float dA[32], dB[32];
+            float d[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) dA[j] = INF;
+            for (int j = 0; j < 32; j++) d[j] = INF;
             float res = INF;
             for (uint32_t st = 0; st < nsteps; st++, cnt++) {
                 const uint32_t buf = cnt & 1;
@@ -476,24 +549,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 const bool two = i + 1 < L;
                 mb_wait(&t_full[buf], (cnt >> 1) & 1);
                 tc_fence_after();
-                float tm[32];
+                float tm0[32], tm1[32];
                 const uint32_t taddr = lane_addr + buf * kTcBufCols;
-                tc_ld32(taddr, tm);
+                tc_ld32(taddr, tm0);
+                if (two) tc_ld32(taddr + kTcN, tm1);
                 tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mb_arrive(&t_empty[buf]);  // the costs are in registers: hand the TMEM buffer back
+                const float na0 = sNa[i * kTcM + m];
                 if (!two) {  // odd L: the last step carries one row
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mb_arrive(&t_empty[buf]);
-                    tc_dp_row<true>(tm, dA, dB, sNa[i * kTcM + m], len, i == 0, res);
+                    tc_dp_row_last(tm0, d, na0, len, i == 0, res);
                 } else {
-                    tc_dp_row_fast(tm, dA, dB, sNa[i * kTcM + m], ng, i == 0);
-                    tc_ld32(taddr + kTcN, tm);
-                    tc_wait_ld();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mb_arrive(&t_empty[buf]);  // both rows are in registers: hand the TMEM buffer back
-                    if (i + 2 == L) tc_dp_row<true>(tm, dB, dA, sNa[(i + 1) * kTcM + m], len, false, res);
-                    else tc_dp_row_fast(tm, dB, dA, sNa[(i + 1) * kTcM + m], ng, false);
+                    const float na1 = sNa[(i + 1) * kTcM + m];
+                    if (i + 2 == L) tc_dp_band_last(tm0, tm1, d, na0, na1, len, i == 0, res);
+                    else tc_dp_band_fast(tm0, tm1, d, na0, na1, ng, i == 0);
                 }
             }
             // result: D(L-1, len-1) / (L + len)
