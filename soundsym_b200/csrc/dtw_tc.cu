@@ -372,6 +372,15 @@ __device__ __forceinline__ void tc_dp_row_fast(const float (&tm)[32], const floa
     }
 }
 
+// (x0 + y, x1 + y) with one packed add.f32x2
+__device__ __forceinline__ void tc_add2(float x0, float x1, float y, float& r0, float& r1) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(c));
+}
+
 // TWO rows (i, i+1) of one segment slot in column-major order, row state updated in place: cell (i, j) reads d[j]
 // (row i-1) and feeds cell (i+1, j), which overwrites d[j]. Two independent dependency chains per thread (ILP 2), no
 // register copies, no guards: per cell FADD (cost + |a|^2), FMNMX3, FADD.
@@ -380,27 +389,48 @@ __device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[32], const floa
     const float INF = __int_as_float(0x7f800000);
     float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
 #pragma unroll
-    for (int j = 0; j < 4 * NG; j++) {
-        const float up0 = d[j];
-        const float c0 = (tm0[j] + na0) + tc_min3(left0, up0, diag0);
-        const float c1 = (tm1[j] + na1) + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
-        diag0 = up0;
-        left0 = c0;
-        left1 = c1;
-        d[j] = c1;
+    for (int j = 0; j < 4 * NG; j += 2) {
+        float e0, e1, f0, f1;  // cost + |a|^2 of columns j, j+1 for both rows: two packed adds instead of four
+        tc_add2(tm0[j], tm0[j + 1], na0, e0, e1);
+        tc_add2(tm1[j], tm1[j + 1], na1, f0, f1);
+        {
+            const float up0 = d[j];
+            const float c0 = e0 + tc_min3(left0, up0, diag0);
+            const float c1 = f0 + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
+            diag0 = up0;
+            left0 = c0;
+            left1 = c1;
+            d[j] = c1;
+        }
+        {
+            const float up0 = d[j + 1];
+            const float c0 = e1 + tc_min3(left0, up0, diag0);
+            const float c1 = f1 + tc_min3(left1, c0, left0);
+            diag0 = up0;
+            left0 = c0;
+            left1 = c1;
+            d[j + 1] = c1;
+        }
     }
 }
-__device__ __forceinline__ void tc_dp_band_fast(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, int ng,
-                                                bool first_row) {
-    switch (ng) {
-        case 1: tc_dp_band_ng<1>(tm0, tm1, d, na0, na1, first_row); break;
-        case 2: tc_dp_band_ng<2>(tm0, tm1, d, na0, na1, first_row); break;
-        case 3: tc_dp_band_ng<3>(tm0, tm1, d, na0, na1, first_row); break;
-        case 4: tc_dp_band_ng<4>(tm0, tm1, d, na0, na1, first_row); break;
-        case 5: tc_dp_band_ng<5>(tm0, tm1, d, na0, na1, first_row); break;
-        case 6: tc_dp_band_ng<6>(tm0, tm1, d, na0, na1, first_row); break;
-        case 7: tc_dp_band_ng<7>(tm0, tm1, d, na0, na1, first_row); break;
-        default: tc_dp_band_ng<8>(tm0, tm1, d, na0, na1, first_row); break;
+// all full bands of one tile except the last pipeline step, with the column-group count fixed at compile time
+// (the dispatch happens once per tile, not per step)
+template <int NG>
+__device__ __forceinline__ void tc_fast_steps(uint32_t nfast, uint32_t& cnt, uint64_t* t_full, uint64_t* t_empty, uint32_t lane_addr,
+                                              const float* __restrict__ na_m, int lane, float (&d)[32]) {
+    for (uint32_t st = 0; st < nfast; st++, cnt++) {
+        const uint32_t buf = cnt & 1;
+        mb_wait(&t_full[buf], (cnt >> 1) & 1);
+        tc_fence_after();
+        float tm0[32], tm1[32];
+        const uint32_t taddr = lane_addr + buf * kTcBufCols;
+        tc_ld32(taddr, tm0);
+        tc_ld32(taddr + kTcN, tm1);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mb_arrive(&t_empty[buf]);  // the costs are in registers: hand the TMEM buffer back
+        tc_dp_band_ng<NG>(tm0, tm1, d, na_m[(2 * st) * kTcM], na_m[(2 * st + 1) * kTcM], st == 0);
     }
 }
 // the band that contains the query's last row (generic, guarded; runs once per tile): captures D(L-1, len-1)
@@ -543,9 +573,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 #pragma unroll
             for (int j = 0; j < 32; j++) d[j] = INF;
             float res = INF;
-            for (uint32_t st = 0; st < nsteps; st++, cnt++) {
+            const uint32_t nfast = nsteps - 1;  // every step but the one that holds the query's last row
+            switch (ng) {
+                case 1: tc_fast_steps<1>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                case 2: tc_fast_steps<2>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                case 3: tc_fast_steps<3>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                case 4: tc_fast_steps<4>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                case 5: tc_fast_steps<5>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                case 6: tc_fast_steps<6>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                case 7: tc_fast_steps<7>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+                default: tc_fast_steps<8>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
+            }
+            {   // last step: rows (L-2, L-1) if L is even, else the single row L-1
                 const uint32_t buf = cnt & 1;
-                const uint32_t i = 2 * st;
+                const uint32_t i = 2 * nfast;
                 const bool two = i + 1 < L;
                 mb_wait(&t_full[buf], (cnt >> 1) & 1);
                 tc_fence_after();
@@ -556,15 +597,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mb_arrive(&t_empty[buf]);  // the costs are in registers: hand the TMEM buffer back
+                if (lane == 0) mb_arrive(&t_empty[buf]);
                 const float na0 = sNa[i * kTcM + m];
-                if (!two) {  // odd L: the last step carries one row
-                    tc_dp_row_last(tm0, d, na0, len, i == 0, res);
-                } else {
-                    const float na1 = sNa[(i + 1) * kTcM + m];
-                    if (i + 2 == L) tc_dp_band_last(tm0, tm1, d, na0, na1, len, i == 0, res);
-                    else tc_dp_band_fast(tm0, tm1, d, na0, na1, ng, i == 0);
-                }
+                if (two) tc_dp_band_last(tm0, tm1, d, na0, sNa[(i + 1) * kTcM + m], len, i == 0, res);
+                else tc_dp_row_last(tm0, d, na0, len, i == 0, res);
+                cnt++;
             }
             // result: D(L-1, len-1) / (L + len)
             if (seg >= 0) tc_insert<KP>(list, worst, res * (1.0f / (float)(L + (uint32_t)len)), (uint32_t)seg);
