@@ -355,8 +355,9 @@ def main():
                                  "or the tensor pipe",
                          "issue_bound": {"cells_per_clk_per_sm": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) / 148.0
                                          / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) if scan_ms > 0 else None,
-                                         "ceiling_cells_per_clk_per_sm": 32.0,
-                                         "ceiling_note": "4 issue slots per cell (FADD, FMNMX3, FADD, MOV) on 128 lanes / clk / SM"},
+                                         "ceiling_cells_per_clk_per_sm": 42.7,
+                                         "ceiling_note": "band loop = 1/2 FADD2 + FMNMX3 + FADD per cell: 1.5 FMA-pipe ops per cell at the measured "
+                                                         "64 lanes / clk / SM"},
                          "cells_per_s_kernel": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) if scan_ms > 0 else None},
             "cpu_baseline": cpu,
             "uncertified_queries": int(uncert),

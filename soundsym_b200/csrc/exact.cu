@@ -216,10 +216,14 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
 // DTW refine: exact f64 recurrence on the candidates. One thread per (query slot, candidate); the DP row lives in a
 // global scratch laid out [column][pair] so that neighbouring threads touch neighbouring addresses.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
-                              const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid,
-                              const uint32_t* __restrict__ cand_idx, uint32_t pair_begin, uint32_t pair_end, int kp,
-                              double* __restrict__ rows, uint32_t row_pairs, double* __restrict__ exact) {
+// SMEM_ROWS: segments of <= 32 frames keep the DP row in shared memory ([column][thread], conflict-free) instead of the
+// global scratch.
+template <bool SMEM_ROWS>
+__global__ void __launch_bounds__(128)
+k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+              const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
+              uint32_t pair_begin, uint32_t pair_end, int kp, double* __restrict__ rows, uint32_t row_pairs, double* __restrict__ exact) {
+    __shared__ double srow[SMEM_ROWS ? 32 * 128 : 1];
     const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t pair = pair_begin + local;
     if (pair >= pair_end) return;
@@ -232,7 +236,8 @@ __global__ void k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* 
     const double* a = qmfcc + qoff[qid] * c;
     const double* b = dmfcc + doff[idx] * c;
     const uint32_t la = (uint32_t)(qoff[qid + 1] - qoff[qid]), lb = (uint32_t)(doff[idx + 1] - doff[idx]);
-    double* row = rows + local;
+    double* row = SMEM_ROWS ? srow + threadIdx.x : rows + local;
+    const size_t rstride = SMEM_ROWS ? 128 : row_pairs;
     double last = kInf;
     for (uint32_t i = 0; i < la; i++) {
         double ar[SS_MAX_NCOEFFS];
@@ -247,12 +252,12 @@ __global__ void k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* 
                     const double dlt = ar[k] - b[(size_t)j * c + k];
                     cost = cost + dlt * dlt;
                 }
-            const double up = i ? row[(size_t)j * row_pairs] : kInf;  // D(i-1, j)
+            const double up = i ? row[(size_t)j * rstride] : kInf;  // D(i-1, j)
             double m;
             if (i == 0 && j == 0) m = 0.0;
             else m = fmin(fmin(up, left), diag);
             const double cur = cost + m;
-            row[(size_t)j * row_pairs] = cur;
+            row[(size_t)j * rstride] = cur;
             diag = up;
             left = cur;
         }
@@ -338,7 +343,8 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)batch * max_ld));
     for (uint32_t pb = 0; pb < npairs; pb += batch) {
         const uint32_t pe = std::min<uint32_t>(npairs, pb + batch);
-        k_dtw_rescore<<<ceil_div(pe - pb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
+        auto kern = max_ld <= 32 ? k_dtw_rescore<true> : k_dtw_rescore<false>;
+        kern<<<ceil_div(pe - pb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
                                                                      d_slot_qid, d->d_cand_idx.p, pb, pe, kp,
                                                                      d->d_rescore_rows.p, batch, d->d_cand_exact.p);
         SS_LAUNCHED(ctx);
