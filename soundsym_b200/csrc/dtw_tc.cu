@@ -246,8 +246,9 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
                                  const uint32_t* __restrict__ qid, float scale, unsigned char* __restrict__ a_blocks,
                                  float* __restrict__ max_norm, float* __restrict__ slot_max_na) {
     const uint32_t g = blockIdx.x, m = threadIdx.x;  // blockDim = 128
-    const uint32_t L = group_len[g];
+    const uint32_t L = group_len[g] & 0xFFFFu;       // longest query of the group; shorter ones are zero-padded
     const uint32_t id = qid[g * kTcM + m];
+    const uint32_t Lm = id != 0xFFFFFFFFu ? (uint32_t)(off[id + 1] - off[id]) : 0u;
     unsigned char* blk = a_blocks + group_off[g];
     float* na = reinterpret_cast<float*>(blk + (size_t)L * kTcATileBytes);
     float mx = 0.f;
@@ -256,7 +257,7 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
 #pragma unroll
         for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
         float nrm = 0.f;
-        if (id != 0xFFFFFFFFu) {
+        if (i < Lm) {
             const double* src = mfcc + (off[id] + i) * c;
             for (int k = 0; k < c; k++) {
                 const __half h = __float2half_rn((float)(src[k] - mu[k]));
@@ -284,7 +285,8 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
 struct TcParams {
     const unsigned char* a_blocks;
     const uint64_t* group_off;
-    const uint32_t* group_len;
+    const uint32_t* group_len;   // longest | shortest << 16 query length of each group of 128
+    const uint32_t* slot_len;    // per query slot: its own length (0 = padding lane)
     uint32_t ngroups;
     const unsigned char* tiles;
     const int4* desc;
@@ -433,9 +435,10 @@ __device__ __forceinline__ void tc_fast_steps(uint32_t nfast, uint32_t& cnt, uin
         tc_dp_band_ng<NG>(tm0, tm1, d, na_m[(2 * st) * kTcM], na_m[(2 * st + 1) * kTcM], st == 0);
     }
 }
-// the band that contains the query's last row (generic, guarded; runs once per tile): captures D(L-1, len-1)
+// a band that may contain the last row of some of the CTA's queries (generic, guarded; the group's queries differ in
+// length by a row or two, so this runs for the last one or two steps of a tile): captures D(Lm-1, len-1) per lane
 __device__ __forceinline__ void tc_dp_band_last(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, int len,
-                                                bool first_row, float& res) {
+                                                bool first_row, bool cap0, bool cap1, float& res) {
     const float INF = __int_as_float(0x7f800000);
     float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
 #pragma unroll
@@ -450,13 +453,13 @@ __device__ __forceinline__ void tc_dp_band_last(const float (&tm0)[32], const fl
                 left0 = c0;
                 left1 = c1;
                 d[j] = c1;
-                if (j == len - 1) res = c1;
+                if (j == len - 1) res = cap0 ? c0 : (cap1 ? c1 : res);  // this lane's query may end on either row
             }
         }
     }
 }
 // a single trailing row (odd query length), in place; captures D(L-1, len-1)
-__device__ __forceinline__ void tc_dp_row_last(const float (&tm)[32], float (&d)[32], float na, int len, bool first_row, float& res) {
+__device__ __forceinline__ void tc_dp_row_last(const float (&tm)[32], float (&d)[32], float na, int len, bool first_row, bool cap, float& res) {
     const float INF = __int_as_float(0x7f800000);
     float left = INF, diag = first_row ? 0.f : INF;
 #pragma unroll
@@ -469,7 +472,7 @@ __device__ __forceinline__ void tc_dp_row_last(const float (&tm)[32], float (&d)
                 diag = up;
                 left = cur;
                 d[j] = cur;
-                if (j == len - 1) res = cur;
+                if (j == len - 1 && cap) res = cur;
             }
         }
     }
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
-    const uint32_t L = p.group_len[g];
+    const uint32_t L = p.group_len[g] & 0xFFFFu, Lmin = p.group_len[g] >> 16;  // longest / shortest query of the group
     const uint32_t nsteps = (L + 1) / 2;  // pipeline steps (two rows each) per tile
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
     const uint32_t ntiles = t1 - t0;
@@ -562,6 +565,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
         if (ntiles) mb_wait(a_full, 0);  // |a|^2 block
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
         uint32_t cnt = 0;
         for (uint32_t n = 0; n < ntiles; n++) {
             const int4 segs = __ldg(&p.desc[2 * (t0 + n)]), lens = __ldg(&p.desc[2 * (t0 + n) + 1]);
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 #pragma unroll
             for (int j = 0; j < 32; j++) d[j] = INF;
             float res = INF;
-            const uint32_t nfast = nsteps - 1;  // every step but the one that holds the query's last row
+            const uint32_t nfast = (Lmin - 1) / 2;  // bands that end before any query of the group does
             switch (ng) {
                 case 1: tc_fast_steps<1>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
                 case 2: tc_fast_steps<2>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
@@ -584,9 +588,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 case 7: tc_fast_steps<7>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
                 default: tc_fast_steps<8>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
             }
-            {   // last step: rows (L-2, L-1) if L is even, else the single row L-1
+            for (uint32_t st = nfast; st < nsteps; st++, cnt++) {  // the steps in which queries of the group end
                 const uint32_t buf = cnt & 1;
-                const uint32_t i = 2 * nfast;
+                const uint32_t i = 2 * st;
                 const bool two = i + 1 < L;
                 mb_wait(&t_full[buf], (cnt >> 1) & 1);
                 tc_fence_after();
@@ -599,12 +603,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 __syncwarp();
                 if (lane == 0) mb_arrive(&t_empty[buf]);
                 const float na0 = sNa[i * kTcM + m];
-                if (two) tc_dp_band_last(tm0, tm1, d, na0, sNa[(i + 1) * kTcM + m], len, i == 0, res);
-                else tc_dp_row_last(tm0, d, na0, len, i == 0, res);
-                cnt++;
+                if (two) tc_dp_band_last(tm0, tm1, d, na0, sNa[(i + 1) * kTcM + m], len, i == 0, i + 1 == Lm, i + 2 == Lm, res);
+                else tc_dp_row_last(tm0, d, na0, len, i == 0, i + 1 == Lm, res);
             }
-            // result: D(L-1, len-1) / (L + len)
-            if (seg >= 0) tc_insert<KP>(list, worst, res * (1.0f / (float)(L + (uint32_t)len)), (uint32_t)seg);
+            // result: D(Lm-1, len-1) / (Lm + len)
+            if (seg >= 0 && Lm) tc_insert<KP>(list, worst, res * (1.0f / (float)(Lm + (uint32_t)len)), (uint32_t)seg);
         }
         unsigned long long* out = p.partial + (((size_t)slice * kTcSlots + slot) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
 #pragma unroll
@@ -726,22 +729,23 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
         if (q->h_off[i + 1] > q->h_off[i]) order.push_back((uint32_t)i);
     auto len_of = [&](uint32_t i) { return (uint32_t)(q->h_off[i + 1] - q->h_off[i]); };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
-    std::vector<uint32_t> glen, gqid;
+    // consecutive chunks of 128 queries in length order: a group's queries differ in length by a row or two at most
+    // (the scan pads the shorter ones with zero rows and captures every lane's result at its own last row)
+    std::vector<uint32_t> glen, gqid, slen;
     std::vector<uint64_t> goff;
     uint64_t bytes = 0;
-    size_t pos = 0;
-    while (pos < order.size()) {
-        const uint32_t L = len_of(order[pos]);
-        size_t end = pos;
-        while (end < order.size() && len_of(order[end]) == L) end++;
-        for (size_t b = pos; b < end; b += kTcM) {
-            glen.push_back(L);
-            goff.push_back(bytes);
-            for (size_t l = 0; l < (size_t)kTcM; l++) gqid.push_back(b + l < end ? order[b + l] : 0xFFFFFFFFu);
-            bytes += (uint64_t)L * (kTcATileBytes + kTcM * 4);
+    for (size_t pos = 0; pos < order.size(); pos += kTcM) {
+        const size_t end = std::min(order.size(), pos + (size_t)kTcM);
+        const uint32_t lmax = len_of(order[pos]), lmin = len_of(order[end - 1]);
+        glen.push_back(lmax | (lmin << 16));
+        goff.push_back(bytes);
+        for (size_t l = 0; l < (size_t)kTcM; l++) {
+            gqid.push_back(pos + l < end ? order[pos + l] : 0xFFFFFFFFu);
+            slen.push_back(pos + l < end ? len_of(order[pos + l]) : 0u);
         }
-        pos = end;
+        bytes += (uint64_t)lmax * (kTcATileBytes + kTcM * 4);
     }
+    SS_TRY(upload(ctx, q->d_tc_slot_len, slen.data(), slen.size()));
     q->tc_ngroups = (uint32_t)glen.size();
     q->h_tc_group_len = glen;
     SS_TRY(upload(ctx, q->d_tc_group_len, glen.data(), glen.size()));
@@ -825,6 +829,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     p.a_blocks = q->d_tc_a.p;
     p.group_off = q->d_tc_group_off.p;
     p.group_len = q->d_tc_group_len.p;
+    p.slot_len = q->d_tc_slot_len.p;
     p.ngroups = q->tc_ngroups;
     p.tiles = reinterpret_cast<const unsigned char*>(d->d_tc_tiles.p);
     p.desc = d->d_tc_desc.p;

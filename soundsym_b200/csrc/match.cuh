@@ -103,7 +103,7 @@ struct ss_queries {
     bool tc_built = false;
     uint32_t tc_ngroups = 0;
     std::vector<uint32_t> h_tc_group_len;
-    ss::DevBuf<uint32_t> d_tc_group_len, d_tc_qid;  // qid: ngroups x 128
+    ss::DevBuf<uint32_t> d_tc_group_len, d_tc_qid, d_tc_slot_len;  // qid / slot_len: ngroups x 128
     ss::DevBuf<uint64_t> d_tc_group_off;            // byte offset of each group's [L x 4 KB tiles][L x 128 floats |a|^2] block
     ss::DevBuf<unsigned char> d_tc_a;
     ss::DevBuf<float> d_tc_max_norm;                // [0] = max |fp16(a - mu)|^2
