@@ -16,8 +16,10 @@
 // Warp roles (416 threads, 1 CTA / SM): warps 0-11 = DP (warp w owns TMEM lane quadrant w % 4 and segment slot w / 4);
 // warp 12 = TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and
 // the MMAs. A pipeline step is TWO query rows (two MMAs, one commit) into one of two 192-column TMEM buffers, so the DP
-// warps pay one mbarrier round trip per two rows and ping-pong their row state between two register arrays (row i reads
-// dA and writes dB, row i+1 reads dB and writes dA), which removes every register copy from the recurrence.
+// warps pay one mbarrier round trip per two rows and advance a two-row band in place (cell (i,j) reads d[j] = row i-1 and
+// feeds cell (i+1,j), which overwrites d[j]): two independent dependency chains per thread and no register copies.
+// Queries are grouped 128 at a time in length order; a group's queries may differ in length by a row or two (shorter ones
+// are zero-padded and every lane captures its result at its own last row).
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -117,45 +119,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_ld4(uint32_t taddr, float* v) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
-}
-// loads the 8*w8 columns of the thread's segment slot (w8 = slot width / 8, tile-uniform) with at most two tcgen05.ld.
-// TMEM reads are the scarce resource of this kernel (measured: ~21 cycles per tcgen05.ld plus ~10.6 cycles per KB, SM-wide),
-// so segments are sorted by length, every tile gets the narrowest slot width that fits its three segments, and only
-// those columns are read.
-__device__ __forceinline__ void tc_ld_cols(uint32_t taddr, float (&tm)[32], int w8) {
-    if (w8 >= 4) {
-        tc_ld32(taddr, tm);
-    } else if (w8 == 3) {
-        tc_ld16(taddr, tm);
-        tc_ld8(taddr + 16, tm + 16);
-    } else if (w8 == 2) {
-        tc_ld16(taddr, tm);
-    } else {
-        tc_ld8(taddr, tm);
-    }
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tc_min3(float a, float b, float c) {
@@ -319,58 +282,6 @@ __device__ __forceinline__ void tc_insert(unsigned long long* list, unsigned lon
         }
         list[s * kTcDpThreads] = key;
         worst = list[(KP - 1) * kTcDpThreads];
-    }
-}
-
-// one DP row of one 32-column segment slot: reads the previous row `din`, writes `dout` (ping-pong, so no register
-// copies): per cell FADD (cost + |a|^2), FMNMX3, FADD. Columns run in groups of 4 behind one uniform guard.
-// LAST (the query's final row) also captures D(L-1, len-1).
-template <bool LAST>
-__device__ __forceinline__ void tc_dp_row(const float (&tm)[32], const float (&din)[32], float (&dout)[32], float na, int len, bool first_row,
-                                          float& res) {
-    const float INF = __int_as_float(0x7f800000);
-    float left = INF, diag = first_row ? 0.f : INF;  // D(i, j-1), D(i-1, j-1)
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 4) {
-        if (j0 < len) {
-#pragma unroll
-            for (int j = j0; j < j0 + 4; j++) {
-                const float up = din[j];
-                const float cur = (tm[j] + na) + tc_min3(left, up, diag);
-                dout[j] = cur;
-                left = cur;
-                diag = up;
-                if (LAST && j == len - 1) res = cur;
-            }
-        }
-    }
-}
-
-// the same row with the number of 4-column groups as a compile-time constant: straight-line code, no guards (the
-// per-group uniform branches of the generic version cost a branch-resolve bubble every 4 cells of the dependent chain)
-template <int NG>
-__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[32], const float (&din)[32], float (&dout)[32], float na, bool first_row) {
-    const float INF = __int_as_float(0x7f800000);
-    float left = INF, diag = first_row ? 0.f : INF;
-#pragma unroll
-    for (int j = 0; j < 4 * NG; j++) {
-        const float up = din[j];
-        const float cur = (tm[j] + na) + tc_min3(left, up, diag);
-        dout[j] = cur;
-        left = cur;
-        diag = up;
-    }
-}
-__device__ __forceinline__ void tc_dp_row_fast(const float (&tm)[32], const float (&din)[32], float (&dout)[32], float na, int ng, bool first_row) {
-    switch (ng) {
-        case 1: tc_dp_row_ng<1>(tm, din, dout, na, first_row); break;
-        case 2: tc_dp_row_ng<2>(tm, din, dout, na, first_row); break;
-        case 3: tc_dp_row_ng<3>(tm, din, dout, na, first_row); break;
-        case 4: tc_dp_row_ng<4>(tm, din, dout, na, first_row); break;
-        case 5: tc_dp_row_ng<5>(tm, din, dout, na, first_row); break;
-        case 6: tc_dp_row_ng<6>(tm, din, dout, na, first_row); break;
-        case 7: tc_dp_row_ng<7>(tm, din, dout, na, first_row); break;
-        default: tc_dp_row_ng<8>(tm, din, dout, na, first_row); break;
     }
 }
 
