@@ -39,8 +39,15 @@ __global__ void k_query_lanes64(const double* __restrict__ mfcc, const uint64_t*
     for (uint32_t e = threadIdx.x >> 5; e < n; e += blockDim.x >> 5) dst[(size_t)e * 32] = src ? src[e] : 0.0;
 }
 
-// one thread per (query, dictionary segment) pair: lanes are 32 equal-length queries, the dictionary segment is
-// warp-uniform (broadcast loads). Accumulation order is rulinalg's dot (A9): 8 interleaved partial sums, then the tail.
+// one thread per (query, dictionary segment) pair: lanes are 32 equal-length queries, the dictionary segments are
+// warp-uniform. A CTA stages G = 4 consecutive segments in shared memory (cooperative coalesced load), and every thread
+// walks its query in chunks of 8 values held in registers, feeding the 8 interleaved partial sums of all 4 pairs from one
+// set of query loads and broadcast LDS.128 reads of the segments: ~0.4 load-store operations per product instead of 2,
+// so the FP64 pipe (one DMUL + one DADD per product — products and sums are rounded separately, --fmad=false) bounds the
+// kernel. Accumulation order is rulinalg's dot (A9): p_u += x[8c+u] * y[8c+u] chunk by chunk, then
+// (p0+p4) + (p1+p5) + (p2+p6) + (p3+p7), then the scalar tail — per pair exactly as the CPU path.
+constexpr int kCosG = 4;        // segments in flight per thread
+constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments fall back to global reads)
 __global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff,
                                                      const double* __restrict__ dnorm, int c, const uint32_t* __restrict__ slice_seg,
                                                      uint32_t nslices, const double* __restrict__ qlanes,
@@ -49,47 +56,92 @@ __global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ 
                                                      const uint32_t* __restrict__ group_qid, uint32_t ngroups,
                                                      const double* __restrict__ qnorm, const double* __restrict__ targets,
                                                      double* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
+    __shared__ __align__(16) double sseg[kCosG][kCosSegCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qb = blockIdx.x / nslices, slice = blockIdx.x % nslices;
     const uint32_t g = qb * 4 + warp;
-    if (g >= ngroups) return;
-    const uint32_t qid = group_qid[g * 32 + lane];
-    const size_t kq = (size_t)group_len[g] * c;
-    const double* y = qlanes + (size_t)group_rowbase[g] * c * 32 + lane;
+    const bool active = g < ngroups;
+    const uint32_t qid = active ? group_qid[g * 32 + lane] : 0xFFFFFFFFu;
+    const size_t kq = active ? (size_t)group_len[g] * c : 0;
+    const double* y = active ? qlanes + (size_t)group_rowbase[g] * c * 32 + lane : qlanes;
     const double nq = qid != 0xFFFFFFFFu ? qnorm[qid] : 1.0;
     const double target = (qid != 0xFFFFFFFFu && targets) ? targets[qid] : 1.0;
     double best = 2.0;  // fold((0, 2.0)), src/sound.rs:361
     uint32_t best_idx = 0xFFFFFFFFu;
-    for (uint32_t s = slice_seg[slice]; s < slice_seg[slice + 1]; s++) {
-        const double* x = dmfcc + doff[s] * c;
-        const size_t kd = (size_t)(doff[s + 1] - doff[s]) * c;
-        const size_t len = kd < kq ? kd : kq;
-        double p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
-        size_t e = 0;
-        for (; e + 8 <= len; e += 8) {
-            p0 = p0 + __ldg(x + e + 0) * y[(e + 0) * 32];
-            p1 = p1 + __ldg(x + e + 1) * y[(e + 1) * 32];
-            p2 = p2 + __ldg(x + e + 2) * y[(e + 2) * 32];
-            p3 = p3 + __ldg(x + e + 3) * y[(e + 3) * 32];
-            p4 = p4 + __ldg(x + e + 4) * y[(e + 4) * 32];
-            p5 = p5 + __ldg(x + e + 5) * y[(e + 5) * 32];
-            p6 = p6 + __ldg(x + e + 6) * y[(e + 6) * 32];
-            p7 = p7 + __ldg(x + e + 7) * y[(e + 7) * 32];
+    const uint32_t s_begin = slice_seg[slice], s_end = slice_seg[slice + 1];
+    for (uint32_t s0 = s_begin; s0 < s_end; s0 += kCosG) {
+        const int ng = (int)min((uint32_t)kCosG, s_end - s0);
+        // ---- stage the segments (all 128 threads; segments are contiguous in dmfcc) ---------------------------------
+        __syncthreads();
+        size_t kd[kCosG];
+        const double* xg[kCosG];
+#pragma unroll
+        for (int u = 0; u < kCosG; u++) {
+            kd[u] = u < ng ? (size_t)(doff[s0 + u + 1] - doff[s0 + u]) * c : 0;
+            xg[u] = dmfcc + doff[s0 + min(u, ng - 1)] * c;
+            if (kd[u] <= (size_t)kCosSegCap)
+                for (size_t e = threadIdx.x; e < kd[u]; e += 128) sseg[u][e] = xg[u][e];
         }
-        double sum = 0.0;
-        sum = sum + (p0 + p4);
-        sum = sum + (p1 + p5);
-        sum = sum + (p2 + p6);
-        sum = sum + (p3 + p7);
-        for (; e < len; e++) sum = sum + __ldg(x + e) * y[e * 32];
-        const double nrm = dnorm[s] * nq;     // norm(me) * norm(you), src/sound.rs:30
-        const double sim = sum / nrm;         // src/sound.rs:32
-        const double dist = fabs(sim - target);  // src/sound.rs:359
-        if (dist < best) {                    // strict '<': first minimum wins, NaN never wins (src/sound.rs:362)
-            best = dist;
-            best_idx = s;
+        __syncthreads();
+        if (!active) continue;
+        // ---- chunks of 8 ---------------------------------------------------------------------------------------------
+        double p[kCosG][8];
+        size_t nchunk[kCosG], len[kCosG];
+        size_t maxchunk = 0;
+#pragma unroll
+        for (int u = 0; u < kCosG; u++) {
+            len[u] = kd[u] < kq ? kd[u] : kq;
+            nchunk[u] = len[u] / 8;
+            maxchunk = nchunk[u] > maxchunk ? nchunk[u] : maxchunk;
+#pragma unroll
+            for (int v = 0; v < 8; v++) p[u][v] = 0.0;
+        }
+        for (size_t ch = 0; ch < maxchunk; ch++) {
+            double yv[8];
+#pragma unroll
+            for (int v = 0; v < 8; v++) yv[v] = y[(ch * 8 + v) * 32];
+#pragma unroll
+            for (int u = 0; u < kCosG; u++) {
+                if (ch < nchunk[u]) {  // warp-uniform
+                    if (kd[u] <= (size_t)kCosSegCap) {
+                        const double2* xs = reinterpret_cast<const double2*>(&sseg[u][ch * 8]);
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            const double2 xx = xs[v];
+                            p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
+                            p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 8; v++) p[u][v] = p[u][v] + __ldg(xg[u] + ch * 8 + v) * yv[v];
+                    }
+                }
+            }
+        }
+        // ---- combine, tail, similarity, argmin (segments in index order: first minimum wins) ---------------------------
+#pragma unroll
+        for (int u = 0; u < kCosG; u++) {
+            if (u < ng) {
+                double sum = 0.0;
+                sum = sum + (p[u][0] + p[u][4]);
+                sum = sum + (p[u][1] + p[u][5]);
+                sum = sum + (p[u][2] + p[u][6]);
+                sum = sum + (p[u][3] + p[u][7]);
+                for (size_t e = nchunk[u] * 8; e < len[u]; e++) {
+                    const double xv = kd[u] <= (size_t)kCosSegCap ? sseg[u][e] : __ldg(xg[u] + e);
+                    sum = sum + xv * y[e * 32];
+                }
+                const double nrm = dnorm[s0 + u] * nq;   // norm(me) * norm(you), src/sound.rs:30
+                const double sim = sum / nrm;            // src/sound.rs:32
+                const double dist = fabs(sim - target);  // src/sound.rs:359
+                if (dist < best) {                       // strict '<': first minimum wins, NaN never wins (src/sound.rs:362)
+                    best = dist;
+                    best_idx = s0 + u;
+                }
+            }
         }
     }
+    if (!active) return;
     const size_t o = (size_t)slice * ngroups * 32 + (size_t)g * 32 + lane;
     part_dist[o] = best;
     part_idx[o] = best_idx;

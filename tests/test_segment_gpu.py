@@ -147,3 +147,52 @@ def test_gmm_train_on_device_matches_seeded_oracle(ctx, section71):
     p.train(seed=0)  # Partitioner::train without a supplied model
     lens = p.partition()
     assert int(lens.sum()) == 1978 * 256 and len(lens) > 50
+
+
+def test_config5_reconstruction_synthetic_end_to_end(ctx):
+    """config 5 in miniature: synthetic 44.1 kHz audio, source = first 40 s, target = last 40 s; MFCC -> train on the GPU ->
+    partition source -> dictionary -> partition target with the source's model -> clone_from_dictionary -> to_sound,
+    every stage compared with the oracle run on the same model."""
+    audio = synth.audio(80.0, seed=42)
+    src = api.Sound.from_samples(audio[: 40 * 44100], 44100.0, ctx=ctx)
+    tgt = api.Sound.from_samples(audio[40 * 44100:], 44100.0, ctx=ctx)
+    osrc, otgt = O.mfcc(src.samples()), O.mfcc(tgt.samples())
+    assert np.all(np.abs(src.mfcc_arrays() - osrc) <= 1e-9 * np.maximum(np.abs(osrc), 1.0))
+    part = api.Partitioner(src, ctx).set_threshold(4).set_depth(3)  # examples/reconstruction.rs:43-45
+    part.train(seed=3)
+    model = part.model
+    splits = part.partition()
+    osplits, osym, _ = O.partition(src.mfcc_arrays(), model, 3, 4)  # oracle on the SAME rows and model
+    assert np.array_equal(ctx.symbols(src.mfcc_arrays(), model), osym)
+    assert np.array_equal(splits, osplits) and int(splits.sum()) == src.num_frames() * 256
+    for mode in (SS_COSINE_REF, SS_DTW):
+        dictionary = api.SoundDictionary.from_segments(src, splits, ctx, mode)
+        part.sound = tgt
+        tsplits = part.partition()
+        otsplits, _, _ = O.partition(tgt.mfcc_arrays(), model, 3, 4)
+        assert np.array_equal(tsplits, otsplits)
+        segs, spos, fpos = [], 0, 0
+        for sp in tsplits:
+            sp = int(sp)
+            m = tgt.mfcc_arrays()[fpos:fpos + sp // 256]
+            segs.append(api.Sound(tgt.samples()[spos:spos + sp], 44100.0, m, None, m.mean(axis=0), None, ctx))
+            spos += sp
+            fpos += sp // 256
+        idx, dist = dictionary.match_indices(segs)
+        # the oracle's matcher on the same MFCC rows
+        doff = np.zeros(len(splits) + 1, dtype=np.uint64)
+        doff[1:] = np.cumsum(splits // np.uint64(256))
+        qoff = np.zeros(len(tsplits) + 1, dtype=np.uint64)
+        qoff[1:] = np.cumsum(tsplits // np.uint64(256))
+        dm, qm = src.mfcc_arrays()[: int(doff[-1])], tgt.mfcc_arrays()[: int(qoff[-1])]
+        if mode == SS_COSINE_REF:
+            oi, od = O.cosine_match(dm, doff, qm, qoff, 12)
+            assert np.array_equal(idx[:, 0], oi) and np.array_equal(dist[:, 0], od)
+        else:
+            oi, od = O.dtw_topk(dm, doff, qm, qoff, 12, 1)
+            assert np.array_equal(idx, oi) and np.allclose(dist, od, rtol=1e-12, atol=0)
+        out = api.SoundSequence(segs, ctx).clone_from_dictionary(dictionary).to_sound()
+        soff = np.zeros(len(splits) + 1, dtype=np.uint64)
+        soff[1:] = np.cumsum(splits)
+        ref = O.resynth(src.samples(), soff, idx[:, 0], tsplits)
+        assert np.array_equal(out.samples(), ref) and out.num_frames() == O.frame_count(len(ref))
