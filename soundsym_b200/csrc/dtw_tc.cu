@@ -42,7 +42,7 @@ constexpr int kTcStages = 4;       // B-tile ring
 constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows = 192 TMEM columns; two buffers
 constexpr int kTcMaxLen = 32;
 constexpr int kTcDpWarps = 4 * kTcSlots;             // 12
-constexpr int kTcThreads = (kTcDpWarps + 1) * 32;    // 416
+constexpr int kTcThreads = (kTcDpWarps + 4) * 32;    // 512: three DP warpgroups + one warpgroup holding the producer warp
 constexpr int kTcDpThreads = kTcDpWarps * 32;        // 384
 
 // byte offset of element (row, k) inside a ROWS x 16 fp16 K-major no-swizzle UMMA tile: core matrix = 8 rows x 16 B;
@@ -427,8 +427,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == kTcDpWarps) {
+    // register re-distribution between warpgroups (setmaxnreg): the producer's warpgroup (one working lane, three idle
+    // warps) hands registers to the three DP warpgroups, whose band loop keeps 32 + 64 values live per thread
+    if (warp >= kTcDpWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    }
+    if (warp > kTcDpWarps) {
+        // idle warps of the producer's warpgroup
+    } else if (warp == kTcDpWarps) {
         if (lane == 0 && ntiles) {
             // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------
             const unsigned a_bytes = L * (kTcATileBytes + kTcM * 4);
@@ -467,6 +473,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         }
     } else {
         // ---- DP warps ---------------------------------------------------------------------------------------------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const int q = warp & 3, slot = warp >> 2;
         const int m = q * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
