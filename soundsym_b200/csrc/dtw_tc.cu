@@ -296,42 +296,59 @@ __device__ __forceinline__ void tc_add2(float x0, float x1, float y, float& r0, 
 
 // TWO rows (i, i+1) of one segment slot in column-major order, row state updated in place: cell (i, j) reads d[j]
 // (row i-1) and feeds cell (i+1, j), which overwrites d[j]. Two independent dependency chains per thread (ILP 2), no
-// register copies, no guards: per cell FADD (cost + |a|^2), FMNMX3, FADD.
+// register copies, no guards: per cell 1/2 FADD2 (cost + |a|^2 for two columns), FMNMX3, FADD. The column count 4*NG is a
+// compile-time constant; e0 / e1 return D(i, len-1) / D(i+1, len-1) (len - 1 lies in the last 4-column group, so four
+// uniform selects per row).
 template <int NG>
-__device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, bool first_row) {
+__device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[32], const float (&tm1)[32], float (&d)[4 * NG], float na0, float na1,
+                                              bool first_row, int len, float& e0, float& e1) {
     const float INF = __int_as_float(0x7f800000);
     float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
 #pragma unroll
     for (int j = 0; j < 4 * NG; j += 2) {
-        float e0, e1, f0, f1;  // cost + |a|^2 of columns j, j+1 for both rows: two packed adds instead of four
-        tc_add2(tm0[j], tm0[j + 1], na0, e0, e1);
-        tc_add2(tm1[j], tm1[j + 1], na1, f0, f1);
-        {
-            const float up0 = d[j];
-            const float c0 = e0 + tc_min3(left0, up0, diag0);
-            const float c1 = f0 + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
+        float x0, x1, y0, y1;  // cost + |a|^2 of columns j, j+1 for both rows: two packed adds instead of four
+        tc_add2(tm0[j], tm0[j + 1], na0, x0, x1);
+        tc_add2(tm1[j], tm1[j + 1], na1, y0, y1);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float up0 = d[j + h];
+            const float c0 = (h ? x1 : x0) + tc_min3(left0, up0, diag0);
+            const float c1 = (h ? y1 : y0) + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
             diag0 = up0;
             left0 = c0;
             left1 = c1;
-            d[j] = c1;
-        }
-        {
-            const float up0 = d[j + 1];
-            const float c0 = e1 + tc_min3(left0, up0, diag0);
-            const float c1 = f1 + tc_min3(left1, c0, left0);
-            diag0 = up0;
-            left0 = c0;
-            left1 = c1;
-            d[j + 1] = c1;
+            d[j + h] = c1;
+            if (j + h >= 4 * (NG - 1) && j + h == len - 1) e0 = c0, e1 = c1;
         }
     }
 }
-// all full bands of one tile except the last pipeline step, with the column-group count fixed at compile time
-// (the dispatch happens once per tile, not per step)
+// a single trailing row (odd group length), in place
 template <int NG>
-__device__ __forceinline__ void tc_fast_steps(uint32_t nfast, uint32_t& cnt, uint64_t* t_full, uint64_t* t_empty, uint32_t lane_addr,
-                                              const float* __restrict__ na_m, int lane, float (&d)[32]) {
-    for (uint32_t st = 0; st < nfast; st++, cnt++) {
+__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[32], float (&d)[4 * NG], float na, bool first_row, int len, float& e0) {
+    const float INF = __int_as_float(0x7f800000);
+    float left = INF, diag = first_row ? 0.f : INF;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const float up = d[j];
+        const float cur = (tm[j] + na) + tc_min3(left, up, diag);
+        diag = up;
+        left = cur;
+        d[j] = cur;
+        if (j >= 4 * (NG - 1) && j == len - 1) e0 = cur;
+    }
+}
+// one dictionary tile for one thread (= one query x one segment slot), column-group count NG fixed at compile time so
+// that the whole step loop is straight-line code over exactly 4*NG row-state registers. Returns D(Lm-1, len-1).
+template <int NG>
+__device__ __forceinline__ float tc_tile(uint32_t L, uint32_t Lm, int len, uint32_t& cnt, uint64_t* t_full, uint64_t* t_empty, uint32_t lane_addr,
+                                         const float* __restrict__ na_m, int lane) {
+    const float INF = __int_as_float(0x7f800000);
+    float d[4 * NG];
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) d[j] = INF;
+    float res = INF;
+    const uint32_t nfull = L >> 1;  // steps that carry two rows
+    for (uint32_t st = 0; st < nfull; st++, cnt++) {
         const uint32_t buf = cnt & 1;
         mb_wait(&t_full[buf], (cnt >> 1) & 1);
         tc_fence_after();
@@ -343,50 +360,26 @@ __device__ __forceinline__ void tc_fast_steps(uint32_t nfast, uint32_t& cnt, uin
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mb_arrive(&t_empty[buf]);  // the costs are in registers: hand the TMEM buffer back
-        tc_dp_band_ng<NG>(tm0, tm1, d, na_m[(2 * st) * kTcM], na_m[(2 * st + 1) * kTcM], st == 0);
+        float e0 = INF, e1 = INF;
+        tc_dp_band_ng<NG>(tm0, tm1, d, na_m[(2 * st) * kTcM], na_m[(2 * st + 1) * kTcM], st == 0, len, e0, e1);
+        res = (2 * st + 1 == Lm) ? e0 : ((2 * st + 2 == Lm) ? e1 : res);  // this lane's query ends in this band?
     }
-}
-// a band that may contain the last row of some of the CTA's queries (generic, guarded; the group's queries differ in
-// length by a row or two, so this runs for the last one or two steps of a tile): captures D(Lm-1, len-1) per lane
-__device__ __forceinline__ void tc_dp_band_last(const float (&tm0)[32], const float (&tm1)[32], float (&d)[32], float na0, float na1, int len,
-                                                bool first_row, bool cap0, bool cap1, float& res) {
-    const float INF = __int_as_float(0x7f800000);
-    float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 4) {
-        if (j0 < len) {
-#pragma unroll
-            for (int j = j0; j < j0 + 4; j++) {
-                const float up0 = d[j];
-                const float c0 = (tm0[j] + na0) + tc_min3(left0, up0, diag0);
-                const float c1 = (tm1[j] + na1) + tc_min3(left1, c0, left0);
-                diag0 = up0;
-                left0 = c0;
-                left1 = c1;
-                d[j] = c1;
-                if (j == len - 1) res = cap0 ? c0 : (cap1 ? c1 : res);  // this lane's query may end on either row
-            }
-        }
+    if (L & 1) {  // odd group length: the last step carries one row
+        const uint32_t buf = cnt & 1;
+        mb_wait(&t_full[buf], (cnt >> 1) & 1);
+        tc_fence_after();
+        float tm0[32];
+        tc_ld32(lane_addr + buf * kTcBufCols, tm0);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mb_arrive(&t_empty[buf]);
+        float e0 = INF;
+        tc_dp_row_ng<NG>(tm0, d, na_m[(L - 1) * kTcM], L == 1, len, e0);
+        res = (L == Lm) ? e0 : res;
+        cnt++;
     }
-}
-// a single trailing row (odd query length), in place; captures D(L-1, len-1)
-__device__ __forceinline__ void tc_dp_row_last(const float (&tm)[32], float (&d)[32], float na, int len, bool first_row, bool cap, float& res) {
-    const float INF = __int_as_float(0x7f800000);
-    float left = INF, diag = first_row ? 0.f : INF;
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 4) {
-        if (j0 < len) {
-#pragma unroll
-            for (int j = j0; j < j0 + 4; j++) {
-                const float up = d[j];
-                const float cur = (tm[j] + na) + tc_min3(left, up, diag);
-                diag = up;
-                left = cur;
-                d[j] = cur;
-                if (j == len - 1 && cap) res = cur;
-            }
-        }
-    }
+    return res;
 }
 
 template <int KP>
@@ -408,7 +401,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
-    const uint32_t L = p.group_len[g] & 0xFFFFu, Lmin = p.group_len[g] >> 16;  // longest / shortest query of the group
+    const uint32_t L = p.group_len[g] & 0xFFFFu;  // longest query of the group (rows of the A block)
     const uint32_t nsteps = (L + 1) / 2;  // pipeline steps (two rows each) per tile
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
     const uint32_t ntiles = t1 - t0;
@@ -491,38 +484,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
             const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : lens.z;
             const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
             const uint32_t lane_addr = lane_base + slot * 32;
-            float d[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) d[j] = INF;
-            float res = INF;
-            const uint32_t nfast = (Lmin - 1) / 2;  // bands that end before any query of the group does
-            switch (ng) {
-                case 1: tc_fast_steps<1>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                case 2: tc_fast_steps<2>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                case 3: tc_fast_steps<3>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                case 4: tc_fast_steps<4>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                case 5: tc_fast_steps<5>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                case 6: tc_fast_steps<6>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                case 7: tc_fast_steps<7>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-                default: tc_fast_steps<8>(nfast, cnt, t_full, t_empty, lane_addr, sNa + m, lane, d); break;
-            }
-            for (uint32_t st = nfast; st < nsteps; st++, cnt++) {  // the steps in which queries of the group end
-                const uint32_t buf = cnt & 1;
-                const uint32_t i = 2 * st;
-                const bool two = i + 1 < L;
-                mb_wait(&t_full[buf], (cnt >> 1) & 1);
-                tc_fence_after();
-                float tm0[32], tm1[32];
-                const uint32_t taddr = lane_addr + buf * kTcBufCols;
-                tc_ld32(taddr, tm0);
-                if (two) tc_ld32(taddr + kTcN, tm1);
-                tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mb_arrive(&t_empty[buf]);
-                const float na0 = sNa[i * kTcM + m];
-                if (two) tc_dp_band_last(tm0, tm1, d, na0, sNa[(i + 1) * kTcM + m], len, i == 0, i + 1 == Lm, i + 2 == Lm, res);
-                else tc_dp_row_last(tm0, d, na0, len, i == 0, i + 1 == Lm, res);
+            float res;
+            switch (ng) {  // one dispatch per tile
+                case 1: res = tc_tile<1>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 2: res = tc_tile<2>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 3: res = tc_tile<3>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 4: res = tc_tile<4>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 5: res = tc_tile<5>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 6: res = tc_tile<6>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 7: res = tc_tile<7>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                default: res = tc_tile<8>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
             }
             // result: D(Lm-1, len-1) / (Lm + len)
             if (seg >= 0 && Lm) tc_insert<KP>(list, worst, res * (1.0f / (float)(Lm + (uint32_t)len)), (uint32_t)seg);
