@@ -5,13 +5,15 @@
 // Idea: the local-cost matrix is a K = 13 contraction, c(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j. One tcgen05.mma per
 // (dictionary tile, query row i) computes, for the CTA's 128 queries at once, the costs of row i against the 96 columns
 // of the tile (3 segment slots x 32 columns):
-//     D[m, n] = sum_k A_i[m, k] * B[n, k],   A_i[m, :] = [-2 a^(m)_i (13), s, s, 0]   (fp16, K-major, no swizzle)
-//                                            B[n, :]   = [ b_n (13), (|b_n|^2/s)_hi, (|b_n|^2/s)_lo, 0 ]
-// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 96 columns, K = 16 = one MMA). TMEM lane m is
-// read back by the threads that own query m (tcgen05.ld 32x32b), which add |a_i|^2 and run the DP recurrence for one
-// segment slot each with the row state in registers:  FADD + FMNMX3 + FADD per cell instead of the fp32 scan's
-// 7 FFMA2 + 2 FADD + FMNMX3. Both sides are centred on the dictionary's mean frame before the fp16 conversion (the cost
-// is translation invariant).
+//     D[m, n] = sum_k A_i[m, k] * B[n, k],   A_i[m, :] = [-2 a^(m)_i (13), s, s, rd(|a_i|^2 / s)]   (fp16, K-major, no swizzle)
+//                                            B[n, :]   = [ b_n (13), (|b_n|^2/s)_hi, (|b_n|^2/s)_lo, s ]
+// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 96 columns, K = 16 = one MMA). The WHOLE local cost
+// comes out of the tensor core: |b|^2 as a hi + lo pair, |a|^2 in the one spare K slot ROUNDED DOWN to fp16, so the scan's
+// cost is <= the cost of the fp16-rounded frames (by at most 2^-10 |a|^2) and the scan distance stays a LOWER bound of
+// their DTW - which is all the certification in k_dtw_finalize needs (a slightly blunter filter, the same proof). TMEM lane
+// m is read back by the threads that own query m (tcgen05.ld 32x32b), which run the DP recurrence for one segment slot
+// each with the row state in registers: FMNMX3 + FADD per cell instead of the fp32 scan's 7 FFMA2 + 2 FADD + FMNMX3.
+// Both sides are centred on the dictionary's mean frame before the fp16 conversion (the cost is translation invariant).
 //
 // Warp roles (416 threads, 1 CTA / SM): warps 0-11 = DP (warp w owns TMEM lane quadrant w % 4 and segment slot w / 4);
 // warp 12 = TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and
@@ -66,6 +68,23 @@ __device__ __forceinline__ void mb_arrive(uint64_t* bar) { asm volatile("mbarrie
 // (measured: 33 issued instructions per cell with a plain try_wait loop).
 __device__ __forceinline__ void mb_wait(uint64_t* bar, unsigned parity) {
     const uint32_t addr = s32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
+}
+__device__ __forceinline__ void mb_arrive_addr(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void mb_wait_addr(uint32_t addr, unsigned parity) {
     for (;;) {
         uint32_t done;
         asm volatile(
@@ -174,7 +193,7 @@ __global__ void k_tc_dict_maxnorm(const double* __restrict__ mfcc, size_t frames
 }
 // one thread per (tile, column n): writes row n of the tile's B operand
 __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
-                                const int4* __restrict__ desc, uint32_t ntiles, float inv_scale, unsigned char* __restrict__ tiles) {
+                                const int4* __restrict__ desc, uint32_t ntiles, float scale, unsigned char* __restrict__ tiles) {
     const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = kTcN
     if (t >= ntiles) return;
     const int4 segs = desc[2 * t], lens = desc[2 * t + 1];
@@ -194,16 +213,17 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
             const float v = __half2float(h);
             nrm += v * v;
         }
-        const float sn = nrm * inv_scale;
+        const float sn = nrm * (1.0f / scale);  // s is a power of two: exact
         const __half hi = __float2half_rn(sn);
         row[13] = hi;
         row[14] = __float2half_rn(sn - __half2float(hi));
+        row[15] = __float2half_rn(scale);  // multiplies the query side's rd(|a|^2 / s)
     }
     unsigned char* base = tiles + (size_t)t * kTcBTileBytes;
 #pragma unroll
     for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcN>((int)n, k)) = row[k];
 }
-// one thread per (group, row i, query m): A_i[m, :] and |a_i|^2
+// one thread per (group, query m), all rows i: A_i[m, :] = [-2 (a_i - mu) (13), s, s, rd(|a_i|^2 / s)]
 __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
                                  const uint32_t* __restrict__ group_len, const uint64_t* __restrict__ group_off,
                                  const uint32_t* __restrict__ qid, float scale, unsigned char* __restrict__ a_blocks,
@@ -213,7 +233,7 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
     const uint32_t id = qid[g * kTcM + m];
     const uint32_t Lm = id != 0xFFFFFFFFu ? (uint32_t)(off[id + 1] - off[id]) : 0u;
     unsigned char* blk = a_blocks + group_off[g];
-    float* na = reinterpret_cast<float*>(blk + (size_t)L * kTcATileBytes);
+    const float inv_scale = 1.0f / scale;  // power of two: exact
     float mx = 0.f;
     for (uint32_t i = 0; i < L; i++) {
         __half row[kTcK];
@@ -230,11 +250,13 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
             }
             row[13] = __float2half_rn(scale);
             row[14] = __float2half_rn(scale);
+            // |a_i|^2 rides in the spare K slot, rounded DOWN: the scan cost never exceeds the cost of the rounded frames
+            // (the host keeps the fp32 scan when max |a|^2 / s would leave the fp16 range)
+            row[15] = __float2half_rd(fminf(nrm * inv_scale, 65504.f));
         }
         unsigned char* base = blk + (size_t)i * kTcATileBytes;
 #pragma unroll
         for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcM>((int)m, k)) = row[k];
-        na[(size_t)i * kTcM + m] = nrm;
         mx = fmaxf(mx, nrm);
     }
     slot_max_na[g * kTcM + m] = mx;
@@ -285,99 +307,149 @@ __device__ __forceinline__ void tc_insert(unsigned long long* list, unsigned lon
     }
 }
 
-// (x0 + y, x1 + y) with one packed add.f32x2
-__device__ __forceinline__ void tc_add2(float x0, float x1, float y, float& r0, float& r1) {
-    unsigned long long a, b, c;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(y));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(c));
+// TMEM -> registers: W (8 / 16 / 32) consecutive columns of this thread's lane
+template <int W>
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tc_ld<8>(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tc_ld<16>(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tc_ld<32>(uint32_t taddr, float* v) { tc_ld32(taddr, v); }
+// the 4*NG columns of one row, with the narrowest loads that cover them
+template <int NG>
+__device__ __forceinline__ void tc_ld_row(uint32_t taddr, float (&v)[4 * NG]) {
+    if constexpr (NG == 2 || NG == 4 || NG == 8) {
+        tc_ld<4 * NG>(taddr, v);
+    } else if constexpr (NG == 6) {
+        tc_ld<16>(taddr, v);
+        tc_ld<8>(taddr + 16, v + 16);
+    } else {  // 1, 3, 5, 7: load the next even group count into a scratch of that width
+        float t[4 * (NG + 1)];
+        tc_ld_row<NG + 1>(taddr, t);
+#pragma unroll
+        for (int j = 0; j < 4 * NG; j++) v[j] = t[j];
+    }
 }
 
 // TWO rows (i, i+1) of one segment slot in column-major order, row state updated in place: cell (i, j) reads d[j]
 // (row i-1) and feeds cell (i+1, j), which overwrites d[j]. Two independent dependency chains per thread (ILP 2), no
-// register copies, no guards: per cell 1/2 FADD2 (cost + |a|^2 for two columns), FMNMX3, FADD. The column count 4*NG is a
-// compile-time constant; e0 / e1 return D(i, len-1) / D(i+1, len-1) (len - 1 lies in the last 4-column group, so four
-// uniform selects per row).
-template <int NG>
-__device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[32], const float (&tm1)[32], float (&d)[4 * NG], float na0, float na1,
-                                              bool first_row, int len, float& e0, float& e1) {
+// register copies, no guards: per cell FMNMX3 + FADD. The column count 4*NG is a compile-time constant. With CAP, e0 / e1
+// return D(i, len-1) / D(i+1, len-1) (len - 1 lies in the last 4-column group: four uniform selects per row); the
+// capture-free instantiation runs in every step that cannot hold the last row of any of the group's queries.
+template <int NG, bool CAP>
+__device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[4 * NG], const float (&tm1)[4 * NG], float (&d)[4 * NG], float dinit, int len,
+                                              float& e0, float& e1) {
     const float INF = __int_as_float(0x7f800000);
-    float left0 = INF, diag0 = first_row ? 0.f : INF, left1 = INF;
+    float left0 = INF, diag0 = dinit, left1 = INF;  // dinit = 0 on the first row of the pair (the virtual D(-1,-1)), +inf after
 #pragma unroll
-    for (int j = 0; j < 4 * NG; j += 2) {
-        float x0, x1, y0, y1;  // cost + |a|^2 of columns j, j+1 for both rows: two packed adds instead of four
-        tc_add2(tm0[j], tm0[j + 1], na0, x0, x1);
-        tc_add2(tm1[j], tm1[j + 1], na1, y0, y1);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const float up0 = d[j + h];
-            const float c0 = (h ? x1 : x0) + tc_min3(left0, up0, diag0);
-            const float c1 = (h ? y1 : y0) + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
-            diag0 = up0;
-            left0 = c0;
-            left1 = c1;
-            d[j + h] = c1;
-            if (j + h >= 4 * (NG - 1) && j + h == len - 1) e0 = c0, e1 = c1;
-        }
+    for (int j = 0; j < 4 * NG; j++) {
+        const float up0 = d[j];
+        const float c0 = tm0[j] + tc_min3(left0, up0, diag0);
+        const float c1 = tm1[j] + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
+        diag0 = up0;
+        left0 = c0;
+        left1 = c1;
+        d[j] = c1;
+        if (CAP && j >= 4 * (NG - 1) && j == len - 1) e0 = c0, e1 = c1;
     }
 }
 // a single trailing row (odd group length), in place
 template <int NG>
-__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[32], float (&d)[4 * NG], float na, bool first_row, int len, float& e0) {
+__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[4 * NG], float (&d)[4 * NG], float dinit, int len, float& e0) {
     const float INF = __int_as_float(0x7f800000);
-    float left = INF, diag = first_row ? 0.f : INF;
+    float left = INF, diag = dinit;
 #pragma unroll
     for (int j = 0; j < 4 * NG; j++) {
         const float up = d[j];
-        const float cur = (tm[j] + na) + tc_min3(left, up, diag);
+        const float cur = tm[j] + tc_min3(left, up, diag);
         diag = up;
         left = cur;
         d[j] = cur;
         if (j >= 4 * (NG - 1) && j == len - 1) e0 = cur;
     }
 }
+
+// consumer side of the TMEM double buffer: which buffer is next and the parity of its "full" barrier
+struct TcCursor {
+    uint32_t buf, par;
+    uint32_t full0, empty0;  // shared-memory addresses of t_full[0] / t_empty[0]
+};
+
+// one pipeline step for one thread: wait for the step's MMAs, pull this slot's columns of both rows into registers, hand
+// the TMEM buffer back, advance the band
+template <int NG, bool CAP>
+__device__ __forceinline__ void tc_step2(TcCursor& cur, uint32_t lane_addr, bool lane0, float (&d)[4 * NG], float dinit, int len, float& e0,
+                                         float& e1) {
+    mb_wait_addr(cur.full0 + cur.buf * 8, cur.par);
+    tc_fence_after();
+    float tm0[4 * NG], tm1[4 * NG];
+    const uint32_t taddr = lane_addr + cur.buf * kTcBufCols;
+    tc_ld_row<NG>(taddr, tm0);
+    tc_ld_row<NG>(taddr + kTcN, tm1);
+    tc_wait_ld();
+    tc_fence_before();
+    __syncwarp();
+    if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);  // the costs are in registers: hand the TMEM buffer back
+    cur.par ^= cur.buf;
+    cur.buf ^= 1;
+    tc_dp_band_ng<NG, CAP>(tm0, tm1, d, dinit, len, e0, e1);
+}
+
 // one dictionary tile for one thread (= one query x one segment slot), column-group count NG fixed at compile time so
 // that the whole step loop is straight-line code over exactly 4*NG row-state registers. Returns D(Lm-1, len-1).
+// L = longest, lmin = shortest query of the CTA's group, Lm = this lane's own.
 template <int NG>
-__device__ __forceinline__ float tc_tile(uint32_t L, uint32_t Lm, int len, uint32_t& cnt, uint64_t* t_full, uint64_t* t_empty, uint32_t lane_addr,
-                                         const float* __restrict__ na_m, int lane) {
+__device__ __forceinline__ float tc_tile(uint32_t L, uint32_t lmin, uint32_t Lm, int len, TcCursor& cur, uint32_t lane_addr, bool lane0) {
     const float INF = __int_as_float(0x7f800000);
     float d[4 * NG];
 #pragma unroll
     for (int j = 0; j < 4 * NG; j++) d[j] = INF;
-    float res = INF;
-    const uint32_t nfull = L >> 1;  // steps that carry two rows
-    for (uint32_t st = 0; st < nfull; st++, cnt++) {
-        const uint32_t buf = cnt & 1;
-        mb_wait(&t_full[buf], (cnt >> 1) & 1);
-        tc_fence_after();
-        float tm0[32], tm1[32];
-        const uint32_t taddr = lane_addr + buf * kTcBufCols;
-        tc_ld32(taddr, tm0);
-        tc_ld32(taddr + kTcN, tm1);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mb_arrive(&t_empty[buf]);  // the costs are in registers: hand the TMEM buffer back
+    float res = INF, dinit = 0.f;
+    const uint32_t nfull = L >> 1;                       // steps that carry two rows
+    const uint32_t ncap = min((lmin - 1) >> 1, nfull);   // steps before any query of the group can end
+    uint32_t st = 0;
+    for (; st < ncap; st++) {
+        float e0, e1;
+        tc_step2<NG, false>(cur, lane_addr, lane0, d, dinit, len, e0, e1);
+        dinit = INF;
+    }
+    for (; st < nfull; st++) {
         float e0 = INF, e1 = INF;
-        tc_dp_band_ng<NG>(tm0, tm1, d, na_m[(2 * st) * kTcM], na_m[(2 * st + 1) * kTcM], st == 0, len, e0, e1);
+        tc_step2<NG, true>(cur, lane_addr, lane0, d, dinit, len, e0, e1);
+        dinit = INF;
         res = (2 * st + 1 == Lm) ? e0 : ((2 * st + 2 == Lm) ? e1 : res);  // this lane's query ends in this band?
     }
     if (L & 1) {  // odd group length: the last step carries one row
-        const uint32_t buf = cnt & 1;
-        mb_wait(&t_full[buf], (cnt >> 1) & 1);
+        mb_wait_addr(cur.full0 + cur.buf * 8, cur.par);
         tc_fence_after();
-        float tm0[32];
-        tc_ld32(lane_addr + buf * kTcBufCols, tm0);
+        float tm0[4 * NG];
+        tc_ld_row<NG>(lane_addr + cur.buf * kTcBufCols, tm0);
         tc_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mb_arrive(&t_empty[buf]);
+        if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);
+        cur.par ^= cur.buf;
+        cur.buf ^= 1;
         float e0 = INF;
-        tc_dp_row_ng<NG>(tm0, d, na_m[(L - 1) * kTcM], L == 1, len, e0);
+        tc_dp_row_ng<NG>(tm0, d, dinit, len, e0);
         res = (L == Lm) ? e0 : res;
-        cnt++;
     }
     return res;
 }
@@ -385,11 +457,10 @@ __device__ __forceinline__ float tc_tile(uint32_t L, uint32_t Lm, int len, uint3
 template <int KP>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    // [A tiles: max_len x 4 KB][|a|^2: max_len x 512 B][B ring: 4 x 3 KB][barriers][candidate lists], 128-byte aligned
+    // [A tiles: max_len x 4 KB][B ring: 4 x 3 KB][barriers][candidate lists], 128-byte aligned
     unsigned char* smem = smem_raw + ((128u - (s32(smem_raw) & 127u)) & 127u);
     unsigned char* sA = smem;
-    float* sNa = reinterpret_cast<float*>(smem + (size_t)p.max_len * kTcATileBytes);
-    unsigned char* sB = smem + (size_t)p.max_len * (kTcATileBytes + kTcM * 4);
+    unsigned char* sB = smem + (size_t)p.max_len * kTcATileBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcBTileBytes);
     uint64_t* a_full = bars;
     uint64_t* b_full = bars + 1;
@@ -401,7 +472,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
-    const uint32_t L = p.group_len[g] & 0xFFFFu;  // longest query of the group (rows of the A block)
+    const uint32_t glen = p.group_len[g];
+    const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;  // longest (= rows of the A block) and shortest query of the group
     const uint32_t nsteps = (L + 1) / 2;  // pipeline steps (two rows each) per tile
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
     const uint32_t ntiles = t1 - t0;
@@ -423,19 +495,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     // register re-distribution between warpgroups (setmaxnreg): the producer's warpgroup (one working lane, three idle
     // warps) hands registers to the three DP warpgroups, whose band loop keeps 32 + 64 values live per thread
     if (warp >= kTcDpWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     }
     if (warp > kTcDpWarps) {
         // idle warps of the producer's warpgroup
     } else if (warp == kTcDpWarps) {
         if (lane == 0 && ntiles) {
             // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------
-            const unsigned a_bytes = L * (kTcATileBytes + kTcM * 4);
-            mb_expect_tx(a_full, a_bytes);
-            const unsigned char* ablk = p.a_blocks + p.group_off[g];
-            // tiles and |a|^2 are contiguous in global memory but land in two smem regions
-            tma_g2s(sA, ablk, L * kTcATileBytes, a_full);
-            tma_g2s(sNa, ablk + (size_t)L * kTcATileBytes, L * kTcM * 4, a_full);
+            mb_expect_tx(a_full, L * kTcATileBytes);
+            tma_g2s(sA, p.a_blocks + p.group_off[g], L * kTcATileBytes, a_full);
             for (uint32_t n = 0; n < ntiles && n < (uint32_t)kTcStages; n++) {
                 mb_expect_tx(&b_full[n], kTcBTileBytes);
                 tma_g2s(sB + n * kTcBTileBytes, p.tiles + (size_t)(t0 + n) * kTcBTileBytes, kTcBTileBytes, &b_full[n]);
@@ -469,31 +537,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const int q = warp & 3, slot = warp >> 2;
         const int m = q * 32 + lane;
-        const float INF = __int_as_float(0x7f800000);
         unsigned long long* list = topk + threadIdx.x;  // [KP][384] keys, this thread's column
 #pragma unroll
         for (int s = 0; s < KP; s++) list[s * kTcDpThreads] = 0xFFFFFFFFFFFFFFFFull;
         unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
-        if (ntiles) mb_wait(a_full, 0);  // |a|^2 block
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 32;
         const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
-        uint32_t cnt = 0;
+        TcCursor cur;
+        cur.buf = 0, cur.par = 0;
+        cur.full0 = s32(t_full), cur.empty0 = s32(t_empty);
+        const bool lane0 = lane == 0;
         for (uint32_t n = 0; n < ntiles; n++) {
             const int4 segs = __ldg(&p.desc[2 * (t0 + n)]), lens = __ldg(&p.desc[2 * (t0 + n) + 1]);
             const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : segs.z;
             const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : lens.z;
             const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
-            const uint32_t lane_addr = lane_base + slot * 32;
             float res;
             switch (ng) {  // one dispatch per tile
-                case 1: res = tc_tile<1>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                case 2: res = tc_tile<2>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                case 3: res = tc_tile<3>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                case 4: res = tc_tile<4>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                case 5: res = tc_tile<5>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                case 6: res = tc_tile<6>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                case 7: res = tc_tile<7>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
-                default: res = tc_tile<8>(L, Lm, len, cnt, t_full, t_empty, lane_addr, sNa + m, lane); break;
+                case 1: res = tc_tile<1>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 2: res = tc_tile<2>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 3: res = tc_tile<3>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 4: res = tc_tile<4>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 5: res = tc_tile<5>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 6: res = tc_tile<6>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 7: res = tc_tile<7>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                default: res = tc_tile<8>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
             }
             // result: D(Lm-1, len-1) / (Lm + len)
             if (seg >= 0 && Lm) tc_insert<KP>(list, worst, res * (1.0f / (float)(Lm + (uint32_t)len)), (uint32_t)seg);
@@ -601,17 +669,19 @@ int dtw_tc_dict_build(ss_dict* d) {
     if (scale > 32768.f) return SS_OK;
     d->tc_nb_scale = scale;
     SS_CUDA(ctx, d->d_tc_tiles.reserve((size_t)ntiles * kTcBTileBytes / 2));
-    k_tc_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_tc_desc.p, ntiles, 1.0f / scale,
+    k_tc_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_tc_desc.p, ntiles, scale,
                                                      reinterpret_cast<unsigned char*>(d->d_tc_tiles.p));
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    static uint64_t serial = 0;
+    d->tc_serial = ++serial;
     d->tc_ready = true;
     return SS_OK;
 }
 
 static int tc_queries_build(ss_dict* d, ss_queries* q) {
     ss_ctx* ctx = q->ctx;
-    if (q->tc_built) return SS_OK;
+    if (q->tc_built && q->tc_dict_serial == d->tc_serial) return SS_OK;  // the A blocks depend on the dictionary's mean frame and scale
     std::vector<uint32_t> order;
     order.reserve(q->nq);
     for (size_t i = 0; i < q->nq; i++)
@@ -632,7 +702,7 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
             gqid.push_back(pos + l < end ? order[pos + l] : 0xFFFFFFFFu);
             slen.push_back(pos + l < end ? len_of(order[pos + l]) : 0u);
         }
-        bytes += (uint64_t)lmax * (kTcATileBytes + kTcM * 4);
+        bytes += (uint64_t)lmax * kTcATileBytes;
     }
     SS_TRY(upload(ctx, q->d_tc_slot_len, slen.data(), slen.size()));
     q->tc_ngroups = (uint32_t)glen.size();
@@ -651,8 +721,13 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
                                                                  q->d_tc_max_norm.p, q->d_tc_slot_max_na.p);
         SS_LAUNCHED(ctx);
     }
+    float qmx = 0.f;
+    SS_CUDA(ctx, cudaMemcpyAsync(&qmx, q->d_tc_max_norm.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    // rd(|a|^2 / s) must stay inside the fp16 range (queries far louder than the dictionary keep the fp32 scan)
+    q->tc_ok = qmx / d->tc_nb_scale < 60000.f;
     q->tc_built = true;
+    q->tc_dict_serial = d->tc_serial;
     return SS_OK;
 }
 
@@ -679,7 +754,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     }
     if (!enabled || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
     SS_TRY(tc_queries_build(d, q));
-    if (!q->tc_ngroups) return SS_OK;
+    if (!q->tc_ngroups || !q->tc_ok) return SS_OK;
     const int kp = k <= 2 ? 8 : 16;  // fp16 products are noisier than the fp32 scan: keep a longer candidate list
     const uint32_t nslots = q->tc_ngroups * kTcM;
     d->last_work = d->total_frames * q->total_frames;
@@ -726,7 +801,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     p.nslices = nslices;
     p.partial = d->d_tc_partial.p;
     p.max_len = q->max_len;
-    const size_t smem = (size_t)q->max_len * (kTcATileBytes + kTcM * 4) + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kTcDpThreads * 8 + 1024;
+    const size_t smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kTcDpThreads * 8 + 1024;
     const uint32_t grid = q->tc_ngroups * nslices;
     if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, grid, smem, nlists, nslots, d));
     else SS_TRY(tc_launch<16>(ctx, p, grid, smem, nlists, nslots, d));

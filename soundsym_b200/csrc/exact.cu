@@ -367,7 +367,9 @@ __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const floa
         } else {
             const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
             const double w = worst > 0.f ? (double)worst : 0.0;
-            lower = w - 2.0 * delta * sqrt(w) - 8e-6 * (na + nb);
+            // E32: fp32 accumulation of the 16 products in the tensor core (<= 16 ulp of na + nb + 2 sqrt(na nb), truncating)
+            // plus <= Lq + Ld <= 64 roundings of the running sum along the path
+            lower = w - 2.0 * delta * sqrt(w) - 2e-5 * (na + nb);
         }
         uncertified = !(lower > kth);
         if (uncertified) atomicAdd(&counters[0], 1ull);

@@ -64,6 +64,7 @@ struct ss_dict {
     bool scan_timed = false;
     // tensor-core scan (dtw_tc.cu): fp16 UMMA tiles of 4 segment slots x 32 columns, segments sorted by length
     bool tc_ready = false;
+    uint64_t tc_serial = 0;                  // identifies this build of the tiles (query A blocks are keyed on it)
     uint32_t tc_ntiles = 0;
     float tc_nb_scale = 1.f;                 // power of two s: the |b|^2 columns hold |b|^2 / s
     ss::DevBuf<double> d_mu;                 // per-coefficient mean of the dictionary frames (both sides are centred on it)
@@ -101,10 +102,12 @@ struct ss_queries {
     bool lane_built = false;
     // tensor-core scan: groups of 128 equal-length queries
     bool tc_built = false;
+    bool tc_ok = false;                      // rd(|a|^2 / s) fits fp16 for every query row
+    uint64_t tc_dict_serial = 0;             // ss_dict::tc_serial the A blocks were built for
     uint32_t tc_ngroups = 0;
     std::vector<uint32_t> h_tc_group_len;
     ss::DevBuf<uint32_t> d_tc_group_len, d_tc_qid, d_tc_slot_len;  // qid / slot_len: ngroups x 128
-    ss::DevBuf<uint64_t> d_tc_group_off;            // byte offset of each group's [L x 4 KB tiles][L x 128 floats |a|^2] block
+    ss::DevBuf<uint64_t> d_tc_group_off;            // byte offset of each group's block of L x 4 KB A tiles
     ss::DevBuf<unsigned char> d_tc_a;
     ss::DevBuf<float> d_tc_max_norm;                // [0] = max |fp16(a - mu)|^2
     ss::DevBuf<float> d_tc_slot_max_na;             // per query slot: max over its rows of |fp16(a - mu)|^2

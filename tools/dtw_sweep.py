@@ -46,3 +46,9 @@ ms = e0.elapsed_time(e1) / n
 work = dev.last_work
 print("TC=%s scan_ms=%.3f RB=%s mode=%d nd=%d nq=%d: %.3f ms/step, %.3e work-units/s (work %.3e, cells %.3e), uncertified %d" %
       (os.environ.get("SS_DTW_TC", "1"), float(ctx.lib.ss_dict_last_scan_ms(dev.h)), os.environ.get("SS_DTW_RB", "4"), mode, nd, nq, ms, work / (ms * 1e-3), work, cells, dev.last_uncertified if mode == SS_DTW else 0), "tc_fallback", dev.last_tc_fallback)
+
+# result fingerprint: identical across SS_DTW_TC=0/1 when both certify (indices are the f64 argmin, distances f64-rescored)
+import hashlib  # noqa: E402
+ctx.sync()
+print("fingerprint idx=%s dist=%s exhaustive=%d" % (hashlib.sha1(oi.cpu().numpy().tobytes()).hexdigest()[:16],
+                                                  hashlib.sha1(od.cpu().numpy().tobytes()).hexdigest()[:16], dev.last_exhaustive))
