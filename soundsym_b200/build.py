@@ -25,7 +25,11 @@ def _newer(a, deps):
     return (not os.path.exists(a)) or any(os.path.getmtime(d) > os.path.getmtime(a) for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defs=()):
+    """variant / defs: development A/B builds, e.g. variant="v7", defs=["-DSS_TC_SLOTS=4"] writes
+    libsoundsym_b200.v7.so next to the product library (select it with SS_B200_LIB=<path>)."""
+    OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + variant if variant else ""))
+    LIB = os.path.join(HERE, "libsoundsym_b200%s.so" % ("." + variant if variant else ""))
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
@@ -36,7 +40,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, s[:-3] + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):
-            cmd = [NVCC] + ARCH + COMMON + PER_FILE.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + ARCH + COMMON + list(defs) + PER_FILE.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for s, p in procs:
@@ -52,4 +56,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _variant = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=_variant,
+                defs=[a for a in sys.argv if a.startswith("-D")]))

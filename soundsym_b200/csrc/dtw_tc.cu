@@ -35,17 +35,28 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 
 constexpr int kTcM = 128;          // queries per CTA = MMA M = TMEM lanes
-constexpr int kTcSlots = 3;        // segment slots per tile (32 columns each)
-constexpr int kTcN = kTcSlots * 32;  // columns per tile = MMA N = 96
+#ifndef SS_TC_SLOTS
+#define SS_TC_SLOTS 4
+#endif
+constexpr int kTcSlots = SS_TC_SLOTS;  // segment slots per tile (32 columns each): 4 -> 16 DP warps, 3 -> 12 DP warps
+constexpr int kTcN = kTcSlots * 32;  // columns per tile = MMA N
 constexpr int kTcK = 16;           // fp16 elements per row = one MMA K step
 constexpr int kTcATileBytes = kTcM * kTcK * 2;  // 4096: one query row of the CTA's 128 queries
 constexpr int kTcBTileBytes = kTcN * kTcK * 2;  // 3072: one dictionary tile
 constexpr int kTcStages = 4;       // B-tile ring
-constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows = 192 TMEM columns; two buffers
+constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows of the tile; two buffers (all 512 TMEM columns at 4 slots)
 constexpr int kTcMaxLen = 32;
-constexpr int kTcDpWarps = 4 * kTcSlots;             // 12
-constexpr int kTcThreads = (kTcDpWarps + 4) * 32;    // 512: three DP warpgroups + one warpgroup holding the producer warp
-constexpr int kTcDpThreads = kTcDpWarps * 32;        // 384
+constexpr int kTcDpWarps = 4 * kTcSlots;             // warp w: TMEM lane quadrant w % 4, segment slot w / 4
+// The producer warp sits in a warpgroup of its own (three idle warps) that hands its registers to the DP warpgroups
+// (setmaxnreg): 3 slots -> 512 threads, 128 at launch, DP 152 / producer 48; 4 slots -> 640 threads, 96 at launch, DP 112 /
+// producer 32, and the DP step pulls its costs from TMEM in 16-column chunks to fit.
+constexpr int kTcRegsDp = kTcSlots == 3 ? 152 : 112, kTcRegsProd = kTcSlots == 3 ? 48 : 32;
+#ifndef SS_TC_CHUNKED
+#define SS_TC_CHUNKED (SS_TC_SLOTS == 4)
+#endif
+constexpr bool kTcChunked = SS_TC_CHUNKED;
+constexpr int kTcThreads = (kTcDpWarps + 4) * 32;
+constexpr int kTcDpThreads = kTcDpWarps * 32;
 
 // byte offset of element (row, k) inside a ROWS x 16 fp16 K-major no-swizzle UMMA tile: core matrix = 8 rows x 16 B;
 // SBO (between 8-row groups) = 128 B, LBO (between the two K chunks) = ROWS / 8 * 128 B
@@ -199,8 +210,8 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
     const int4 segs = desc[2 * t], lens = desc[2 * t + 1];
     const int W = 32;  // slot width
     const int slot = (int)n / W, j = (int)n % W;
-    const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : -1;
-    const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : 0;
+    const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : segs.w;
+    const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : lens.w;
     __half row[kTcK];
 #pragma unroll
     for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
@@ -353,22 +364,31 @@ __device__ __forceinline__ void tc_ld_row(uint32_t taddr, float (&v)[4 * NG]) {
 // register copies, no guards: per cell FMNMX3 + FADD. The column count 4*NG is a compile-time constant. With CAP, e0 / e1
 // return D(i, len-1) / D(i+1, len-1) (len - 1 lies in the last 4-column group: four uniform selects per row); the
 // capture-free instantiation runs in every step that cannot hold the last row of any of the group's queries.
+struct TcCarry {  // what a band carries from column j-1 to column j: D(i, j-1), D(i-1, j-1), D(i+1, j-1)
+    float left0, diag0, left1;
+};
+// columns [J0, J1) of the band; tm0 / tm1 hold the costs of those columns only
+template <int NG, bool CAP, int J0, int J1, int W>
+__device__ __forceinline__ void tc_dp_band_cols(const float (&tm0)[W], const float (&tm1)[W], float (&d)[4 * NG], TcCarry& c, int len, float& e0,
+                                                float& e1) {
+#pragma unroll
+    for (int j = J0; j < J1; j++) {
+        const float up0 = d[j];
+        const float c0 = tm0[j - J0] + tc_min3(c.left0, up0, c.diag0);
+        const float c1 = tm1[j - J0] + tc_min3(c.left1, c0, c.left0);  // up = D(i, j), diag = D(i, j-1)
+        c.diag0 = up0;
+        c.left0 = c0;
+        c.left1 = c1;
+        d[j] = c1;
+        if (CAP && j >= 4 * (NG - 1) && j == len - 1) e0 = c0, e1 = c1;
+    }
+}
 template <int NG, bool CAP>
 __device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[4 * NG], const float (&tm1)[4 * NG], float (&d)[4 * NG], float dinit, int len,
                                               float& e0, float& e1) {
     const float INF = __int_as_float(0x7f800000);
-    float left0 = INF, diag0 = dinit, left1 = INF;  // dinit = 0 on the first row of the pair (the virtual D(-1,-1)), +inf after
-#pragma unroll
-    for (int j = 0; j < 4 * NG; j++) {
-        const float up0 = d[j];
-        const float c0 = tm0[j] + tc_min3(left0, up0, diag0);
-        const float c1 = tm1[j] + tc_min3(left1, c0, left0);  // up = D(i, j), diag = D(i, j-1)
-        diag0 = up0;
-        left0 = c0;
-        left1 = c1;
-        d[j] = c1;
-        if (CAP && j >= 4 * (NG - 1) && j == len - 1) e0 = c0, e1 = c1;
-    }
+    TcCarry c = {INF, dinit, INF};  // dinit = 0 on the first row of the pair (the virtual D(-1,-1)), +inf after
+    tc_dp_band_cols<NG, CAP, 0, 4 * NG, 4 * NG>(tm0, tm1, d, c, len, e0, e1);
 }
 // a single trailing row (odd group length), in place
 template <int NG>
@@ -399,17 +419,41 @@ __device__ __forceinline__ void tc_step2(TcCursor& cur, uint32_t lane_addr, bool
                                          float& e1) {
     mb_wait_addr(cur.full0 + cur.buf * 8, cur.par);
     tc_fence_after();
-    float tm0[4 * NG], tm1[4 * NG];
     const uint32_t taddr = lane_addr + cur.buf * kTcBufCols;
-    tc_ld_row<NG>(taddr, tm0);
-    tc_ld_row<NG>(taddr + kTcN, tm1);
-    tc_wait_ld();
-    tc_fence_before();
-    __syncwarp();
-    if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);  // the costs are in registers: hand the TMEM buffer back
-    cur.par ^= cur.buf;
-    cur.buf ^= 1;
-    tc_dp_band_ng<NG, CAP>(tm0, tm1, d, dinit, len, e0, e1);
+    if constexpr (kTcChunked && NG > 4) {
+        // 120-register budget: the step's costs come in two column chunks (16 + the rest), each two rows
+        const float INF = __int_as_float(0x7f800000);
+        TcCarry c = {INF, dinit, INF};
+        {
+            float a0[16], a1[16];
+            tc_ld<16>(taddr, a0);
+            tc_ld<16>(taddr + kTcN, a1);
+            tc_wait_ld();
+            tc_dp_band_cols<NG, false, 0, 16, 16>(a0, a1, d, c, len, e0, e1);
+        }
+        constexpr int W2 = NG <= 6 ? 8 : 16;  // the remaining 4 NG - 16 columns, loaded as x8 or x16
+        float b0[W2], b1[W2];
+        tc_ld<W2>(taddr + 16, b0);
+        tc_ld<W2>(taddr + kTcN + 16, b1);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);  // the costs are in registers: hand the TMEM buffer back
+        cur.par ^= cur.buf;
+        cur.buf ^= 1;
+        tc_dp_band_cols<NG, CAP, 16, 4 * NG, W2>(b0, b1, d, c, len, e0, e1);
+    } else {
+        float tm0[4 * NG], tm1[4 * NG];
+        tc_ld_row<NG>(taddr, tm0);
+        tc_ld_row<NG>(taddr + kTcN, tm1);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);  // the costs are in registers: hand the TMEM buffer back
+        cur.par ^= cur.buf;
+        cur.buf ^= 1;
+        tc_dp_band_ng<NG, CAP>(tm0, tm1, d, dinit, len, e0, e1);
+    }
 }
 
 // one dictionary tile for one thread (= one query x one segment slot), column-group count NG fixed at compile time so
@@ -494,9 +538,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     const uint32_t tmem_base = *tmem_slot;
     // register re-distribution between warpgroups (setmaxnreg): the producer's warpgroup (one working lane, three idle
     // warps) hands registers to the three DP warpgroups, whose band loop keeps 32 + 64 values live per thread
-    if (warp >= kTcDpWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    }
+    if (warp >= kTcDpWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcRegsProd));
     if (warp > kTcDpWarps) {
         // idle warps of the producer's warpgroup
     } else if (warp == kTcDpWarps) {
@@ -534,7 +576,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         }
     } else {
         // ---- DP warps ---------------------------------------------------------------------------------------------------
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcRegsDp));
         const int q = warp & 3, slot = warp >> 2;
         const int m = q * 32 + lane;
         unsigned long long* list = topk + threadIdx.x;  // [KP][384] keys, this thread's column
@@ -549,8 +591,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         const bool lane0 = lane == 0;
         for (uint32_t n = 0; n < ntiles; n++) {
             const int4 segs = __ldg(&p.desc[2 * (t0 + n)]), lens = __ldg(&p.desc[2 * (t0 + n) + 1]);
-            const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : segs.z;
-            const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : lens.z;
+            const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : segs.w;
+            const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : lens.w;
             const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
             float res;
             switch (ng) {  // one dispatch per tile
@@ -639,9 +681,8 @@ int dtw_tc_dict_build(ss_dict* d) {
             ln[s] = o < order.size() ? len_of(order[o]) : 0;
             d->h_tc_tile_frames[t] += (uint32_t)ln[s];
         }
-        const int W = 32;
-        desc[2 * t] = make_int4(sg[0], sg[1], sg[2], -1);
-        desc[2 * t + 1] = make_int4(ln[0], ln[1], ln[2], W);
+        desc[2 * t] = make_int4(sg[0], sg[1], sg[2], kTcSlots > 3 ? sg[kTcSlots - 1] : -1);
+        desc[2 * t + 1] = make_int4(ln[0], ln[1], ln[2], kTcSlots > 3 ? ln[kTcSlots - 1] : 0);
     }
     d->tc_ntiles = ntiles;
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
@@ -763,7 +804,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     static int waves = 0;
     if (!waves) {
         const char* e = getenv("SS_DTW_TC_WAVES");
-        waves = e ? std::max(1, atoi(e)) : 4;
+        waves = e ? std::max(1, atoi(e)) : 8;
     }
     uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->tc_ntiles, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups));
     std::vector<uint32_t>& st = d->h_slice_tile;
