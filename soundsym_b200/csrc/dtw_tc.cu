@@ -94,8 +94,40 @@ __device__ __forceinline__ void mb_wait(uint64_t* bar, unsigned parity) {
         __nanosleep(32);
     }
 }
-__device__ __forceinline__ void mb_arrive_addr(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+// DP-warp side of the TMEM hand-off, by shared-memory address. The wait is the bare try_wait loop (the instruction itself
+// suspends the thread up to the hint); the arrive is issued by one elected lane once the whole warp has reached it.
 __device__ __forceinline__ void mb_wait_addr(uint32_t addr, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+__device__ __forceinline__ void mb_arrive_elect(uint32_t addr) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tma_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
+                 "r"(bytes), "r"(s32(bar))
+                 : "memory");
+}
+// the same primitives by 32-bit shared address (the producer lane keeps no generic pointers)
+__device__ __forceinline__ void mbs_expect_tx(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbs_wait_sleep(uint32_t bar, unsigned parity) {
     for (;;) {
         uint32_t done;
         asm volatile(
@@ -105,16 +137,19 @@ __device__ __forceinline__ void mb_wait_addr(uint32_t addr, unsigned parity) {
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(20000u)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) break;
         __nanosleep(32);
     }
 }
-__device__ __forceinline__ void tma_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
-                 "r"(bytes), "r"(s32(bar))
+__device__ __forceinline__ void tmas_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void tcs_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -136,6 +171,10 @@ template <int ROWS>
 __device__ __forceinline__ uint64_t tc_smem_desc(const void* p) {
     // start >> 4 | LBO >> 4 << 16 | SBO (128 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_NONE
     return (uint64_t)((s32(p) & 0x3FFFF) >> 4) | ((uint64_t)((ROWS / 8 * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+template <int ROWS>
+__device__ __forceinline__ uint64_t tc_smem_desc_s(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((ROWS / 8 * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
@@ -207,11 +246,10 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
                                 const int4* __restrict__ desc, uint32_t ntiles, float scale, unsigned char* __restrict__ tiles) {
     const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = kTcN
     if (t >= ntiles) return;
-    const int4 segs = desc[2 * t], lens = desc[2 * t + 1];
     const int W = 32;  // slot width
     const int slot = (int)n / W, j = (int)n % W;
-    const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : segs.w;
-    const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : lens.w;
+    const int2 sl = reinterpret_cast<const int2*>(desc)[(size_t)t * 4 + slot];
+    const int seg = sl.x, len = sl.y;
     __half row[kTcK];
 #pragma unroll
     for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
@@ -361,16 +399,15 @@ __device__ __forceinline__ void tc_ld_row(uint32_t taddr, float (&v)[4 * NG]) {
 
 // TWO rows (i, i+1) of one segment slot in column-major order, row state updated in place: cell (i, j) reads d[j]
 // (row i-1) and feeds cell (i+1, j), which overwrites d[j]. Two independent dependency chains per thread (ILP 2), no
-// register copies, no guards: per cell FMNMX3 + FADD. The column count 4*NG is a compile-time constant. With CAP, e0 / e1
-// return D(i, len-1) / D(i+1, len-1) (len - 1 lies in the last 4-column group: four uniform selects per row); the
-// capture-free instantiation runs in every step that cannot hold the last row of any of the group's queries.
+// register copies, no guards: per cell FMNMX3 + FADD. The column count 4*NG is a compile-time constant. The band also
+// hands back row i's values of the last 4-column group (c0l; row i+1's are d[4 NG - 4 ..]): the column len - 1 lies in
+// that group, and the caller picks D(i, len-1) / D(i+1, len-1) from them only in the steps where a query can end.
 struct TcCarry {  // what a band carries from column j-1 to column j: D(i, j-1), D(i-1, j-1), D(i+1, j-1)
     float left0, diag0, left1;
 };
 // columns [J0, J1) of the band; tm0 / tm1 hold the costs of those columns only
-template <int NG, bool CAP, int J0, int J1, int W>
-__device__ __forceinline__ void tc_dp_band_cols(const float (&tm0)[W], const float (&tm1)[W], float (&d)[4 * NG], TcCarry& c, int len, float& e0,
-                                                float& e1) {
+template <int NG, int J0, int J1, int W>
+__device__ __forceinline__ void tc_dp_band_cols(const float (&tm0)[W], const float (&tm1)[W], float (&d)[4 * NG], TcCarry& c, float (&c0l)[4]) {
 #pragma unroll
     for (int j = J0; j < J1; j++) {
         const float up0 = d[j];
@@ -380,19 +417,12 @@ __device__ __forceinline__ void tc_dp_band_cols(const float (&tm0)[W], const flo
         c.left0 = c0;
         c.left1 = c1;
         d[j] = c1;
-        if (CAP && j >= 4 * (NG - 1) && j == len - 1) e0 = c0, e1 = c1;
+        if (j >= 4 * (NG - 1)) c0l[j - 4 * (NG - 1)] = c0;
     }
-}
-template <int NG, bool CAP>
-__device__ __forceinline__ void tc_dp_band_ng(const float (&tm0)[4 * NG], const float (&tm1)[4 * NG], float (&d)[4 * NG], float dinit, int len,
-                                              float& e0, float& e1) {
-    const float INF = __int_as_float(0x7f800000);
-    TcCarry c = {INF, dinit, INF};  // dinit = 0 on the first row of the pair (the virtual D(-1,-1)), +inf after
-    tc_dp_band_cols<NG, CAP, 0, 4 * NG, 4 * NG>(tm0, tm1, d, c, len, e0, e1);
 }
 // a single trailing row (odd group length), in place
 template <int NG>
-__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[4 * NG], float (&d)[4 * NG], float dinit, int len, float& e0) {
+__device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[4 * NG], float (&d)[4 * NG], float dinit) {
     const float INF = __int_as_float(0x7f800000);
     float left = INF, diag = dinit;
 #pragma unroll
@@ -402,57 +432,66 @@ __device__ __forceinline__ void tc_dp_row_ng(const float (&tm)[4 * NG], float (&
         diag = up;
         left = cur;
         d[j] = cur;
-        if (j >= 4 * (NG - 1) && j == len - 1) e0 = cur;
     }
 }
+__device__ __forceinline__ float tc_pick4(const float* v, int r) { return r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3])); }
 
-// consumer side of the TMEM double buffer: which buffer is next and the parity of its "full" barrier
+// consumer side of the TMEM double buffer: the address of the next buffer's "full" barrier (its "empty" barrier sits 16
+// bytes above), the parity to wait for, and this thread's TMEM address in that buffer. The two barriers / buffers are
+// flipped by subtracting from their sum.
 struct TcCursor {
-    uint32_t buf, par;
-    uint32_t full0, empty0;  // shared-memory addresses of t_full[0] / t_empty[0]
+    uint32_t buf, par, full, taddr, full_sum, taddr_sum;
+    __device__ __forceinline__ void init(uint32_t full0, uint32_t lane_addr) {
+        buf = 0, par = 0, full = full0, taddr = lane_addr;
+        full_sum = 2 * full0 + 8, taddr_sum = 2 * lane_addr + (uint32_t)kTcBufCols;
+    }
+    __device__ __forceinline__ void wait() const {
+        mb_wait_addr(full, par);
+        tc_fence_after();
+    }
+    // the step's costs are in registers: hand the TMEM buffer back and move to the other one
+    __device__ __forceinline__ void release() {
+        tc_fence_before();
+        mb_arrive_elect(full + 16);
+        par ^= buf;
+        buf ^= 1u;
+        full = full_sum - full;
+        taddr = taddr_sum - taddr;
+    }
 };
 
 // one pipeline step for one thread: wait for the step's MMAs, pull this slot's columns of both rows into registers, hand
 // the TMEM buffer back, advance the band
-template <int NG, bool CAP>
-__device__ __forceinline__ void tc_step2(TcCursor& cur, uint32_t lane_addr, bool lane0, float (&d)[4 * NG], float dinit, int len, float& e0,
-                                         float& e1) {
-    mb_wait_addr(cur.full0 + cur.buf * 8, cur.par);
-    tc_fence_after();
-    const uint32_t taddr = lane_addr + cur.buf * kTcBufCols;
+template <int NG>
+__device__ __forceinline__ void tc_step2(TcCursor& cur, float (&d)[4 * NG], float dinit, float (&c0l)[4]) {
+    const float INF = __int_as_float(0x7f800000);
+    cur.wait();
+    TcCarry c = {INF, dinit, INF};  // dinit = 0 on the first row of the pair (the virtual D(-1,-1)), +inf after
     if constexpr (kTcChunked && NG > 4) {
-        // 120-register budget: the step's costs come in two column chunks (16 + the rest), each two rows
-        const float INF = __int_as_float(0x7f800000);
-        TcCarry c = {INF, dinit, INF};
+        // 112-register budget: the step's costs come in two column chunks (16 + the rest), each two rows; the compiler
+        // starts the second chunk's loads while the first is being consumed
+        const uint32_t taddr = cur.taddr;
         {
             float a0[16], a1[16];
             tc_ld<16>(taddr, a0);
             tc_ld<16>(taddr + kTcN, a1);
             tc_wait_ld();
-            tc_dp_band_cols<NG, false, 0, 16, 16>(a0, a1, d, c, len, e0, e1);
+            tc_dp_band_cols<NG, 0, 16, 16>(a0, a1, d, c, c0l);
         }
         constexpr int W2 = NG <= 6 ? 8 : 16;  // the remaining 4 NG - 16 columns, loaded as x8 or x16
         float b0[W2], b1[W2];
         tc_ld<W2>(taddr + 16, b0);
         tc_ld<W2>(taddr + kTcN + 16, b1);
         tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);  // the costs are in registers: hand the TMEM buffer back
-        cur.par ^= cur.buf;
-        cur.buf ^= 1;
-        tc_dp_band_cols<NG, CAP, 16, 4 * NG, W2>(b0, b1, d, c, len, e0, e1);
+        cur.release();
+        tc_dp_band_cols<NG, 16, 4 * NG, W2>(b0, b1, d, c, c0l);
     } else {
         float tm0[4 * NG], tm1[4 * NG];
-        tc_ld_row<NG>(taddr, tm0);
-        tc_ld_row<NG>(taddr + kTcN, tm1);
+        tc_ld_row<NG>(cur.taddr, tm0);
+        tc_ld_row<NG>(cur.taddr + kTcN, tm1);
         tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);  // the costs are in registers: hand the TMEM buffer back
-        cur.par ^= cur.buf;
-        cur.buf ^= 1;
-        tc_dp_band_ng<NG, CAP>(tm0, tm1, d, dinit, len, e0, e1);
+        cur.release();
+        tc_dp_band_cols<NG, 0, 4 * NG, 4 * NG>(tm0, tm1, d, c, c0l);
     }
 }
 
@@ -460,40 +499,38 @@ __device__ __forceinline__ void tc_step2(TcCursor& cur, uint32_t lane_addr, bool
 // that the whole step loop is straight-line code over exactly 4*NG row-state registers. Returns D(Lm-1, len-1).
 // L = longest, lmin = shortest query of the CTA's group, Lm = this lane's own.
 template <int NG>
-__device__ __forceinline__ float tc_tile(uint32_t L, uint32_t lmin, uint32_t Lm, int len, TcCursor& cur, uint32_t lane_addr, bool lane0) {
+__device__ __forceinline__ float tc_tile(uint32_t L, uint32_t lmin, uint32_t Lm, int len, TcCursor& cur) {
     const float INF = __int_as_float(0x7f800000);
     float d[4 * NG];
 #pragma unroll
     for (int j = 0; j < 4 * NG; j++) d[j] = INF;
     float res = INF, dinit = 0.f;
-    const uint32_t nfull = L >> 1;                       // steps that carry two rows
+    const uint32_t nfull = L >> 1;           // steps that carry two rows
     const uint32_t ncap = min((lmin - 1) >> 1, nfull);   // steps before any query of the group can end
+    const int r = (len - 1) & 3;             // where column len - 1 sits in the last 4-column group
     uint32_t st = 0;
-    for (; st < ncap; st++) {
-        float e0, e1;
-        tc_step2<NG, false>(cur, lane_addr, lane0, d, dinit, len, e0, e1);
+#pragma unroll 1
+    for (; st < ncap; st++) {  // no query of the group ends in these steps
+        float c0l[4];
+        tc_step2<NG>(cur, d, dinit, c0l);
         dinit = INF;
     }
-    for (; st < nfull; st++) {
-        float e0 = INF, e1 = INF;
-        tc_step2<NG, true>(cur, lane_addr, lane0, d, dinit, len, e0, e1);
+#pragma unroll 1
+    for (; st < nfull; st++) {  // only the last step or two of a tile
+        float c0l[4];
+        tc_step2<NG>(cur, d, dinit, c0l);
         dinit = INF;
+        const float e0 = tc_pick4(c0l, r), e1 = tc_pick4(&d[4 * (NG - 1)], r);
         res = (2 * st + 1 == Lm) ? e0 : ((2 * st + 2 == Lm) ? e1 : res);  // this lane's query ends in this band?
     }
     if (L & 1) {  // odd group length: the last step carries one row
-        mb_wait_addr(cur.full0 + cur.buf * 8, cur.par);
-        tc_fence_after();
+        cur.wait();
         float tm0[4 * NG];
-        tc_ld_row<NG>(lane_addr + cur.buf * kTcBufCols, tm0);
+        tc_ld_row<NG>(cur.taddr, tm0);
         tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane0) mb_arrive_addr(cur.empty0 + cur.buf * 8);
-        cur.par ^= cur.buf;
-        cur.buf ^= 1;
-        float e0 = INF;
-        tc_dp_row_ng<NG>(tm0, d, dinit, len, e0);
-        res = (L == Lm) ? e0 : res;
+        cur.release();
+        tc_dp_row_ng<NG>(tm0, d, dinit);
+        res = (L == Lm) ? tc_pick4(&d[4 * (NG - 1)], r) : res;
     }
     return res;
 }
@@ -509,16 +546,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     uint64_t* a_full = bars;
     uint64_t* b_full = bars + 1;
     uint64_t* b_empty = b_full + kTcStages;
-    uint64_t* t_full = b_empty + kTcStages;
-    uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* t_full = bars + 10;
+    uint64_t* t_empty = bars + 12;  // = t_full + 16 bytes (TcCursor::release)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][384]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
     const uint32_t glen = p.group_len[g];
     const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;  // longest (= rows of the A block) and shortest query of the group
-    const uint32_t nsteps = (L + 1) / 2;  // pipeline steps (two rows each) per tile
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
     const uint32_t ntiles = t1 - t0;
 
@@ -543,35 +579,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         // idle warps of the producer's warpgroup
     } else if (warp == kTcDpWarps) {
         if (lane == 0 && ntiles) {
-            // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------
-            mb_expect_tx(a_full, L * kTcATileBytes);
-            tma_g2s(sA, p.a_blocks + p.group_off[g], L * kTcATileBytes, a_full);
+            // ---- producer: TMA + MMA issue (32-bit shared addresses and running counters: it lives in kTcRegsProd registers)
+            const uint32_t bars_s = s32(bars), sA_s = s32(sA), sB_s = s32(sB);
+            const uint32_t a_full_s = bars_s, b_full_s = bars_s + 8, b_empty_s = bars_s + 8 + 8 * kTcStages, t_full_s = bars_s + 80,
+                           t_empty_s = bars_s + 96;
+            mbs_expect_tx(a_full_s, L * kTcATileBytes);
+            tmas_g2s(sA_s, p.a_blocks + p.group_off[g], L * kTcATileBytes, a_full_s);
+            const unsigned char* tile_src = p.tiles + (size_t)t0 * kTcBTileBytes;
             for (uint32_t n = 0; n < ntiles && n < (uint32_t)kTcStages; n++) {
-                mb_expect_tx(&b_full[n], kTcBTileBytes);
-                tma_g2s(sB + n * kTcBTileBytes, p.tiles + (size_t)(t0 + n) * kTcBTileBytes, kTcBTileBytes, &b_full[n]);
+                mbs_expect_tx(b_full_s + 8 * n, kTcBTileBytes);
+                tmas_g2s(sB_s + n * kTcBTileBytes, tile_src + (size_t)n * kTcBTileBytes, kTcBTileBytes, b_full_s + 8 * n);
             }
-            mb_wait(a_full, 0);
+            tile_src += (size_t)kTcStages * kTcBTileBytes;  // the next tile to fetch
+            mbs_wait_sleep(a_full_s, 0);
             const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);  // f16 x f16 -> f32, K-major
-            uint32_t cnt = 0;
+            const uint64_t adesc0 = tc_smem_desc_s<kTcM>(sA_s);
+            uint32_t cnt = 0, stage = 0, sphase = 0;
             for (uint32_t n = 0; n < ntiles; n++) {
-                const int stage = n % kTcStages;
-                mb_wait(&b_full[stage], (n / kTcStages) & 1);
-                const uint64_t bdesc = tc_smem_desc<kTcN>(sB + stage * kTcBTileBytes);
-                for (uint32_t st = 0; st < nsteps; st++, cnt++) {
+                mbs_wait_sleep(b_full_s + 8 * stage, sphase);
+                const uint64_t bdesc = tc_smem_desc_s<kTcN>(sB_s + stage * kTcBTileBytes);
+                uint64_t adesc = adesc0;  // advances by one A tile (4 KB = 256 descriptor units) per row
+                for (uint32_t row = 0; row < L; row += 2, cnt++) {
                     const uint32_t buf = cnt & 1;
-                    if (cnt >= 2) mb_wait(&t_empty[buf], ((cnt >> 1) - 1) & 1);
+                    if (cnt >= 2) mbs_wait_sleep(t_empty_s + 8 * buf, ((cnt >> 1) - 1) & 1);
                     tc_fence_after();
-                    tc_mma_f16(tmem_base + buf * kTcBufCols, tc_smem_desc<kTcM>(sA + (size_t)(2 * st) * kTcATileBytes), bdesc, idesc);
-                    if (2 * st + 1 < L)
-                        tc_mma_f16(tmem_base + buf * kTcBufCols + kTcN, tc_smem_desc<kTcM>(sA + (size_t)(2 * st + 1) * kTcATileBytes), bdesc, idesc);
-                    tc_commit(&t_full[buf]);
+                    const uint32_t tm = tmem_base + buf * kTcBufCols;
+                    tc_mma_f16(tm, adesc, bdesc, idesc);
+                    if (row + 1 < L) tc_mma_f16(tm + kTcN, adesc + (kTcATileBytes >> 4), bdesc, idesc);
+                    tcs_commit(t_full_s + 8 * buf);
+                    adesc += 2 * (kTcATileBytes >> 4);
                 }
-                tc_commit(&b_empty[stage]);
+                tcs_commit(b_empty_s + 8 * stage);
                 if (n + kTcStages < ntiles) {  // refill this stage once its MMAs have completed
-                    mb_wait(&b_empty[stage], (n / kTcStages) & 1);
-                    mb_expect_tx(&b_full[stage], kTcBTileBytes);
-                    tma_g2s(sB + stage * kTcBTileBytes, p.tiles + (size_t)(t0 + n + kTcStages) * kTcBTileBytes, kTcBTileBytes, &b_full[stage]);
+                    mbs_wait_sleep(b_empty_s + 8 * stage, sphase);
+                    mbs_expect_tx(b_full_s + 8 * stage, kTcBTileBytes);
+                    tmas_g2s(sB_s + stage * kTcBTileBytes, tile_src, kTcBTileBytes, b_full_s + 8 * stage);
+                    tile_src += kTcBTileBytes;
                 }
+                if (++stage == (uint32_t)kTcStages) stage = 0, sphase ^= 1;
             }
         }
     } else {
@@ -586,27 +631,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 32;
         const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
         TcCursor cur;
-        cur.buf = 0, cur.par = 0;
-        cur.full0 = s32(t_full), cur.empty0 = s32(t_empty);
-        const bool lane0 = lane == 0;
+        cur.init(s32(t_full), lane_addr);
         for (uint32_t n = 0; n < ntiles; n++) {
-            const int4 segs = __ldg(&p.desc[2 * (t0 + n)]), lens = __ldg(&p.desc[2 * (t0 + n) + 1]);
-            const int seg = slot == 0 ? segs.x : slot == 1 ? segs.y : slot == 2 ? segs.z : segs.w;
-            const int len = slot == 0 ? lens.x : slot == 1 ? lens.y : slot == 2 ? lens.z : lens.w;
+            const int2 sl = __ldg(reinterpret_cast<const int2*>(p.desc) + (size_t)(t0 + n) * 4 + slot);  // {segment, length} of this slot
+            const int seg = sl.x, len = sl.y;
             const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
             float res;
             switch (ng) {  // one dispatch per tile
-                case 1: res = tc_tile<1>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                case 2: res = tc_tile<2>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                case 3: res = tc_tile<3>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                case 4: res = tc_tile<4>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                case 5: res = tc_tile<5>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                case 6: res = tc_tile<6>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                case 7: res = tc_tile<7>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
-                default: res = tc_tile<8>(L, lmin, Lm, len, cur, lane_addr, lane0); break;
+                case 1: res = tc_tile<1>(L, lmin, Lm, len, cur); break;
+                case 2: res = tc_tile<2>(L, lmin, Lm, len, cur); break;
+                case 3: res = tc_tile<3>(L, lmin, Lm, len, cur); break;
+                case 4: res = tc_tile<4>(L, lmin, Lm, len, cur); break;
+                case 5: res = tc_tile<5>(L, lmin, Lm, len, cur); break;
+                case 6: res = tc_tile<6>(L, lmin, Lm, len, cur); break;
+                case 7: res = tc_tile<7>(L, lmin, Lm, len, cur); break;
+                default: res = tc_tile<8>(L, lmin, Lm, len, cur); break;
             }
             // result: D(Lm-1, len-1) / (Lm + len)
-            if (seg >= 0 && Lm) tc_insert<KP>(list, worst, res * (1.0f / (float)(Lm + (uint32_t)len)), (uint32_t)seg);
+            if (seg >= 0 && Lm) tc_insert<KP>(list, worst, __fdividef(res, (float)(Lm + (uint32_t)len)), (uint32_t)seg);
         }
         unsigned long long* out = p.partial + (((size_t)slice * kTcSlots + slot) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
 #pragma unroll
@@ -681,8 +723,9 @@ int dtw_tc_dict_build(ss_dict* d) {
             ln[s] = o < order.size() ? len_of(order[o]) : 0;
             d->h_tc_tile_frames[t] += (uint32_t)ln[s];
         }
-        desc[2 * t] = make_int4(sg[0], sg[1], sg[2], kTcSlots > 3 ? sg[kTcSlots - 1] : -1);
-        desc[2 * t + 1] = make_int4(ln[0], ln[1], ln[2], kTcSlots > 3 ? ln[kTcSlots - 1] : 0);
+        // four {segment, length} pairs per tile (the fourth is empty with 3 slots)
+        desc[2 * t] = make_int4(sg[0], ln[0], sg[1], ln[1]);
+        desc[2 * t + 1] = make_int4(sg[2], ln[2], kTcSlots > 3 ? sg[kTcSlots - 1] : -1, kTcSlots > 3 ? ln[kTcSlots - 1] : 0);
     }
     d->tc_ntiles = ntiles;
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));

@@ -69,7 +69,7 @@ struct ss_dict {
     float tc_nb_scale = 1.f;                 // power of two s: the |b|^2 columns hold |b|^2 / s
     ss::DevBuf<double> d_mu;                 // per-coefficient mean of the dictionary frames (both sides are centred on it)
     ss::DevBuf<uint16_t> d_tc_tiles;         // ntiles x 4 KB
-    ss::DevBuf<int4> d_tc_desc;              // ntiles x 2: {seg[4]}, {len[4]}
+    ss::DevBuf<int4> d_tc_desc;              // ntiles x 2 = four {segment, length} pairs per tile
     std::vector<uint32_t> h_tc_tile_frames;  // sum of the 4 lengths (slice balancing)
     ss::DevBuf<unsigned long long> d_tc_partial;
     ss::DevBuf<float> d_tc_max_norm;         // [0] = max |fp16(b - mu)|^2
