@@ -268,22 +268,65 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
 // DTW refine: exact f64 recurrence on the candidates. One thread per (query slot, candidate); the DP row lives in a
 // global scratch laid out [column][pair] so that neighbouring threads touch neighbouring addresses.
 // ---------------------------------------------------------------------------------------------------------------
+// Lower bound on the EXACT distance of any pair whose scan distance is >= w (see k_dtw_finalize for the derivation):
+//   bound_mode 0 (fp32 scan):  |scan - exact| <= eps (max|a|^2 + max|b|^2)
+//   bound_mode 1 (fp16 scan):  exact >= w - 2 delta sqrt(w) - E32,  delta = 2^-11 (|a| + |b|)
+__device__ __forceinline__ double scan_lower_bound(float scan, double na, double nb, double eps, int bound_mode) {
+    if (bound_mode == 0) return (double)scan - eps * (na + nb);
+    const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
+    const double w = scan > 0.f ? (double)scan : 0.0;
+    // E32: fp32 accumulation of the 16 products in the tensor core (<= 16 ulp of na + nb + 2 sqrt(na nb), truncating)
+    // plus <= Lq + Ld <= 64 roundings of the running sum along the path
+    return w - 2.0 * delta * sqrt(w) - 2e-5 * (na + nb);
+}
+
+// Thread t of the launch handles candidate s_begin + t % s_count of slot t / s_count. Two launches per match:
+//   (s_begin, s_count) = (0, k):       the k best candidates by scan distance, unconditionally;
+//   (s_begin, s_count) = (k, kp - k):  the rest, but only those whose scan distance does not already PROVE (by the scan's
+//                                      error bound) that they are farther than the k-th exact distance found in the first
+//                                      launch - such a candidate cannot enter the top-k and is recorded as +inf.
 // SMEM_ROWS: segments of <= 32 frames keep the DP row in shared memory ([column][thread], conflict-free) instead of the
 // global scratch.
+struct RescoreBound {
+    const float* cand_adist;   // scan distances of the candidates (nullptr: rescore unconditionally)
+    const float* max_na;       // [0] max |a|^2 over the queries
+    const float* max_nb;       // [0] max |b|^2 over the shard
+    const float* slot_max_na;  // per slot max |a|^2 (nullable)
+    double eps;
+    int bound_mode, k;
+};
 template <bool SMEM_ROWS>
 __global__ void __launch_bounds__(128)
 k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
               const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
-              uint32_t pair_begin, uint32_t pair_end, int kp, double* __restrict__ rows, uint32_t row_pairs, double* __restrict__ exact) {
+              uint32_t t_begin, uint32_t t_end, int kp, int s_begin, int s_count, RescoreBound rb, double* __restrict__ rows,
+              uint32_t row_pairs, double* __restrict__ exact, unsigned long long* __restrict__ counters) {
     __shared__ double srow[SMEM_ROWS ? 32 * 128 : 1];
     const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t pair = pair_begin + local;
-    if (pair >= pair_end) return;
-    const uint32_t qid = group_qid[pair / kp];
+    const uint32_t t = t_begin + local;
+    if (t >= t_end) return;
+    const uint32_t slot = t / (uint32_t)s_count;
+    const uint32_t pair = slot * (uint32_t)kp + (uint32_t)s_begin + t % (uint32_t)s_count;
+    const uint32_t qid = group_qid[slot];
     const uint32_t idx = cand_idx[pair];
     if (qid == 0xFFFFFFFFu || idx == 0xFFFFFFFFu) {
         exact[pair] = kInf;
         return;
+    }
+    if (rb.cand_adist) {
+        // k-th smallest exact distance among the slot's first k candidates
+        double kth = 0.0;
+        for (int s = 0; s < rb.k; s++) {
+            double e = exact[(size_t)slot * kp + s];
+            if (!(e < kInf)) e = kInf;  // empty slot / NaN: nothing can be ruled out
+            kth = fmax(kth, e);
+        }
+        const double na = rb.slot_max_na ? (double)rb.slot_max_na[slot] : (double)rb.max_na[0];
+        if (scan_lower_bound(rb.cand_adist[pair], na, (double)rb.max_nb[0], rb.eps, rb.bound_mode) > kth) {
+            exact[pair] = kInf;  // provably outside the top-k
+            return;
+        }
+        atomicAdd(&counters[1], 1ull);
     }
     const double* a = qmfcc + qoff[qid] * c;
     const double* b = dmfcc + doff[idx] * c;
@@ -362,15 +405,7 @@ __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const floa
         const double na = slot_max_na ? (double)slot_max_na[slot] : (double)max_na[0];
         const double nb = (double)max_nb[0];
         double lower;
-        if (bound_mode == 0) {
-            lower = (double)worst - eps * (na + nb);
-        } else {
-            const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
-            const double w = worst > 0.f ? (double)worst : 0.0;
-            // E32: fp32 accumulation of the 16 products in the tensor core (<= 16 ulp of na + nb + 2 sqrt(na nb), truncating)
-            // plus <= Lq + Ld <= 64 roundings of the running sum along the path
-            lower = w - 2.0 * delta * sqrt(w) - 2e-5 * (na + nb);
-        }
+        lower = scan_lower_bound(worst, na, nb, eps, bound_mode);
         uncertified = !(lower > kth);
         if (uncertified) atomicAdd(&counters[0], 1ull);
     }
@@ -395,13 +430,21 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     const uint64_t budget = 32ull << 20;  // doubles of DP-row scratch (256 MB)
     const uint32_t batch = (uint32_t)std::min<uint64_t>(npairs, std::max<uint64_t>(1024, budget / max_ld));
     SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)batch * max_ld));
-    for (uint32_t pb = 0; pb < npairs; pb += batch) {
-        const uint32_t pe = std::min<uint32_t>(npairs, pb + batch);
-        auto kern = max_ld <= 32 ? k_dtw_rescore<true> : k_dtw_rescore<false>;
-        kern<<<ceil_div(pe - pb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
-                                                                     d_slot_qid, d->d_cand_idx.p, pb, pe, kp,
-                                                                     d->d_rescore_rows.p, batch, d->d_cand_exact.p);
-        SS_LAUNCHED(ctx);
+    auto kern = max_ld <= 32 ? k_dtw_rescore<true> : k_dtw_rescore<false>;
+    // the candidate lists are ascending in scan distance: the first k unconditionally, the others only if the scan's error
+    // bound cannot already rule them out against the k-th exact distance of the first launch
+    for (int phase = 0; phase < 2; phase++) {
+        const int s_begin = phase ? std::min(k, kp) : 0, s_count = phase ? kp - std::min(k, kp) : std::min(k, kp);
+        if (s_count <= 0) continue;
+        RescoreBound rb = {phase ? d->d_cand_adist.p : nullptr, d_max_na, d_max_nb, d_slot_max_na, eps, bound_mode, std::min(k, kp)};
+        const uint32_t nt = nslots * (uint32_t)s_count;
+        for (uint32_t tb = 0; tb < nt; tb += batch) {
+            const uint32_t te = std::min<uint32_t>(nt, tb + batch);
+            kern<<<ceil_div(te - tb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,
+                                                                   d->d_cand_idx.p, tb, te, kp, s_begin, s_count, rb, d->d_rescore_rows.p,
+                                                                   batch, d->d_cand_exact.p, d->d_counters.p);
+            SS_LAUNCHED(ctx);
+        }
     }
     k_dtw_finalize<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_idx.p, d->d_cand_adist.p, d->d_cand_exact.p,
                                                                   d_slot_qid, nslots, kp, k, d->index_base, d_max_na, d_max_nb, eps,
