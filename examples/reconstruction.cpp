@@ -17,6 +17,7 @@ int main(int argc, char** argv) {
     std::string src, tgt, out, model_path;
     size_t depth = 3, threshold = 4;  // examples/reconstruction.rs:44-45
     bool dtw = false, partition_only = false;
+    std::string dict_dir, query_dir, splits_dir;  // --matcher <dictionary dir> <query dir>: the flow of examples/matcher.rs
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&]() { return i + 1 < argc ? std::string(argv[++i]) : std::string(); };
@@ -28,13 +29,35 @@ int main(int argc, char** argv) {
         else if (a == "--threshold") threshold = std::stoul(next());
         else if (a == "--dtw") dtw = true;
         else if (a == "--partition-only") partition_only = true;
+        else if (a == "--matcher") dict_dir = next(), query_dir = next();
+        else if (a == "--write-splits") splits_dir = next();
     }
     try {
+        if (!dict_dir.empty()) {
+            // examples/matcher.rs:19-52: a dictionary of whole files, every query file matched against it unless it is
+            // quieter than 0.03 (then silence); here the queries are matched in ONE batched call
+            auto dictionary = SoundDictionary::from_path(dict_dir);
+            dictionary->mode = dtw ? SS_DTW : SS_COSINE_REF;
+            auto queries = SoundDictionary::from_path(query_dir);
+            std::vector<std::shared_ptr<Sound>> loud;
+            for (auto& q : queries->sounds)
+                if (!(q->max_power() < 0.03)) loud.push_back(q);
+            std::vector<uint32_t> idx;
+            std::vector<double> dist;
+            if (!loud.empty()) dictionary->match_indices(loud, {}, 1, &idx, &dist);
+            printf("{\"dictionary\": %zu, \"queries\": %zu, \"silent\": %zu, \"matches\": [", dictionary->sounds.size(), queries->sounds.size(),
+                   queries->sounds.size() - loud.size());
+            for (size_t i = 0; i < loud.size(); i++)
+                printf("%s[\"%s\", \"%s\"]", i ? "," : "", loud[i]->name.value_or("").c_str(), dictionary->sounds[idx[i]]->name.value_or("").c_str());
+            printf("]}\n");
+            return 0;
+        }
         auto source = std::make_shared<Sound>(Sound::from_path(src));
         Partitioner partitioner(source);
         partitioner.set_threshold(threshold).set_depth(depth);
         if (!model_path.empty()) partitioner.train(GaussianMixtureModel::load(model_path));
         const std::vector<size_t> splits = partitioner.partition();  // "Must first train model" without -m
+        if (!splits_dir.empty()) write_splits(*source, splits, splits_dir);  // examples/partition.rs:76
         if (partition_only) {
             printf("{\"source_frames\": %zu, \"max_power\": %.17g, \"nsplits\": %zu, \"splits\": [", source->num_frames(), source->max_power(), splits.size());
             for (size_t i = 0; i < splits.size(); i++) printf("%s%zu", i ? "," : "", splits[i]);

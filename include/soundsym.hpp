@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <limits>
 #include <memory>
@@ -135,21 +136,6 @@ class Sound {
         max_power_ = std::fmax(max_power_, mp);
     }
 
-    /// Sound::write_file (src/sound.rs:129-143): 32-bit integer PCM
-    void write_file(const std::string& path) const {
-        std::ofstream f(path, std::ios::binary);
-        const uint32_t bytes = (uint32_t)(samples_.size() * 4), sr = (uint32_t)sample_rate_;
-        auto u32 = [&](uint32_t v) { f.write(reinterpret_cast<const char*>(&v), 4); };
-        auto u16 = [&](uint16_t v) { f.write(reinterpret_cast<const char*>(&v), 2); };
-        f.write("RIFF", 4), u32(36 + bytes), f.write("WAVEfmt ", 8), u32(16), u16(1), u16(1), u32(sr), u32(sr * 4), u16(4), u16(32);
-        f.write("data", 4), u32(bytes);
-        for (double s : samples_) {
-            const double v = std::trunc(2147483647.0 * s);
-            const int32_t i = v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v);
-            f.write(reinterpret_cast<const char*>(&i), 4);
-        }
-    }
-
     double max_power() const { return max_power_; }
     const std::vector<double>& samples() const { return samples_; }
     double sample_rate() const { return sample_rate_; }
@@ -169,6 +155,64 @@ class Sound {
         s.mean_mfccs_ = mean_of(s.mfccs_);
         s.max_power_ = std::numeric_limits<double>::quiet_NaN();  // analysed on demand by callers that gate on it
         return s;
+    }
+
+    /// many sounds analysed in ONE device pass (ss_sound_analyze_batch): what SoundDictionary::from_path and
+    /// SoundSequence::from_timestamps build their Sounds from. All sounds share sample_rate.
+    static std::vector<std::shared_ptr<Sound>> from_samples_batch(std::vector<std::vector<double>> cuts, double sample_rate,
+                                                                  const std::vector<std::optional<std::string>>& names, Context& ctx) {
+        std::vector<uint64_t> off(cuts.size() + 1, 0), foff(cuts.size() + 1, 0);
+        std::vector<double> flat;
+        size_t frames = 0;
+        for (size_t i = 0; i < cuts.size(); i++) {
+            off[i + 1] = off[i] + cuts[i].size();
+            flat.insert(flat.end(), cuts[i].begin(), cuts[i].end());
+            size_t f = 0;
+            ss_frame_count(cuts[i].size(), &f);
+            frames += f;
+        }
+        std::vector<double> mfcc(frames * NCOEFFS), mp(cuts.size(), 0.0), mean(cuts.size() * NCOEFFS, 0.0);
+        ctx.check(ss_sound_analyze_batch(ctx.get(), flat.data(), off.data(), cuts.size(), sample_rate, (int)NCOEFFS, mfcc.data(), foff.data(),
+                                         mp.data(), mean.data()));
+        std::vector<std::shared_ptr<Sound>> out;
+        for (size_t i = 0; i < cuts.size(); i++) {
+            auto s = std::make_shared<Sound>();
+            s->ctx_ = &ctx;
+            s->name = i < names.size() ? names[i] : std::nullopt;
+            s->sample_rate_ = sample_rate;
+            s->samples_ = std::move(cuts[i]);
+            s->mfccs_.assign(mfcc.begin() + foff[i] * NCOEFFS, mfcc.begin() + foff[i + 1] * NCOEFFS);
+            s->mean_mfccs_.assign(mean.begin() + i * NCOEFFS, mean.begin() + (i + 1) * NCOEFFS);
+            s->max_power_ = mp[i];
+            out.push_back(std::move(s));
+        }
+        return out;
+    }
+    /// a mono integer-PCM WAV as f64 samples, s / (i32::MAX >> (32 - bits)) (src/sound.rs:117-120), on the host
+    static std::vector<double> read_wav_samples(const std::string& path, double* sr) {
+        int bits = 0;
+        std::vector<int32_t> pcm = read_wav_pcm(path, &bits, sr);
+        const double denom = (double)(INT32_MAX >> (32 - bits));
+        std::vector<double> out(pcm.size());
+        for (size_t i = 0; i < pcm.size(); i++) out[i] = (double)pcm[i] / denom;
+        return out;
+    }
+    /// Sound::write_file (src/sound.rs:129-143): 32-bit integer PCM, (sample * i32::MAX) as i32
+    void write_file(const std::string& path) const { write_wav_i32(path, samples_.data(), samples_.size(), sample_rate_); }
+    static void write_wav_i32(const std::string& path, const double* s, size_t n, double sample_rate) {
+        std::ofstream f(path, std::ios::binary);
+        if (!f) throw CosError(SS_ERR_INVALID, "cannot create " + path);
+        const uint32_t bytes = (uint32_t)(n * 4), riff = 36 + bytes, sixteen = 16, rate = (uint32_t)sample_rate, brate = rate * 4;
+        const uint16_t pcm = 1, ch = 1, align = 4, bits = 32;
+        f.write("RIFF", 4), f.write((const char*)&riff, 4), f.write("WAVEfmt ", 8), f.write((const char*)&sixteen, 4);
+        f.write((const char*)&pcm, 2), f.write((const char*)&ch, 2), f.write((const char*)&rate, 4), f.write((const char*)&brate, 4);
+        f.write((const char*)&align, 2), f.write((const char*)&bits, 2), f.write("data", 4), f.write((const char*)&bytes, 4);
+        std::vector<int32_t> q(n);
+        for (size_t i = 0; i < n; i++) {  // Rust's `as i32`: truncate toward zero, saturate, NaN -> 0
+            const double v = s[i] * 2147483647.0;
+            q[i] = v != v ? 0 : (v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v));
+        }
+        f.write((const char*)q.data(), bytes);
     }
 
    private:
@@ -242,6 +286,38 @@ class SoundDictionary {
         }
         ss_dict_destroy(dev_);
         dev_ = nullptr;
+    }
+    /// SoundDictionary::from_path (src/sound.rs:304-320): every *.wav directly inside `dir` becomes one Sound (sorted by
+    /// name: read_dir's order is platform-defined). Files are decoded on the host and analysed together, one
+    /// ss_sound_analyze_batch per distinct sample rate.
+    static std::unique_ptr<SoundDictionary> from_path(const std::string& dir, Context& ctx = Context::global()) {
+        namespace fs = std::filesystem;
+        std::vector<std::string> files;
+        for (const auto& e : fs::directory_iterator(dir))
+            if (e.is_regular_file() && e.path().extension() == ".wav") files.push_back(e.path().string());
+        std::sort(files.begin(), files.end());
+        auto d = std::make_unique<SoundDictionary>(ctx);
+        d->sounds.resize(files.size());
+        std::vector<double> rates(files.size());
+        std::vector<std::vector<double>> samples(files.size());
+        for (size_t i = 0; i < files.size(); i++) samples[i] = Sound::read_wav_samples(files[i], &rates[i]);
+        std::vector<bool> done(files.size(), false);
+        for (size_t i = 0; i < files.size(); i++) {
+            if (done[i]) continue;
+            std::vector<size_t> sel;
+            std::vector<std::vector<double>> cuts;
+            std::vector<std::optional<std::string>> names;
+            for (size_t j = i; j < files.size(); j++)
+                if (!done[j] && rates[j] == rates[i]) {
+                    sel.push_back(j);
+                    cuts.push_back(std::move(samples[j]));
+                    names.push_back(fs::path(files[j]).stem().string());
+                    done[j] = true;
+                }
+            auto snds = Sound::from_samples_batch(std::move(cuts), rates[i], names, ctx);
+            for (size_t k = 0; k < sel.size(); k++) d->sounds[sel[k]] = std::move(snds[k]);
+        }
+        return d;
     }
     static std::unique_ptr<SoundDictionary> from_segments(const Sound& sound, const std::vector<size_t>& segments, Context& ctx = Context::global()) {
         auto d = std::make_unique<SoundDictionary>(ctx);
@@ -326,6 +402,10 @@ class SoundSequence {
         return Sound::from_samples(std::move(out), sr, std::nullopt, std::nullopt, *ctx_);
     }
 
+    /// SoundSequence::from_timestamps (src/sound.rs:419-430): one new Sound per (start, end, label), cut at
+    /// round(start * sr) ..= round(end * sr); all cuts analysed in one batch
+    static SoundSequence from_timestamps(const std::shared_ptr<Sound>& sound, const std::vector<struct Timestamp>& timestamps);
+
     /// SoundSequence::morph_to (src/sound.rs:440-449), batched
     SoundSequence morph_to(const std::vector<double>& distances, SoundDictionary& dict) {
         const size_t n = std::min(sounds_.size(), distances.size());
@@ -356,6 +436,10 @@ class Partitioner {
     std::optional<GaussianMixtureModel> model;
 
     explicit Partitioner(std::shared_ptr<Sound> s) : sound(std::move(s)) {}
+    /// Partitioner::from_path (src/lib.rs:85-88)
+    static Partitioner from_path(const std::string& path, Context& ctx = Context::global()) {
+        return Partitioner(std::make_shared<Sound>(Sound::from_path(path, ctx)));
+    }
     Partitioner& set_depth(size_t d) { return depth = d, *this; }
     Partitioner& set_threshold(size_t t) { return threshold = t, *this; }
     /// Partitioner::train (src/lib.rs:101-107). EM training is not on the data-parallel path (the reference's is randomly
@@ -393,5 +477,72 @@ class Partitioner {
     }
     std::vector<size_t> partition() const { return partition_other(*sound); }
 };
+
+/// Timestamp (src/sound.rs:508)
+struct Timestamp {
+    double start = 0, end = 0;
+    std::optional<std::string> label;
+};
+
+/// audacity_labels_to_timestamps (src/sound.rs:511-531): `start<TAB>end<TAB>label` per line; a missing or unparsable number is
+/// 0.0, a missing label is none
+inline std::vector<Timestamp> audacity_labels_to_timestamps(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw CosError(SS_ERR_INVALID, "cannot open " + path);
+    auto num = [](const std::string& t) {
+        try {
+            size_t used = 0;
+            const double v = std::stod(t, &used);
+            return used == t.size() ? v : 0.0;
+        } catch (...) {
+            return 0.0;
+        }
+    };
+    std::vector<Timestamp> out;
+    std::string line;
+    while (std::getline(f, line)) {
+        const size_t a = line.find_first_not_of(" \t\r\n"), b = line.find_last_not_of(" \t\r\n");
+        line = a == std::string::npos ? std::string() : line.substr(a, b - a + 1);
+        std::vector<std::string> parts;
+        size_t pos = 0;
+        for (;;) {
+            const size_t tab = line.find('\t', pos);
+            parts.push_back(line.substr(pos, tab == std::string::npos ? std::string::npos : tab - pos));
+            if (tab == std::string::npos) break;
+            pos = tab + 1;
+        }
+        Timestamp t;
+        if (parts.size() > 0) t.start = num(parts[0]);
+        if (parts.size() > 1) t.end = num(parts[1]);
+        if (parts.size() > 2) t.label = parts[2];
+        out.push_back(std::move(t));
+    }
+    return out;
+}
+
+inline SoundSequence SoundSequence::from_timestamps(const std::shared_ptr<Sound>& sound, const std::vector<Timestamp>& timestamps) {
+    const double sr = sound->sample_rate();
+    std::vector<std::vector<double>> cuts;
+    std::vector<std::optional<std::string>> names;
+    for (const Timestamp& t : timestamps) {
+        const long long a = std::llround(t.start * sr), b = std::llround(t.end * sr);
+        if (a < 0 || b + 1 > (long long)sound->samples().size() || a > b + 1) throw CosError(SS_ERR_INVALID, "timestamp outside the sound");
+        cuts.emplace_back(sound->samples().begin() + a, sound->samples().begin() + b + 1);
+        names.push_back(t.label);
+    }
+    return SoundSequence(Sound::from_samples_batch(std::move(cuts), sr, names, sound->context()), sound->context());
+}
+
+/// write_splits (src/lib.rs:155-178): consecutive cuts of `sound` as `<out>/<idx:05>_<len>.wav`, 32-bit integer PCM
+inline void write_splits(const Sound& sound, const std::vector<size_t>& splits, const std::string& out_path) {
+    size_t pos = 0;
+    for (size_t idx = 0; idx < splits.size(); idx++) {
+        const size_t n = std::min(splits[idx], sound.samples().size() - std::min(pos, sound.samples().size()));
+        char name[64];
+        snprintf(name, sizeof(name), "/%05zu_%zu.wav", idx, splits[idx]);
+        Sound::write_wav_i32(out_path + name, sound.samples().data() + pos, n, sound.sample_rate());
+        pos += n;
+    }
+}
 
 }  // namespace soundsym

@@ -95,6 +95,16 @@ int ss_sound_analyze(ss_ctx* ctx, const double* samples, size_t n, double sample
  *                        three analyses. out_samples (n doubles, the Sound's `samples` Vec) may be NULL. */
 int ss_sound_analyze_pcm(ss_ctx* ctx, const void* pcm, size_t n, int bits_per_sample, double sample_rate, int ncoeffs,
                          double* out_samples, double* out_mfcc, size_t* out_frames, double* out_max_power, double* out_mean_mfccs);
+/* ss_sound_analyze_batch   SoundDictionary::from_path (src/sound.rs:304-320: one Sound::from_path per .wav of a directory)
+ *                          as ONE upload and one MFCC launch. `samples` holds nsounds sounds back to
+ *                          back, sound i = samples[sample_offsets[i] .. sample_offsets[i+1]) (offsets[0] = 0), all at the
+ *                          same sample_rate. Every sound is framed on its own (no frame straddles two sounds):
+ *                          out_frame_offsets (nsounds + 1) gives each sound's row range in out_mfcc (sum of the per-sound
+ *                          frame counts x ncoeffs doubles); out_max_power (nsounds) and out_mean_mfccs (nsounds x ncoeffs,
+ *                          NaN row for a sound without a full frame) as Sound::from_samples computes them. The three
+ *                          outputs may be NULL. Values equal ss_sound_analyze on each sound alone. */
+int ss_sound_analyze_batch(ss_ctx* ctx, const double* samples, const uint64_t* sample_offsets, size_t nsounds, double sample_rate,
+                           int ncoeffs, double* out_mfcc, uint64_t* out_frame_offsets, double* out_max_power, double* out_mean_mfccs);
 int ss_mfcc(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc,
             size_t* out_frames);
 int ss_max_power(ss_ctx* ctx, const double* samples, size_t n, double* out);

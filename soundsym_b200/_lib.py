@@ -16,7 +16,7 @@ SS_MAX_TOPK = 8
 # every symbol include/soundsym_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
     "ss_version", "ss_ctx_create", "ss_ctx_destroy", "ss_last_error", "ss_ctx_stream", "ss_ctx_sync", "ss_ctx_device",
-    "ss_ctx_launch_count", "ss_frame_count", "ss_decode_pcm", "ss_sound_analyze", "ss_sound_analyze_pcm", "ss_mfcc", "ss_max_power", "ss_mfcc_dev",
+    "ss_ctx_launch_count", "ss_frame_count", "ss_decode_pcm", "ss_sound_analyze", "ss_sound_analyze_pcm", "ss_sound_analyze_batch", "ss_mfcc", "ss_max_power", "ss_mfcc_dev",
     "ss_symbols", "ss_gmm_train", "ss_vote_split", "ss_partition", "ss_dict_create", "ss_dict_destroy", "ss_dict_len", "ss_dict_match",
     "ss_queries_create", "ss_queries_destroy", "ss_dict_match_dev", "ss_topk_merge_dev", "ss_dict_last_work",
     "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_dict_last_exhaustive", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances",
@@ -57,6 +57,7 @@ def load():
     L.ss_decode_pcm.argtypes = [vp, vp, sz, i, vp]
     L.ss_sound_analyze.argtypes = [vp, vp, sz, dbl, i, vp, P(sz), P(dbl), vp]
     L.ss_sound_analyze_pcm.argtypes = [vp, vp, sz, i, dbl, i, vp, vp, P(sz), P(dbl), vp]
+    L.ss_sound_analyze_batch.argtypes = [vp, vp, vp, sz, dbl, i, vp, vp, vp, vp]
     L.ss_mfcc.argtypes = [vp, vp, sz, dbl, i, vp, P(sz)]
     L.ss_max_power.argtypes = [vp, vp, sz, P(dbl)]
     L.ss_mfcc_dev.argtypes = [vp, vp, sz, dbl, i, vp]

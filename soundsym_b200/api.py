@@ -98,6 +98,24 @@ class Context:
                                                  C.byref(frames), C.byref(mp), _ptr(mean)))
         return samples, mfcc, float(mp.value), mean
 
+    def analyze_batch(self, samples, sample_offsets, sample_rate=44100.0, ncoeffs=NCOEFFS):
+        """Many sounds back to back, analysed in one upload / one MFCC launch (ss_sound_analyze_batch)
+        -> (mfcc [sum frames, C], frame_offsets [n + 1], max_power [n], mean_mfccs [n, C])."""
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        off = np.ascontiguousarray(sample_offsets, dtype=np.uint64)
+        n = off.shape[0] - 1
+        foff = np.zeros(n + 1, dtype=np.uint64)
+        frames = 0
+        for i in range(n):
+            ln = int(off[i + 1]) - int(off[i])
+            frames += (ln - BIN) // HOP + 1 if ln >= BIN else 0
+        mfcc = np.empty((frames, ncoeffs), dtype=np.float64)
+        mp = np.zeros(n, dtype=np.float64)
+        mean = np.empty((n, ncoeffs), dtype=np.float64)
+        self.check(self.lib.ss_sound_analyze_batch(self.h, _ptr(samples), _ptr(off), n, float(sample_rate), int(ncoeffs), _ptr(mfcc),
+                                                   _ptr(foff), _ptr(mp), _ptr(mean)))
+        return mfcc, foff, mp, mean
+
     def mfcc(self, samples, sample_rate=44100.0, ncoeffs=NCOEFFS):
         samples = np.ascontiguousarray(samples, dtype=np.float64)
         frames = C.c_size_t()
@@ -389,6 +407,30 @@ class SoundDictionary:
         self._dev = None
 
     @classmethod
+    def from_path(cls, path, ctx=None, mode=SS_COSINE_REF):
+        """SoundDictionary::from_path (src/sound.rs:304-320): every *.wav of a directory (not recursive, other entries
+        skipped) becomes one Sound, in directory order (sorted here: read_dir's order is platform-defined). The files
+        are decoded on the host, then analysed together: one ss_sound_analyze_batch per distinct sample rate."""
+        import os
+        d = cls(ctx, mode)
+        names = sorted(n for n in os.listdir(path) if os.path.splitext(n)[1] == ".wav" and os.path.isfile(os.path.join(path, n)))
+        loaded = []
+        for nme in names:
+            pcm, sr, bits = _read_wav_pcm(os.path.join(path, nme))
+            denom = float(0x7FFFFFFF >> (32 - bits))  # src/sound.rs:118-120
+            loaded.append((os.path.splitext(nme)[0], sr, pcm.astype(np.float64) / denom))
+        d.sounds = [None] * len(loaded)
+        for sr in sorted(set(l[1] for l in loaded)):
+            sel = [i for i, l in enumerate(loaded) if l[1] == sr]
+            off = np.zeros(len(sel) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([loaded[i][2].shape[0] for i in sel])
+            flat = np.concatenate([loaded[i][2] for i in sel]) if sel else np.zeros(0)
+            mfcc, foff, mp, mean = d._ctx.analyze_batch(flat, off, sr, NCOEFFS)
+            for j, i in enumerate(sel):
+                d.sounds[i] = Sound(loaded[i][2], sr, mfcc[int(foff[j]):int(foff[j + 1])], float(mp[j]), mean[j], loaded[i][0], d._ctx)
+        return d
+
+    @classmethod
     def from_segments(cls, sound, segments, ctx=None, mode=SS_COSINE_REF):
         d = cls(ctx or sound._ctx, mode)
         d.add_segments(sound, segments)
@@ -484,6 +526,28 @@ class SoundSequence:
         seq._assembled = out
         return seq
 
+    @classmethod
+    def from_timestamps(cls, sound, timestamps):
+        """SoundSequence::from_timestamps (src/sound.rs:419-430): one new Sound per (start, end, label), cut at
+        round(t * sample_rate) .. round(end * sample_rate) inclusive. The cuts are analysed together
+        (ss_sound_analyze_batch) instead of one Sound::from_samples each."""
+        sr = sound.sample_rate()
+        src = sound.samples()
+        cuts = []
+        for t in timestamps:
+            a, b = int(round(t[0] * sr)), int(round(t[1] * sr))
+            if a < 0 or b + 1 > len(src) or a > b + 1:
+                raise IndexError("timestamp (%r, %r) outside the sound" % (t[0], t[1]))  # the reference panics on the slice
+            cuts.append(src[a:b + 1])
+        off = np.zeros(len(cuts) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([c.shape[0] for c in cuts])
+        flat = np.concatenate(cuts) if cuts else np.zeros(0)
+        ctx = sound._ctx or default_context()
+        mfcc, foff, mp, mean = ctx.analyze_batch(flat, off, sr, NCOEFFS)
+        sounds = [Sound(np.array(c), sr, mfcc[int(foff[j]):int(foff[j + 1])], float(mp[j]), mean[j], t[2], ctx)
+                  for j, (c, t) in enumerate(zip(cuts, timestamps))]
+        return cls(sounds, ctx)
+
     def morph_to(self, distances, dictionary):
         """src/sound.rs:440-449 (batched: one at_distance per (sound, distance) pair)."""
         n = min(len(self._sounds), len(distances))
@@ -518,6 +582,11 @@ class Partitioner:
         self.model = None
         self._ctx = ctx or sound._ctx or default_context()
 
+    @classmethod
+    def from_path(cls, path, ctx=None):
+        """Partitioner::from_path (src/lib.rs:85-88)."""
+        return cls(Sound.from_path(path, ctx), ctx)
+
     def set_depth(self, depth):
         self.depth = int(depth)
         return self
@@ -538,3 +607,50 @@ class Partitioner:
 
     def partition(self):
         return self.partition_other(self.sound)
+
+
+class Timestamp(tuple):
+    """src/sound.rs:508: (start seconds, end seconds, optional label)."""
+
+    def __new__(cls, start, end, label=None):
+        return super().__new__(cls, (float(start), float(end), label))
+
+
+def audacity_labels_to_timestamps(path):
+    """src/sound.rs:511-531: one `start<TAB>end<TAB>label` line per stamp; a field that is missing or does not parse is
+    0.0, a missing label is None."""
+    def num(x):
+        try:
+            return float(x)
+        except (TypeError, ValueError):
+            return 0.0
+    out = []
+    with open(path, "r") as f:
+        for line in f:
+            if not line:
+                continue
+            parts = line.strip().split("\t")
+            out.append(Timestamp(num(parts[0]) if len(parts) > 0 else 0.0, num(parts[1]) if len(parts) > 1 else 0.0,
+                                 parts[2] if len(parts) > 2 else None))
+    return out
+
+
+def _write_wav_i32(path, samples, sample_rate):
+    # hound WavSpec{channels 1, bits 32, Int}; `(sample * i32::MAX as f64) as i32` saturates and truncates toward zero
+    v = np.asarray(samples, dtype=np.float64) * 2147483647.0
+    v = np.where(np.isnan(v), 0.0, v)
+    q = np.clip(np.trunc(v), -2147483648.0, 2147483647.0).astype("<i4")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + q.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, int(sample_rate), int(sample_rate) * 4,
+                4, 32) + b"data" + struct.pack("<I", q.nbytes))
+        f.write(q.tobytes())
+
+
+def write_splits(sound, splits, out_path):
+    """write_splits (src/lib.rs:155-178): consecutive cuts of `sound` written as `<out>/<idx:05>_<len>.wav`, 32-bit PCM."""
+    import os
+    pos, samples = 0, sound.samples()
+    for idx, split in enumerate(splits):
+        split = int(split)
+        _write_wav_i32(os.path.join(out_path, "%05d_%d.wav" % (idx, split)), samples[pos:pos + split], sound.sample_rate())
+        pos += split

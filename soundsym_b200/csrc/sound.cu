@@ -33,10 +33,17 @@ struct SoundState {
     DevBuf<double> d_samples, d_mfcc, d_partial, d_small;
     DevBuf<int32_t> d_pcm;
     DevBuf<unsigned long long> d_maxbits;
-    DevBuf<uint64_t> d_off_a, d_off_b;
+    DevBuf<uint64_t> d_off_a, d_off_b, d_off_pf;
     DevBuf<uint32_t> d_idx;
+    // chunked ingest (ss_sound_analyze / _pcm on long inputs): the H2D copy of chunk k+1 runs on copy_stream while chunk k is
+    // converted and analysed on the ctx stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     ~SoundState() {
         for (auto* t : tables) delete t;
+        for (auto& e : ev_chunk)
+            if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -142,9 +149,21 @@ __device__ __forceinline__ void dft8(cplx* u) {
 constexpr int kMfccWarps = 4;
 constexpr int kHalf = SS_BIN / 2;  // 512
 
+// largest s in [0, n) with off[s] <= x (off ascending, off[0] = 0 <= x < off[n])
+__device__ __forceinline__ uint32_t seg_of(const uint64_t* __restrict__ off, uint32_t n, uint64_t x) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(kMfccWarps * 32)
 k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restrict__ win, const double2* __restrict__ tw,
-       const double* __restrict__ dctm, const int* __restrict__ bins, int c, double energy_floor, double* __restrict__ out) {
+       const double* __restrict__ dctm, const int* __restrict__ bins, int c, double energy_floor, double* __restrict__ out,
+       const uint64_t* __restrict__ frame_off = nullptr, const uint64_t* __restrict__ samp_off = nullptr, uint32_t nsounds = 0) {
     extern __shared__ __align__(16) unsigned char mfcc_smem[];
     double2* s_buf = reinterpret_cast<double2*>(mfcc_smem);                                   // [warps][512]  32 KB
     double* s_pw = reinterpret_cast<double*>(mfcc_smem + sizeof(double2) * kMfccWarps * kHalf);  // [warps][512]  16 KB
@@ -156,7 +175,16 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
     const int kb0 = bins[0], kb1 = bins[c + 1];
 
     for (size_t f = (size_t)blockIdx.x * kMfccWarps + warp; f < frames; f += (size_t)gridDim.x * kMfccWarps) {
-        const double2* s2 = reinterpret_cast<const double2*>(samples + f * SS_HOP);
+        // one sound: frame f starts at sample f * HOP. Batch (ss_sound_analyze_batch): frame f belongs to the sound whose
+        // frame range holds it and starts at that sound's first sample + local frame * HOP (any alignment: scalar loads)
+        size_t start = f * SS_HOP;
+        if (frame_off) {
+            const uint32_t snd = seg_of(frame_off, nsounds, f);
+            start = samp_off[snd] + (f - frame_off[snd]) * SS_HOP;
+        }
+        const bool aligned = (start & 1) == 0;
+        const double* s1 = samples + start;
+        const double2* s2 = reinterpret_cast<const double2*>(s1);
         const double2* w2 = reinterpret_cast<const double2*>(win);
         // ---- pass 0 (Ns = 1): z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]) straight from global memory --------------------
         cplx u[2][8];
@@ -165,7 +193,7 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
             const int i = lane + 32 * h;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                const double2 sv = s2[i + 64 * t];
+                const double2 sv = aligned ? s2[i + 64 * t] : make_double2(s1[2 * (i + 64 * t)], s1[2 * (i + 64 * t) + 1]);
                 const double2 wv = __ldg(&w2[i + 64 * t]);
                 u[h][t] = cplx{sv.x * wv.x, sv.y * wv.y};
             }
@@ -247,6 +275,32 @@ __global__ void k_max_power(const double* __restrict__ samples, size_t frames, u
     }
     for (int o = 16; o; o >>= 1) rms = fmax(rms, __shfl_xor_sync(0xffffffffu, rms, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(rms));  // rms >= 0
+}
+
+// batch forms (ss_sound_analyze_batch): per-sound max power and per-sound mean MFCC
+__global__ void k_max_power_batch(const double* __restrict__ samples, const uint64_t* __restrict__ samp_off, const uint64_t* __restrict__ pf_off,
+                                  uint32_t nsounds, size_t pframes, unsigned long long* __restrict__ out_bits /* nsounds, zeroed */) {
+    const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= pframes) return;
+    const uint32_t snd = seg_of(pf_off, nsounds, f);
+    const double* s = samples + samp_off[snd] + (f - pf_off[snd]) * 64;
+    double acc = 0.0;
+    for (int i = 0; i < 128; i++) acc = __dadd_rn(acc, __dmul_rn(s[i], s[i]));
+    double rms = __dsqrt_rn(__ddiv_rn(acc, 128.0));
+    if (!(rms == rms)) rms = 0.0;
+    atomicMax(&out_bits[snd], (unsigned long long)__double_as_longlong(rms));  // rms >= 0
+}
+// one thread per (sound, coefficient): the reference's row-by-row accumulation, then / frames (NaN for an empty sound)
+__global__ void k_mean_batch(const double* __restrict__ mfcc, const uint64_t* __restrict__ frame_off, uint32_t nsounds, int c,
+                             double* __restrict__ out /* nsounds x c */) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nsounds * c) return;
+    const uint32_t snd = (uint32_t)(t / c);
+    const int col = (int)(t % c);
+    const uint64_t f0 = frame_off[snd], f1 = frame_off[snd + 1];
+    double acc = 0.0;
+    for (uint64_t f = f0; f < f1; f++) acc = acc + mfcc[f * c + col];
+    out[t] = acc / (double)(f1 - f0);
 }
 
 // column sums in two deterministic stages
@@ -342,16 +396,73 @@ int ss_mfcc_dev(ss_ctx* ctx, const double* d_samples, size_t n, double sample_ra
     return mfcc_launch(ctx, d_samples, n, sample_rate, ncoeffs, d_out_mfcc, frames);
 }
 
-// the three analyses on samples already in st->d_samples; stream-synchronised on return
+// Chunked, double-buffered ingest: samples arrive in chunks of kChunkSamples; chunk k+1 is copied
+// host -> device on copy_stream while chunk k is converted (integer PCM) and the MFCC frames it completes are computed on
+// the ctx stream. Works for pinned and pageable host memory alike (with pageable memory the copy call blocks the host,
+// but the previous chunk's kernels are already enqueued). Results are identical to the one-shot path: the same kernels
+// run on sub-ranges, and every frame is independent.
+constexpr size_t kChunkSamples = size_t(4) << 20;
+
+// bits = 0: f64 samples; 16: int16 PCM; 24 / 32: int32 PCM. Leaves the samples in st->d_samples and, if want_mfcc, the MFCC
+// frames in st->d_mfcc.
+static int ingest_chunked(ss_ctx* ctx, SoundState* st, const void* src, size_t n, int bits, double sample_rate, int ncoeffs, bool want_mfcc) {
+    if (!st->copy_stream) {
+        SS_CUDA(ctx, cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : st->ev_chunk) SS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    size_t frames = 0;
+    ss_frame_count(n, &frames);
+    SS_CUDA(ctx, st->d_samples.reserve(n));
+    if (want_mfcc && frames) SS_CUDA(ctx, st->d_mfcc.reserve(frames * (size_t)ncoeffs));
+    const size_t esz = bits == 0 ? sizeof(double) : (bits == 16 ? sizeof(int16_t) : sizeof(int32_t));
+    if (bits) SS_CUDA(ctx, st->d_pcm.reserve(bits == 16 ? (n + 1) / 2 : n));
+    const double denom = bits ? (double)(INT32_MAX >> (32 - bits)) : 1.0;  // src/sound.rs:118-120
+    // the copy stream must not overwrite buffers that earlier work on the ctx stream still reads
+    SS_CUDA(ctx, cudaEventRecord(st->ev_chunk[0], ctx->stream));
+    SS_CUDA(ctx, cudaStreamWaitEvent(st->copy_stream, st->ev_chunk[0], 0));
+    size_t frames_done = 0;
+    int k = 0;
+    for (size_t s0 = 0; s0 < n; s0 += kChunkSamples, k++) {
+        const size_t s1 = std::min(n, s0 + kChunkSamples), cn = s1 - s0;
+        unsigned char* dst = bits == 0 ? reinterpret_cast<unsigned char*>(st->d_samples.p) : reinterpret_cast<unsigned char*>(st->d_pcm.p);
+        SS_CUDA(ctx, cudaMemcpyAsync(dst + s0 * esz, static_cast<const unsigned char*>(src) + s0 * esz, cn * esz, cudaMemcpyHostToDevice,
+                                     st->copy_stream));
+        SS_CUDA(ctx, cudaEventRecord(st->ev_chunk[k & 1], st->copy_stream));
+        SS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->ev_chunk[k & 1], 0));
+        if (bits == 16) {
+            k_decode_pcm16<<<ceil_div((long long)cn, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const int16_t*>(st->d_pcm.p) + s0, cn, denom,
+                                                                                st->d_samples.p + s0);
+            SS_LAUNCHED(ctx);
+        } else if (bits) {
+            k_decode_pcm<<<ceil_div((long long)cn, 256), 256, 0, ctx->stream>>>(st->d_pcm.p + s0, cn, denom, st->d_samples.p + s0);
+            SS_LAUNCHED(ctx);
+        }
+        if (want_mfcc) {
+            size_t f1 = 0;
+            ss_frame_count(s1, &f1);  // frames that lie entirely inside the samples received so far
+            if (f1 > frames_done) {
+                SS_TRY(mfcc_launch(ctx, st->d_samples.p + frames_done * 256, s1 - frames_done * 256, sample_rate, ncoeffs,
+                                   st->d_mfcc.p + frames_done * (size_t)ncoeffs, f1 - frames_done));
+                frames_done = f1;
+            }
+        }
+    }
+    return SS_OK;
+}
+
+// the three analyses on samples already in st->d_samples (mfcc_done: st->d_mfcc already holds the frames);
+// stream-synchronised on return
 static int analyze_resident(ss_ctx* ctx, SoundState* st, size_t n, double sample_rate, int ncoeffs, double* out_mfcc, size_t* out_frames,
-                            double* out_max_power, double* out_mean_mfccs) {
+                            double* out_max_power, double* out_mean_mfccs, bool mfcc_done = false) {
     size_t frames = 0;
     ss_frame_count(n, &frames);
     if (out_frames) *out_frames = frames;
     const bool want_mfcc = out_mfcc || out_mean_mfccs;
     if (want_mfcc && frames) {
-        SS_CUDA(ctx, st->d_mfcc.reserve(frames * (size_t)ncoeffs));
-        SS_TRY(mfcc_launch(ctx, st->d_samples.p, n, sample_rate, ncoeffs, st->d_mfcc.p, frames));
+        if (!mfcc_done) {
+            SS_CUDA(ctx, st->d_mfcc.reserve(frames * (size_t)ncoeffs));
+            SS_TRY(mfcc_launch(ctx, st->d_samples.p, n, sample_rate, ncoeffs, st->d_mfcc.p, frames));
+        }
         if (out_mfcc)
             SS_CUDA(ctx, cudaMemcpyAsync(out_mfcc, st->d_mfcc.p, frames * (size_t)ncoeffs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -388,6 +499,10 @@ int ss_sound_analyze(ss_ctx* ctx, const double* samples, size_t n, double sample
     if (n && !samples) return set_error(ctx, SS_ERR_INVALID, "samples is NULL");
     SS_CUDA(ctx, cudaSetDevice(ctx->device));
     SoundState* st = sound_state(ctx);
+    if (n > kChunkSamples) {
+        SS_TRY(ingest_chunked(ctx, st, samples, n, 0, sample_rate, ncoeffs, out_mfcc || out_mean_mfccs));
+        return analyze_resident(ctx, st, n, sample_rate, ncoeffs, out_mfcc, out_frames, out_max_power, out_mean_mfccs, true);
+    }
     SS_TRY(upload(ctx, st->d_samples, samples, n));
     return analyze_resident(ctx, st, n, sample_rate, ncoeffs, out_mfcc, out_frames, out_max_power, out_mean_mfccs);
 }
@@ -401,6 +516,11 @@ int ss_sound_analyze_pcm(ss_ctx* ctx, const void* pcm, size_t n, int bits_per_sa
     if (n && !pcm) return set_error(ctx, SS_ERR_INVALID, "pcm is NULL");
     SS_CUDA(ctx, cudaSetDevice(ctx->device));
     SoundState* st = sound_state(ctx);
+    if (n > kChunkSamples) {
+        SS_TRY(ingest_chunked(ctx, st, pcm, n, bits_per_sample, sample_rate, ncoeffs, out_mfcc || out_mean_mfccs));
+        if (out_samples) SS_CUDA(ctx, cudaMemcpyAsync(out_samples, st->d_samples.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        return analyze_resident(ctx, st, n, sample_rate, ncoeffs, out_mfcc, out_frames, out_max_power, out_mean_mfccs, true);
+    }
     SS_CUDA(ctx, st->d_samples.reserve(n));
     const double denom = (double)(INT32_MAX >> (32 - bits_per_sample));  // src/sound.rs:118-120
     if (n) {
@@ -417,6 +537,71 @@ int ss_sound_analyze_pcm(ss_ctx* ctx, const void* pcm, size_t n, int bits_per_sa
         if (out_samples) SS_CUDA(ctx, cudaMemcpyAsync(out_samples, st->d_samples.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     return analyze_resident(ctx, st, n, sample_rate, ncoeffs, out_mfcc, out_frames, out_max_power, out_mean_mfccs);
+}
+
+int ss_sound_analyze_batch(ss_ctx* ctx, const double* samples, const uint64_t* sample_offsets, size_t nsounds, double sample_rate, int ncoeffs,
+                           double* out_mfcc, uint64_t* out_frame_offsets, double* out_max_power, double* out_mean_mfccs) {
+    if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");
+    SS_TRY(check_c(ctx, ncoeffs));
+    if (!sample_offsets || !out_frame_offsets) return set_error(ctx, SS_ERR_INVALID, "sample_offsets / out_frame_offsets is NULL");
+    if (nsounds >= 0xFFFFFFFFull) return set_error(ctx, SS_ERR_INVALID, "too many sounds");
+    if (sample_offsets[0] != 0) return set_error(ctx, SS_ERR_INVALID, "sample_offsets[0] must be 0");
+    std::vector<uint64_t> foff(nsounds + 1, 0), poff(nsounds + 1, 0);
+    for (size_t i = 0; i < nsounds; i++) {
+        if (sample_offsets[i + 1] < sample_offsets[i]) return set_error(ctx, SS_ERR_INVALID, "sample_offsets must be non-decreasing");
+        const size_t n = sample_offsets[i + 1] - sample_offsets[i];
+        size_t fr = 0;
+        ss_frame_count(n, &fr);
+        foff[i + 1] = foff[i] + fr;
+        poff[i + 1] = poff[i] + (n >= 128 ? (n - 128) / 64 + 1 : 0);
+    }
+    memcpy(out_frame_offsets, foff.data(), (nsounds + 1) * sizeof(uint64_t));
+    const size_t n = sample_offsets[nsounds], frames = foff[nsounds], pframes = poff[nsounds];
+    if (n && !samples) return set_error(ctx, SS_ERR_INVALID, "samples is NULL");
+    if (!nsounds) return SS_OK;
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SoundState* st = sound_state(ctx);
+    SS_TRY(upload(ctx, st->d_samples, samples, n));
+    SS_TRY(upload(ctx, st->d_off_a, sample_offsets, nsounds + 1));
+    const bool want_mfcc = (out_mfcc || out_mean_mfccs) && frames;
+    if (want_mfcc) {
+        SS_TRY(upload(ctx, st->d_off_b, foff.data(), nsounds + 1));
+        SS_CUDA(ctx, st->d_mfcc.reserve(frames * (size_t)ncoeffs));
+        SoundTables* t = nullptr;
+        SS_TRY(get_tables(ctx, sample_rate, ncoeffs, &t));
+        const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 16);
+        const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * 16);
+        SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(st->d_samples.p, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, ncoeffs,
+                                                             1e-10, st->d_mfcc.p, st->d_off_b.p, st->d_off_a.p, (uint32_t)nsounds);
+        SS_LAUNCHED(ctx);
+        if (out_mfcc)
+            SS_CUDA(ctx, cudaMemcpyAsync(out_mfcc, st->d_mfcc.p, frames * (size_t)ncoeffs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (out_mean_mfccs) {
+        if (!frames) SS_TRY(upload(ctx, st->d_off_b, foff.data(), nsounds + 1));
+        SS_CUDA(ctx, st->d_partial.reserve(nsounds * (size_t)ncoeffs));
+        k_mean_batch<<<ceil_div((long long)nsounds * ncoeffs, 128), 128, 0, ctx->stream>>>(st->d_mfcc.p, st->d_off_b.p, (uint32_t)nsounds, ncoeffs,
+                                                                                         st->d_partial.p);
+        SS_LAUNCHED(ctx);
+        SS_CUDA(ctx, cudaMemcpyAsync(out_mean_mfccs, st->d_partial.p, nsounds * (size_t)ncoeffs * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    }
+    if (out_max_power) {
+        static_assert(sizeof(unsigned long long) == sizeof(double), "max power travels as the bit pattern of a non-negative double");
+        SS_CUDA(ctx, st->d_maxbits.reserve(nsounds));
+        SS_CUDA(ctx, cudaMemsetAsync(st->d_maxbits.p, 0, nsounds * sizeof(unsigned long long), ctx->stream));
+        if (pframes) {
+            DevBuf<uint64_t>& d_poff = st->d_off_pf;
+            SS_TRY(upload(ctx, d_poff, poff.data(), nsounds + 1));
+            k_max_power_batch<<<ceil_div((long long)pframes, 128), 128, 0, ctx->stream>>>(st->d_samples.p, st->d_off_a.p, d_poff.p, (uint32_t)nsounds,
+                                                                                         pframes, st->d_maxbits.p);
+            SS_LAUNCHED(ctx);
+        }
+        SS_CUDA(ctx, cudaMemcpyAsync(out_max_power, st->d_maxbits.p, nsounds * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors (foff, poff) go out of scope
+    return SS_OK;
 }
 
 int ss_mfcc(ss_ctx* ctx, const double* samples, size_t n, double sample_rate, int ncoeffs, double* out_mfcc, size_t* out_frames) {

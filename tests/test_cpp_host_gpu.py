@@ -66,3 +66,38 @@ def test_cpp_partition_and_reconstruction(tmp_path, section71, sample_excerpt):
 def test_cpp_host_mirror_compiles():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples"), "-B"], stdout=subprocess.DEVNULL)
     assert os.path.exists(BIN)
+
+
+@pytest.mark.gpu
+def test_cpp_matcher_flow_from_directories(tmp_path, section71):
+    """examples/matcher.rs through the C++ mirror: write_splits (examples/partition.rs) -> SoundDictionary::from_path on the
+    directory of cuts (batched analysis) -> every query file matched in one call; compared with the Python mirror, which
+    shares nothing with it above the C ABI."""
+    from oracle import oracle as O
+    from soundsym_b200 import api
+    src, mdl = str(tmp_path / "source.wav"), str(tmp_path / "model.bin")
+    ddir, qdir = tmp_path / "dict", tmp_path / "queries"
+    ddir.mkdir(), qdir.mkdir()
+    write_wav(src, section71["pcm"], 16)
+    write_model(mdl, section71)
+    rc, r = run(["-s", src, "-m", mdl, "--depth", "4", "--threshold", "3", "--partition-only", "--write-splits", str(ddir)])
+    splits = [int(x) for x in section71["splits_d4t3"]]
+    assert rc == 0 and r["splits"] == splits
+    files = sorted(os.listdir(ddir))
+    assert files == ["%05d_%d.wav" % (i, s) for i, s in enumerate(splits)]
+    # queries: a few cuts of the same recording at shifted positions, one of them silent
+    s16 = O.decode_pcm(section71["pcm"].astype(np.int32), 16)
+    rng = np.random.default_rng(3)
+    for i in range(6):
+        a = int(rng.integers(0, len(s16) - 30000))
+        write_wav(str(qdir / ("q%d.wav" % i)), section71["pcm"][a:a + int(rng.integers(3000, 20000))], 16)
+    write_wav(str(qdir / "silence.wav"), np.zeros(5000, dtype=np.int16), 16)
+    rc, r = run(["--matcher", str(ddir), str(qdir)])
+    ctx = api.Context(0)
+    d = api.SoundDictionary.from_path(str(ddir), ctx)
+    q = api.SoundDictionary.from_path(str(qdir), ctx)
+    loud = [s for s in q.sounds if not s.max_power() < 0.03]  # examples/matcher.rs:40
+    assert 1 <= len(loud) < 7  # the all-zero file is silent, the loudest passages are not
+    assert rc == 0 and r["dictionary"] == len(splits) and r["queries"] == 7 and r["silent"] == 7 - len(loud)
+    idx, _ = d.match_indices(loud)
+    assert r["matches"] == [[s.name, d.sounds[int(i)].name] for s, i in zip(loud, idx[:, 0])]

@@ -144,3 +144,83 @@ def test_pcm_ingest_equals_decode_then_analyze(ctx, section71, sample_excerpt, t
     assert np.array_equal(snd.samples(), s16)
     with pytest.raises(SoundsymError):
         ctx.analyze_pcm(section71["pcm"], 8)
+
+
+def test_chunked_ingest_equals_one_shot(ctx):
+    """Inputs longer than one ingest chunk (4 Mi samples) go through the double-buffered path: the H2D copy of chunk k+1
+    overlaps the conversion + MFCC of chunk k. Frames are independent, so the result must be bit-identical to analysing
+    the same samples in one piece - checked on windows that straddle every chunk boundary and on both ends."""
+    rng = np.random.default_rng(11)
+    n = 9_500_000 + 777  # three chunks, ragged tail
+    pcm = (rng.standard_normal(n) * 3000).astype(np.int16)
+    samples, mfcc, mp, mean = ctx.analyze_pcm(pcm, 16)
+    ref = pcm.astype(np.float64) / 32767.0
+    assert np.array_equal(samples, ref)
+    frames = (n - 1024) // 256 + 1
+    assert mfcc.shape == (frames, 12)
+    chunk_frames = (4 << 20) // 256
+    for f0 in (0, chunk_frames - 40, 2 * chunk_frames - 40, frames - 80):
+        sub = ref[f0 * 256: (f0 + 79) * 256 + 1024]  # 80 frames, far below the chunk size: one-shot path
+        m_sub, _, _ = ctx.analyze(sub)
+        assert np.array_equal(mfcc[f0:f0 + 80], m_sub), f0
+    # f64 entry point takes the same path
+    m64, mp64, mean64 = ctx.analyze(ref)
+    assert np.array_equal(m64, mfcc) and mp64 == mp and np.array_equal(mean64, mean)
+    pf = np.lib.stride_tricks.sliding_window_view(ref, 128)[::64]
+    assert abs(mp - np.sqrt((pf * pf).sum(axis=1) / 128).max()) <= 1e-12
+    assert np.allclose(mean, mfcc.mean(axis=0), rtol=1e-10, atol=1e-12)
+
+
+def test_analyze_batch_equals_individual(ctx):
+    """ss_sound_analyze_batch: many sounds back to back, framed on their own, one launch. Ragged lengths, odd offsets
+    (misaligned 16-byte loads), sounds without a full MFCC frame or without a full power frame, an empty sound."""
+    rng = np.random.default_rng(5)
+    lens = [5000, 1023, 1024, 1025, 0, 127, 128, 44101, 3333, 256 * 40 + 1024 + 255]
+    sounds = [rng.standard_normal(l) * 0.2 for l in lens]
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    mfcc, foff, mp, mean = ctx.analyze_batch(np.concatenate(sounds), off)
+    assert int(foff[-1]) == mfcc.shape[0]
+    for i, s in enumerate(sounds):
+        m1, mp1, mean1 = ctx.analyze(s)
+        assert int(foff[i + 1] - foff[i]) == m1.shape[0]
+        assert np.array_equal(mfcc[int(foff[i]):int(foff[i + 1])], m1), i
+        assert mp[i] == mp1, i
+        if m1.shape[0]:
+            assert np.allclose(mean[i], mean1, rtol=0, atol=1e-12), i
+        else:
+            assert np.all(np.isnan(mean[i])), i
+    m0, f0, p0, a0 = ctx.analyze_batch(np.zeros(0), np.zeros(1, dtype=np.uint64))
+    assert m0.shape == (0, 12) and f0.tolist() == [0] and p0.shape == (0,)
+
+
+def test_dictionary_from_path_write_splits_and_timestamps(ctx, section71, tmp_path):
+    """write_splits (src/lib.rs:155-178) -> SoundDictionary::from_path (src/sound.rs:304-320) round trip, and
+    SoundSequence::from_timestamps (:419-430); both analyse all their sounds in one batch."""
+    s16 = O.decode_pcm(section71["pcm"].astype(np.int32), 16)
+    snd = api.Sound.from_samples(s16[:200000], 44100.0, None, "src", ctx)
+    splits = [30000, 1500, 70000, 900, 97600]
+    api.write_splits(snd, splits, str(tmp_path))
+    (tmp_path / "notes.txt").write_text("not a wav")
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == ["00000_30000.wav", "00001_1500.wav", "00002_70000.wav", "00003_900.wav", "00004_97600.wav", "notes.txt"]
+    d = api.SoundDictionary.from_path(str(tmp_path), ctx)
+    assert [s.name for s in d.sounds] == [n[:-4] for n in names[:5]]
+    pos = 0
+    for s, ln in zip(d.sounds, splits):
+        one = api.Sound.from_path(str(tmp_path / (s.name + ".wav")), ctx)
+        assert len(s.samples()) == ln and np.array_equal(s.samples(), one.samples())
+        assert np.array_equal(s.mfcc_arrays(), one.mfcc_arrays()) and s.max_power() == one.max_power()
+        # 32-bit PCM of the writer: trunc(sample * i32::MAX) / i32::MAX
+        assert np.array_equal(s.samples(), np.trunc(s16[pos:pos + ln] * 2147483647.0) / 2147483647.0)
+        pos += ln
+    stamps = [api.Timestamp(0.0, 0.5, "a"), api.Timestamp(0.5, 0.51, None), api.Timestamp(1.25, 2.0, "c")]
+    seq = api.SoundSequence.from_timestamps(snd, stamps)
+    assert [s.name for s in seq.sounds()] == ["a", None, "c"]
+    for s, t in zip(seq.sounds(), stamps):
+        a, b = int(round(t[0] * 44100)), int(round(t[1] * 44100))
+        ref = api.Sound.from_samples(s16[a:b + 1], 44100.0, None, None, ctx)
+        assert np.array_equal(s.samples(), ref.samples()) and np.array_equal(s.mfcc_arrays(), ref.mfcc_arrays())
+    assert len(seq.distances()) == 2
+    p = api.Partitioner.from_path(str(tmp_path / "00002_70000.wav"), ctx)
+    assert p.depth == 5 and p.threshold == 4 and p.sound.num_frames() == (70000 - 1024) // 256 + 1
