@@ -361,6 +361,83 @@ k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ dof
     exact[pair] = (la && lb) ? last / (double)(la + lb) : kInf;
 }
 
+// The same refine with one WARP per candidate pair, for sequences of <= 32 frames on both sides (the tensor-core scan's
+// domain). Lane j owns dictionary column j: its frame sits in registers, the query rows are broadcast loads, and the
+// local costs of the whole pair go to shared memory first (39 f64 operations per cell, all 32 lanes busy, coalesced
+// loads - the thread-per-pair form spends its time on 13 fully divergent loads per cell). The recurrence then runs as an
+// anti-diagonal wavefront: at step t lane j computes cell (t - j, j) from its own previous value (up), its left
+// neighbour's previous value (left, one 64-bit shuffle) and the value it received a step earlier (diag). Every cell is
+// produced by the same operations in the same order as in k_dtw_rescore, so the distances stay bit-equal to the oracle.
+__global__ void __launch_bounds__(128)
+k_dtw_rescore_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                   const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
+                   uint32_t t_begin, uint32_t t_end, int kp, int s_begin, int s_count, RescoreBound rb, double* __restrict__ exact,
+                   unsigned long long* __restrict__ counters) {
+    __shared__ double scost[4][32 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = t_begin + blockIdx.x * 4 + warp;
+    if (t >= t_end) return;  // warp-uniform from here on
+    const uint32_t slot = t / (uint32_t)s_count;
+    const uint32_t pair = slot * (uint32_t)kp + (uint32_t)s_begin + t % (uint32_t)s_count;
+    const uint32_t qid = group_qid[slot];
+    const uint32_t idx = cand_idx[pair];
+    if (qid == 0xFFFFFFFFu || idx == 0xFFFFFFFFu) {
+        if (lane == 0) exact[pair] = kInf;
+        return;
+    }
+    if (rb.cand_adist) {
+        double kth = 0.0;
+        for (int s = 0; s < rb.k; s++) {
+            double e = exact[(size_t)slot * kp + s];
+            if (!(e < kInf)) e = kInf;  // empty slot / NaN: nothing can be ruled out
+            kth = fmax(kth, e);
+        }
+        const double na = rb.slot_max_na ? (double)rb.slot_max_na[slot] : (double)rb.max_na[0];
+        if (scan_lower_bound(rb.cand_adist[pair], na, (double)rb.max_nb[0], rb.eps, rb.bound_mode) > kth) {
+            if (lane == 0) exact[pair] = kInf;  // provably outside the top-k
+            return;
+        }
+        if (lane == 0) atomicAdd(&counters[1], 1ull);
+    }
+    const double* a = qmfcc + qoff[qid] * c;
+    const double* b = dmfcc + doff[idx] * c;
+    const int la = (int)(qoff[qid + 1] - qoff[qid]), lb = (int)(doff[idx + 1] - doff[idx]);  // both <= 32 (host-checked)
+    double br[SS_MAX_NCOEFFS];
+#pragma unroll
+    for (int k = 0; k < SS_MAX_NCOEFFS; k++) br[k] = (k < c && lane < lb) ? b[(size_t)lane * c + k] : 0.0;
+    double* cst = scost[warp];
+    for (int i = 0; i < la; i++) {
+        double cost = 0.0;
+#pragma unroll
+        for (int k = 0; k < SS_MAX_NCOEFFS; k++)
+            if (k < c) {
+                const double dlt = a[(size_t)i * c + k] - br[k];
+                cost = cost + dlt * dlt;
+            }
+        cst[i * 32 + lane] = cost;
+    }
+    __syncwarp();
+    double cur = kInf, recv_prev = kInf, result = kInf;  // own last cell D(i-1, j); what the left neighbour sent one step ago
+    for (int step = 0; step < la + lb - 1; step++) {
+        const double recv = __shfl_up_sync(0xffffffffu, cur, 1);  // left neighbour's last cell = D(i, j-1)
+        const int i = step - lane;
+        const bool active = lane < lb && i >= 0 && i < la;
+        if (active) {
+            const double up = cur;                              // D(i-1, j)  (+inf before the first row)
+            const double left = lane ? recv : kInf;             // D(i, j-1)
+            const double diag = lane ? recv_prev : kInf;        // D(i-1, j-1)
+            double m;
+            if (i == 0 && lane == 0) m = 0.0;
+            else m = fmin(fmin(up, left), diag);
+            cur = cst[i * 32 + lane] + m;
+            if (i == la - 1 && lane == lb - 1) result = cur;
+        }
+        recv_prev = recv;
+    }
+    result = __shfl_sync(0xffffffffu, result, lb > 0 ? lb - 1 : 0);
+    if (lane == 0) exact[pair] = (la && lb) ? result / (double)(la + lb) : kInf;
+}
+
 __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
                                const double* __restrict__ exact, const uint32_t* __restrict__ group_qid, uint32_t nslots, int kp,
                                int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb, double eps,
@@ -438,6 +515,13 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
         if (s_count <= 0) continue;
         RescoreBound rb = {phase ? d->d_cand_adist.p : nullptr, d_max_na, d_max_nb, d_slot_max_na, eps, bound_mode, std::min(k, kp)};
         const uint32_t nt = nslots * (uint32_t)s_count;
+        if (max_ld <= 32 && q->max_len <= 32) {  // one warp per pair
+            k_dtw_rescore_warp<<<ceil_div(nt, 4), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,
+                                                                         d->d_cand_idx.p, 0, nt, kp, s_begin, s_count, rb, d->d_cand_exact.p,
+                                                                         d->d_counters.p);
+            SS_LAUNCHED(ctx);
+            continue;
+        }
         for (uint32_t tb = 0; tb < nt; tb += batch) {
             const uint32_t te = std::min<uint32_t>(nt, tb + batch);
             kern<<<ceil_div(te - tb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,
