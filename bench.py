@@ -7,11 +7,11 @@ Workload (config 4 of BASELINE.json): synthetic dictionary of 10
 (top-1, SS_DTW). With N GPUs the dictionary is partitioned into N contiguous shards (balanced by frames), every rank
 sees all queries, per-rank top-k are all-gathered over NCCL and merged on every rank  ->  "scaling": "strong".
 
-  value      cells/s with the queries' f64 MFCCs already in HBM: layout kernel + fp32 scan + merge + f64 refine
+  value      cells/s with the queries' f64 MFCCs already in HBM: layout kernel + tensor-core scan + merge + f64 refine
              (+ all-gather + merge for N > 1), CUDA events on the library's stream, max over ranks.
   e2e        the same through the reference-facing call ss_dict_match with pinned HOST buffers: H2D of the queries and
              D2H of the results inside the timed region, every step.
-  roofline   the dominant kernel (k_dtw_scan), timed live with CUDA events around its launch (ss_dict_last_scan_ms);
+  roofline   the dominant kernel (k_dtw_scan_tc), timed live with CUDA events around its launch (ss_dict_last_scan_ms);
              algorithmic bytes = sum over pairs of (Lq + Ld) * C * 4 B, peak = MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference   the f64 CPU oracle ("port": the Rust reference cannot be built here) on a bounded
              sample of the same workload, on the box's host cores.
@@ -355,9 +355,9 @@ def main():
                                  "or the tensor pipe",
                          "issue_bound": {"cells_per_clk_per_sm": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) / 148.0
                                          / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) if scan_ms > 0 else None,
-                                         "ceiling_cells_per_clk_per_sm": 42.7,
-                                         "ceiling_note": "band loop = 1/2 FADD2 + FMNMX3 + FADD per cell: 1.5 FMA-pipe ops per cell at the measured "
-                                                         "64 lanes / clk / SM"},
+                                         "ceiling_cells_per_clk_per_sm": 45.3,
+                                         "ceiling_note": "the register-resident band alone (FMNMX3 + FADD per cell, no TMEM, no barriers) measured on "
+                                                         "B200 with 16 warps / SM: tools/microbench_band.cu, profiles/r1_microbench_band.log"},
                          "cells_per_s_kernel": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) if scan_ms > 0 else None},
             "cpu_baseline": cpu,
             "uncertified_queries": int(uncert),
