@@ -51,7 +51,7 @@ class ClockSampler:
     is used instead of an `nvidia-smi -lms` child because starting nvidia-smi next to a ~1 s timed region stalled the
     driver and inflated the measured step by 30-60 % (measured; see DESIGN.md "Measurement")."""
 
-    def __init__(self, gpu_index, period_s=0.2):
+    def __init__(self, gpu_index, period_s=0.01):
         self.gpu, self.period = gpu_index, period_s
         self.rows, self.on, self.t, self.h = [], False, None, None
         try:
@@ -71,20 +71,24 @@ class ClockSampler:
         except Exception:
             self.h = None
 
-    def _loop(self):
+    def _sample(self):
         nv = self.nv
-        while self.alive:
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
             try:
-                if self.on:
-                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                    try:
-                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    except Exception:
-                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                    self.rows.append((sm, pw, rs))
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((sm, pw, rs))
+        except Exception:
+            pass
+
+    def _loop(self):
+        # the timed region of an 8-GPU run is ~40 ms: sample every 10 ms while it is on
+        while self.alive:
+            if self.on:
+                self._sample()
             time.sleep(self.period)
 
     def prepare(self):
@@ -99,6 +103,8 @@ class ClockSampler:
         self.on = True
 
     def stop(self):
+        if self.h is not None and self.on and not self.rows:
+            self._sample()  # region shorter than one period: one reading while the last step is still in flight
         self.on = False
         self.alive = False
         if self.h is None or not self.rows:
