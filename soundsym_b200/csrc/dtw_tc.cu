@@ -46,6 +46,7 @@ constexpr int kTcBTileBytes = kTcN * kTcK * 2;  // 3072: one dictionary tile
 constexpr int kTcStages = 4;       // B-tile ring
 constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows of the tile; two buffers (all 512 TMEM columns at 4 slots)
 constexpr int kTcMaxLen = 32;
+constexpr int kTcPairCol = 16;     // segments of <= 16 frames share a slot two by two: the second one's columns start here
 constexpr int kTcDpWarps = 4 * kTcSlots;             // warp w: TMEM lane quadrant w % 4, segment slot w / 4
 // The producer warp sits in a warpgroup of its own (three idle warps) that hands its registers to the DP warpgroups
 // (setmaxnreg): 3 slots -> 512 threads, 128 at launch, DP 152 / producer 48; 4 slots -> 640 threads, 96 at launch, DP 112 /
@@ -247,9 +248,11 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
     const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = kTcN
     if (t >= ntiles) return;
     const int W = 32;  // slot width
-    const int slot = (int)n / W, j = (int)n % W;
-    const int2 sl = reinterpret_cast<const int2*>(desc)[(size_t)t * 4 + slot];
-    const int seg = sl.x, len = sl.y;
+    const int slot = (int)n / W;
+    int j = (int)n % W;
+    const int4 sl = desc[(size_t)t * 4 + slot];  // {segment A, length A, segment B, length B}; B >= 0: a pair of short segments
+    int seg = sl.x, len = sl.y;
+    if (sl.z >= 0 && j >= kTcPairCol) seg = sl.z, len = sl.w, j -= kTcPairCol;  // B's columns start at column 16 of the slot
     __half row[kTcK];
 #pragma unroll
     for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
@@ -535,6 +538,95 @@ __device__ __forceinline__ float tc_tile(uint32_t L, uint32_t lmin, uint32_t Lm,
     return res;
 }
 
+// ---- two short segments (<= 16 frames each) in one slot: columns [0, 4 NG) and [16, 16 + 4 NG) ---------------------------
+// A step for short segments is mostly hand-off overhead (about 30 of its 42..102 instructions); sharing it between two
+// segments halves that. The two bands are independent: each has its own row state, carry and capture. Both run with the
+// larger of the two column-group counts, so a band's column len - 1 can sit in any group: the capture steps keep the
+// whole of row i (FULL) and pick by index.
+template <int N>
+__device__ __forceinline__ float tc_pick_n(const float (&v)[N], int idx) {
+    float r = v[0];
+#pragma unroll
+    for (int j = 1; j < N; j++) r = idx == j ? v[j] : r;
+    return r;
+}
+template <int NG, bool FULL>
+__device__ __forceinline__ void tc_dp_band_pair(const float (&tm0)[4 * NG], const float (&tm1)[4 * NG], float (&d)[4 * NG], float dinit,
+                                                float (&row0)[4 * NG]) {
+    const float INF = __int_as_float(0x7f800000);
+    float left0 = INF, diag0 = dinit, left1 = INF;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const float up0 = d[j];
+        const float c0 = tm0[j] + tc_min3(left0, up0, diag0);
+        const float c1 = tm1[j] + tc_min3(left1, c0, left0);
+        diag0 = up0;
+        left0 = c0;
+        left1 = c1;
+        d[j] = c1;
+        if (FULL) row0[j] = c0;
+    }
+}
+template <int NG, bool FULL>
+__device__ __forceinline__ void tc_step2_pair(TcCursor& cur, float (&dA)[4 * NG], float (&dB)[4 * NG], float dinit, float (&rowA)[4 * NG],
+                                              float (&rowB)[4 * NG]) {
+    cur.wait();
+    const uint32_t taddr = cur.taddr;
+    {
+        float a0[4 * NG], a1[4 * NG];
+        tc_ld_row<NG>(taddr, a0);
+        tc_ld_row<NG>(taddr + kTcN, a1);
+        tc_wait_ld();
+        tc_dp_band_pair<NG, FULL>(a0, a1, dA, dinit, rowA);
+    }
+    float b0[4 * NG], b1[4 * NG];
+    tc_ld_row<NG>(taddr + kTcPairCol, b0);
+    tc_ld_row<NG>(taddr + kTcN + kTcPairCol, b1);
+    tc_wait_ld();
+    cur.release();
+    tc_dp_band_pair<NG, FULL>(b0, b1, dB, dinit, rowB);
+}
+// returns D(Lm-1, lenA-1) and D(Lm-1, lenB-1); lenB = 0 when the slot's second place is empty
+template <int NG>
+__device__ __forceinline__ void tc_tile_pair(uint32_t L, uint32_t lmin, uint32_t Lm, int lenA, int lenB, TcCursor& cur, float& resA, float& resB) {
+    const float INF = __int_as_float(0x7f800000);
+    float dA[4 * NG], dB[4 * NG];
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) dA[j] = INF, dB[j] = INF;
+    resA = INF, resB = INF;
+    float dinit = 0.f;
+    const uint32_t nfull = L >> 1;
+    const uint32_t ncap = min((lmin - 1) >> 1, nfull);
+    uint32_t st = 0;
+#pragma unroll 1
+    for (; st < ncap; st++) {  // no query of the group ends in these steps
+        float rowA[4 * NG], rowB[4 * NG];
+        tc_step2_pair<NG, false>(cur, dA, dB, dinit, rowA, rowB);
+        dinit = INF;
+    }
+#pragma unroll 1
+    for (; st < nfull; st++) {  // only the last step or two of a tile
+        float rowA[4 * NG], rowB[4 * NG];
+        tc_step2_pair<NG, true>(cur, dA, dB, dinit, rowA, rowB);
+        dinit = INF;
+        const bool end0 = 2 * st + 1 == Lm, end1 = 2 * st + 2 == Lm;  // this lane's query ends in this band?
+        resA = end0 ? tc_pick_n<4 * NG>(rowA, lenA - 1) : (end1 ? tc_pick_n<4 * NG>(dA, lenA - 1) : resA);
+        resB = end0 ? tc_pick_n<4 * NG>(rowB, lenB - 1) : (end1 ? tc_pick_n<4 * NG>(dB, lenB - 1) : resB);
+    }
+    if (L & 1) {  // odd group length: the last step carries one row
+        cur.wait();
+        float a0[4 * NG], b0[4 * NG];
+        tc_ld_row<NG>(cur.taddr, a0);
+        tc_ld_row<NG>(cur.taddr + kTcPairCol, b0);
+        tc_wait_ld();
+        cur.release();
+        tc_dp_row_ng<NG>(a0, dA, dinit);
+        tc_dp_row_ng<NG>(b0, dB, dinit);
+        resA = (L == Lm) ? tc_pick_n<4 * NG>(dA, lenA - 1) : resA;
+        resB = (L == Lm) ? tc_pick_n<4 * NG>(dB, lenB - 1) : resB;
+    }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -633,8 +725,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         TcCursor cur;
         cur.init(s32(t_full), lane_addr);
         for (uint32_t n = 0; n < ntiles; n++) {
-            const int2 sl = __ldg(reinterpret_cast<const int2*>(p.desc) + (size_t)(t0 + n) * 4 + slot);  // {segment, length} of this slot
+            const int4 sl = __ldg(p.desc + (size_t)(t0 + n) * 4 + slot);  // {segment A, length A, segment B, length B} of this slot
             const int seg = sl.x, len = sl.y;
+            if (sl.z >= 0) {  // a pair of short segments (warp-uniform: the slot is the warp's)
+                const int ngp = (max(sl.y, sl.w) + 3) >> 2;
+                float resA, resB;
+                switch (ngp) {
+                    case 1: tc_tile_pair<1>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
+                    case 2: tc_tile_pair<2>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
+                    case 3: tc_tile_pair<3>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
+                    default: tc_tile_pair<4>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
+                }
+                if (Lm) {
+                    tc_insert<KP>(list, worst, __fdividef(resA, (float)(Lm + (uint32_t)sl.y)), (uint32_t)sl.x);
+                    if (sl.w > 0) tc_insert<KP>(list, worst, __fdividef(resB, (float)(Lm + (uint32_t)sl.w)), (uint32_t)sl.z);
+                }
+                continue;
+            }
             const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
             float res;
             switch (ng) {  // one dispatch per tile
@@ -712,21 +819,32 @@ int dtw_tc_dict_build(ss_dict* d) {
         if (d->h_off[s + 1] > d->h_off[s]) order.push_back((uint32_t)s);
     auto len_of = [&](uint32_t s) { return (int)(d->h_off[s + 1] - d->h_off[s]); };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
-    const uint32_t ntiles = (uint32_t)((order.size() + kTcSlots - 1) / kTcSlots);
-    std::vector<int4> desc(2 * (size_t)ntiles);
-    d->h_tc_tile_frames.assign(ntiles, 0);
-    for (uint32_t t = 0; t < ntiles; t++) {
-        int sg[kTcSlots], ln[kTcSlots];
-        for (int s = 0; s < kTcSlots; s++) {
-            const size_t o = (size_t)t * kTcSlots + s;
-            sg[s] = o < order.size() ? (int)order[o] : -1;
-            ln[s] = o < order.size() ? len_of(order[o]) : 0;
-            d->h_tc_tile_frames[t] += (uint32_t)ln[s];
-        }
-        // four {segment, length} pairs per tile (the fourth is empty with 3 slots)
-        desc[2 * t] = make_int4(sg[0], ln[0], sg[1], ln[1]);
-        desc[2 * t + 1] = make_int4(sg[2], ln[2], kTcSlots > 3 ? sg[kTcSlots - 1] : -1, kTcSlots > 3 ? ln[kTcSlots - 1] : 0);
+    // A tile has 4 slots of 32 columns. A segment longer than 16 frames takes a slot of its own; shorter ones share a slot
+    // two by two (the second at column 16), so that the per-step hand-off is paid once for both. Per slot the descriptor is
+    // {segment A, length A, segment B, length B}, B = -1 when absent.
+    static int pairing = -1;
+    if (pairing < 0) {
+        const char* e = getenv("SS_DTW_TC_PAIR");
+        pairing = e ? atoi(e) : 1;
     }
+    std::vector<int4> desc;
+    d->h_tc_tile_frames.clear();  // per tile: an instruction-count estimate of one pipeline step (slice balancing)
+    for (size_t o = 0; o < order.size();) {
+        const bool pair = pairing && len_of(order[o]) <= kTcPairCol;
+        const size_t take = std::min<size_t>(order.size() - o, pair ? 2 * kTcSlots : kTcSlots);
+        uint32_t cost = 0;
+        for (int sidx = 0; sidx < 4; sidx++) {
+            int4 e = make_int4(-1, 0, -1, 0);
+            if (sidx < kTcSlots && (size_t)sidx < take) e.x = (int)order[o + sidx], e.y = len_of(order[o + sidx]);
+            if (pair && (size_t)(kTcSlots + sidx) < take) e.z = (int)order[o + kTcSlots + sidx], e.w = len_of(order[o + kTcSlots + sidx]);
+            if (pair && e.x >= 0 && e.z < 0) e.z = e.x, e.w = 0;  // a pair slot without a partner: B = an empty band of A's segment (never inserted: length 0)
+            desc.push_back(e);
+            cost = std::max<uint32_t>(cost, 32u + 16u * (uint32_t)(((e.y + 3) >> 2) + (e.z >= 0 ? ((std::max(e.y, e.w) + 3) >> 2) : 0)));
+        }
+        d->h_tc_tile_frames.push_back(cost);
+        o += take;
+    }
+    const uint32_t ntiles = (uint32_t)(desc.size() / 4);
     d->tc_ntiles = ntiles;
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
     SS_CUDA(ctx, d->d_mu.reserve(16));
@@ -847,7 +965,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     static int waves = 0;
     if (!waves) {
         const char* e = getenv("SS_DTW_TC_WAVES");
-        waves = e ? std::max(1, atoi(e)) : 8;
+        waves = e ? std::max(1, atoi(e)) : 16;
     }
     uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->tc_ntiles, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups));
     std::vector<uint32_t>& st = d->h_slice_tile;

@@ -196,3 +196,31 @@ def test_fp32_scan_forced_matches_tensor_core_scan(ctx):
     i2, dd2 = fp.match(q, qoff, SS_DTW, 4)
     assert np.array_equal(i1, i2) and np.array_equal(d1, dd2)
     assert fp.last_tc_fallback == 0
+
+
+def test_tc_scan_declines_loud_queries_and_rekeys_query_blocks_per_dictionary(ctx):
+    """(1) The tensor-core scan carries |a|^2 / s in one fp16 slot: queries far louder than the dictionary would overflow
+    it, so they must take the fp32 scan and still come out exact. (2) The fp16 query blocks are centred on the dictionary's
+    mean frame and scaled by its s: one resident query batch matched against two different dictionaries must be rebuilt
+    for the second one."""
+    import torch
+    d, doff = synth.segments(300, 13, seed=41)
+    q, qoff = synth.segments(40, 13, seed=42)
+    dev = api.DeviceDictionary(ctx, d, doff)
+    loud = q * 400.0
+    idx, dist = dev.match(loud, qoff, SS_DTW, 2)
+    oidx, odist = O.dtw_topk(d, doff, loud, qoff, 13, 2)
+    check_dtw(idx, dist, oidx, odist, 2)
+    assert dev.last_uncertified == 0
+    d2 = d * 0.5 + 37.5  # another mean frame, another norm scale
+    dev2 = api.DeviceDictionary(ctx, d2, doff)
+    qs = api.DeviceQueries(ctx, q, qoff)
+    nq = len(qoff) - 1
+    o_idx = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+    o_dist = torch.empty((nq, 2), dtype=torch.float64, device="cuda")
+    for dd, dv in ((d, dev), (d2, dev2), (d, dev)):
+        ctx.check(ctx.lib.ss_dict_match_dev(dv.h, qs.h, SS_DTW, None, 2, o_idx.data_ptr(), o_dist.data_ptr()))
+        ctx.sync()
+        oidx, odist = O.dtw_topk(dd, doff, q, qoff, 13, 2)
+        check_dtw(o_idx.cpu().numpy().astype(np.uint32), o_dist.cpu().numpy(), oidx, odist, 2)
+        assert dv.last_uncertified == 0 and dv.last_tc_fallback == 0
