@@ -327,8 +327,9 @@ struct TcParams {
     uint32_t ngroups;
     const unsigned char* tiles;
     const int4* desc;
-    const uint32_t* slice_tile;  // nslices + 1
-    uint32_t nslices;
+    const uint32_t* slice_tile;  // all slices + 1
+    uint32_t nslices;            // slices of THIS launch, starting at slice_begin
+    uint32_t slice_begin;
     unsigned long long* partial;  // [nslices * 3 slots][ngroups * 128][KP]
     uint32_t max_len;
 };
@@ -541,8 +542,8 @@ __device__ __forceinline__ float tc_tile(uint32_t L, uint32_t lmin, uint32_t Lm,
 // ---- two short segments (<= 16 frames each) in one slot: columns [0, 4 NG) and [16, 16 + 4 NG) ---------------------------
 // A step for short segments is mostly hand-off overhead (about 30 of its 42..102 instructions); sharing it between two
 // segments halves that. The two bands are independent: each has its own row state, carry and capture. Both run with the
-// larger of the two column-group counts, so a band's column len - 1 can sit in any group: the capture steps keep the
-// whole of row i (FULL) and pick by index.
+// larger of the two column-group counts, so a band's column len - 1 can sit in any group: the capture steps select it by
+// index (CAP), column by column.
 template <int N>
 __device__ __forceinline__ float tc_pick_n(const float (&v)[N], int idx) {
     float r = v[0];
@@ -550,9 +551,9 @@ __device__ __forceinline__ float tc_pick_n(const float (&v)[N], int idx) {
     for (int j = 1; j < N; j++) r = idx == j ? v[j] : r;
     return r;
 }
-template <int NG, bool FULL>
-__device__ __forceinline__ void tc_dp_band_pair(const float (&tm0)[4 * NG], const float (&tm1)[4 * NG], float (&d)[4 * NG], float dinit,
-                                                float (&row0)[4 * NG]) {
+template <int NG, bool CAP>
+__device__ __forceinline__ void tc_dp_band_pair(const float (&tm0)[4 * NG], const float (&tm1)[4 * NG], float (&d)[4 * NG], float dinit, int len,
+                                                float& e0) {
     const float INF = __int_as_float(0x7f800000);
     float left0 = INF, diag0 = dinit, left1 = INF;
 #pragma unroll
@@ -564,12 +565,12 @@ __device__ __forceinline__ void tc_dp_band_pair(const float (&tm0)[4 * NG], cons
         left0 = c0;
         left1 = c1;
         d[j] = c1;
-        if (FULL) row0[j] = c0;
+        if (CAP) e0 = j == len - 1 ? c0 : e0;  // D(i, len-1); the second row's value stays in d[len-1]
     }
 }
-template <int NG, bool FULL>
-__device__ __forceinline__ void tc_step2_pair(TcCursor& cur, float (&dA)[4 * NG], float (&dB)[4 * NG], float dinit, float (&rowA)[4 * NG],
-                                              float (&rowB)[4 * NG]) {
+template <int NG, bool CAP>
+__device__ __forceinline__ void tc_step2_pair(TcCursor& cur, float (&dA)[4 * NG], float (&dB)[4 * NG], float dinit, int lenA, int lenB, float& e0A,
+                                              float& e0B) {
     cur.wait();
     const uint32_t taddr = cur.taddr;
     {
@@ -577,14 +578,14 @@ __device__ __forceinline__ void tc_step2_pair(TcCursor& cur, float (&dA)[4 * NG]
         tc_ld_row<NG>(taddr, a0);
         tc_ld_row<NG>(taddr + kTcN, a1);
         tc_wait_ld();
-        tc_dp_band_pair<NG, FULL>(a0, a1, dA, dinit, rowA);
+        tc_dp_band_pair<NG, CAP>(a0, a1, dA, dinit, lenA, e0A);
     }
     float b0[4 * NG], b1[4 * NG];
     tc_ld_row<NG>(taddr + kTcPairCol, b0);
     tc_ld_row<NG>(taddr + kTcN + kTcPairCol, b1);
     tc_wait_ld();
     cur.release();
-    tc_dp_band_pair<NG, FULL>(b0, b1, dB, dinit, rowB);
+    tc_dp_band_pair<NG, CAP>(b0, b1, dB, dinit, lenB, e0B);
 }
 // returns D(Lm-1, lenA-1) and D(Lm-1, lenB-1); lenB = 0 when the slot's second place is empty
 template <int NG>
@@ -600,18 +601,18 @@ __device__ __forceinline__ void tc_tile_pair(uint32_t L, uint32_t lmin, uint32_t
     uint32_t st = 0;
 #pragma unroll 1
     for (; st < ncap; st++) {  // no query of the group ends in these steps
-        float rowA[4 * NG], rowB[4 * NG];
-        tc_step2_pair<NG, false>(cur, dA, dB, dinit, rowA, rowB);
+        float e0A, e0B;
+        tc_step2_pair<NG, false>(cur, dA, dB, dinit, lenA, lenB, e0A, e0B);
         dinit = INF;
     }
 #pragma unroll 1
     for (; st < nfull; st++) {  // only the last step or two of a tile
-        float rowA[4 * NG], rowB[4 * NG];
-        tc_step2_pair<NG, true>(cur, dA, dB, dinit, rowA, rowB);
+        float e0A = INF, e0B = INF;
+        tc_step2_pair<NG, true>(cur, dA, dB, dinit, lenA, lenB, e0A, e0B);
         dinit = INF;
         const bool end0 = 2 * st + 1 == Lm, end1 = 2 * st + 2 == Lm;  // this lane's query ends in this band?
-        resA = end0 ? tc_pick_n<4 * NG>(rowA, lenA - 1) : (end1 ? tc_pick_n<4 * NG>(dA, lenA - 1) : resA);
-        resB = end0 ? tc_pick_n<4 * NG>(rowB, lenB - 1) : (end1 ? tc_pick_n<4 * NG>(dB, lenB - 1) : resB);
+        resA = end0 ? e0A : (end1 ? tc_pick_n<4 * NG>(dA, lenA - 1) : resA);
+        resB = end0 ? e0B : (end1 ? tc_pick_n<4 * NG>(dB, lenB - 1) : resB);
     }
     if (L & 1) {  // odd group length: the last step carries one row
         cur.wait();
@@ -627,7 +628,9 @@ __device__ __forceinline__ void tc_tile_pair(uint32_t L, uint32_t lmin, uint32_t
     }
 }
 
-template <int KP>
+// PAIRED selects the tile kind the launch covers (the dictionary's tiles are sorted: single-segment slots first, paired
+// slots after; each kind gets its own instantiation so that neither pays for the other's registers and code).
+template <int KP, bool PAIRED>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // [A tiles: max_len x 4 KB][B ring: 4 x 3 KB][barriers][candidate lists], 128-byte aligned
@@ -644,7 +647,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][384]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x / p.nslices, slice = blockIdx.x % p.nslices;
+    const uint32_t g = blockIdx.x / p.nslices, slice = p.slice_begin + blockIdx.x % p.nslices;
+    // the other tile kind's launch may start filling SMs as this one's CTAs retire (programmatic dependent launch; the two
+    // write disjoint candidate lists and neither reads the other's output)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t glen = p.group_len[g];
     const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;  // longest (= rows of the A block) and shortest query of the group
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
@@ -726,36 +732,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         cur.init(s32(t_full), lane_addr);
         for (uint32_t n = 0; n < ntiles; n++) {
             const int4 sl = __ldg(p.desc + (size_t)(t0 + n) * 4 + slot);  // {segment A, length A, segment B, length B} of this slot
-            const int seg = sl.x, len = sl.y;
-            if (sl.z >= 0) {  // a pair of short segments (warp-uniform: the slot is the warp's)
+            if constexpr (PAIRED) {  // two short segments per slot (an empty place has length 0)
                 const int ngp = (max(sl.y, sl.w) + 3) >> 2;
                 float resA, resB;
                 switch (ngp) {
+                    case 0:
                     case 1: tc_tile_pair<1>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
                     case 2: tc_tile_pair<2>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
                     case 3: tc_tile_pair<3>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
                     default: tc_tile_pair<4>(L, lmin, Lm, sl.y, sl.w, cur, resA, resB); break;
                 }
                 if (Lm) {
-                    tc_insert<KP>(list, worst, __fdividef(resA, (float)(Lm + (uint32_t)sl.y)), (uint32_t)sl.x);
+                    if (sl.y > 0) tc_insert<KP>(list, worst, __fdividef(resA, (float)(Lm + (uint32_t)sl.y)), (uint32_t)sl.x);
                     if (sl.w > 0) tc_insert<KP>(list, worst, __fdividef(resB, (float)(Lm + (uint32_t)sl.w)), (uint32_t)sl.z);
                 }
-                continue;
+            } else {
+                const int seg = sl.x, len = sl.y;
+                const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
+                float res;
+                switch (ng) {  // one dispatch per tile
+                    case 1: res = tc_tile<1>(L, lmin, Lm, len, cur); break;
+                    case 2: res = tc_tile<2>(L, lmin, Lm, len, cur); break;
+                    case 3: res = tc_tile<3>(L, lmin, Lm, len, cur); break;
+                    case 4: res = tc_tile<4>(L, lmin, Lm, len, cur); break;
+                    case 5: res = tc_tile<5>(L, lmin, Lm, len, cur); break;
+                    case 6: res = tc_tile<6>(L, lmin, Lm, len, cur); break;
+                    case 7: res = tc_tile<7>(L, lmin, Lm, len, cur); break;
+                    default: res = tc_tile<8>(L, lmin, Lm, len, cur); break;
+                }
+                // result: D(Lm-1, len-1) / (Lm + len)
+                if (seg >= 0 && Lm) tc_insert<KP>(list, worst, __fdividef(res, (float)(Lm + (uint32_t)len)), (uint32_t)seg);
             }
-            const int ng = (len + 3) >> 2;  // 4-column groups of the DP row (tile-uniform up to +-1: segments are sorted by length)
-            float res;
-            switch (ng) {  // one dispatch per tile
-                case 1: res = tc_tile<1>(L, lmin, Lm, len, cur); break;
-                case 2: res = tc_tile<2>(L, lmin, Lm, len, cur); break;
-                case 3: res = tc_tile<3>(L, lmin, Lm, len, cur); break;
-                case 4: res = tc_tile<4>(L, lmin, Lm, len, cur); break;
-                case 5: res = tc_tile<5>(L, lmin, Lm, len, cur); break;
-                case 6: res = tc_tile<6>(L, lmin, Lm, len, cur); break;
-                case 7: res = tc_tile<7>(L, lmin, Lm, len, cur); break;
-                default: res = tc_tile<8>(L, lmin, Lm, len, cur); break;
-            }
-            // result: D(Lm-1, len-1) / (Lm + len)
-            if (seg >= 0 && Lm) tc_insert<KP>(list, worst, __fdividef(res, (float)(Lm + (uint32_t)len)), (uint32_t)seg);
         }
         unsigned long long* out = p.partial + (((size_t)slice * kTcSlots + slot) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
 #pragma unroll
@@ -828,6 +835,7 @@ int dtw_tc_dict_build(ss_dict* d) {
         pairing = e ? atoi(e) : 1;
     }
     std::vector<int4> desc;
+    d->tc_first_pair_tile = 0xFFFFFFFFu;
     d->h_tc_tile_frames.clear();  // per tile: an instruction-count estimate of one pipeline step (slice balancing)
     for (size_t o = 0; o < order.size();) {
         const bool pair = pairing && len_of(order[o]) <= kTcPairCol;
@@ -837,13 +845,14 @@ int dtw_tc_dict_build(ss_dict* d) {
             int4 e = make_int4(-1, 0, -1, 0);
             if (sidx < kTcSlots && (size_t)sidx < take) e.x = (int)order[o + sidx], e.y = len_of(order[o + sidx]);
             if (pair && (size_t)(kTcSlots + sidx) < take) e.z = (int)order[o + kTcSlots + sidx], e.w = len_of(order[o + kTcSlots + sidx]);
-            if (pair && e.x >= 0 && e.z < 0) e.z = e.x, e.w = 0;  // a pair slot without a partner: B = an empty band of A's segment (never inserted: length 0)
             desc.push_back(e);
-            cost = std::max<uint32_t>(cost, 32u + 16u * (uint32_t)(((e.y + 3) >> 2) + (e.z >= 0 ? ((std::max(e.y, e.w) + 3) >> 2) : 0)));
+            cost = std::max<uint32_t>(cost, 32u + 16u * (uint32_t)(pair ? 2 * ((std::max(e.y, e.w) + 3) >> 2) : ((e.y + 3) >> 2)));
         }
+        if (pair && d->tc_first_pair_tile == 0xFFFFFFFFu) d->tc_first_pair_tile = (uint32_t)d->h_tc_tile_frames.size();
         d->h_tc_tile_frames.push_back(cost);
         o += take;
     }
+    if (d->tc_first_pair_tile == 0xFFFFFFFFu) d->tc_first_pair_tile = (uint32_t)d->h_tc_tile_frames.size();
     const uint32_t ntiles = (uint32_t)(desc.size() / 4);
     d->tc_ntiles = ntiles;
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
@@ -933,12 +942,32 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
     return SS_OK;
 }
 
-template <int KP>
-static int tc_launch(ss_ctx* ctx, const TcParams& p, uint32_t grid, size_t smem, uint32_t nlists, uint32_t nslots, ss_dict* d) {
-    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_tc<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
-    k_dtw_scan_tc<KP><<<grid, kTcThreads, smem, ctx->stream>>>(p);
+template <int KP, bool PAIRED>
+static int tc_launch_kind(ss_ctx* ctx, TcParams p, uint32_t slice_begin, uint32_t nslices, size_t smem, bool dependent) {
+    if (!nslices) return SS_OK;
+    p.slice_begin = slice_begin;
+    p.nslices = nslices;
+    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_tc<KP, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.ngroups * nslices);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;  // may start while the previous scan launch is still draining
+    cfg.attrs = attr;
+    cfg.numAttrs = dependent ? 1 : 0;
+    SS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_dtw_scan_tc<KP, PAIRED>, p));
     SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+// slices [0, nsingle) hold single-segment tiles, [nsingle, nslices) paired ones
+template <int KP>
+static int tc_launch(ss_ctx* ctx, const TcParams& p, uint32_t nsingle, uint32_t nslices, size_t smem, uint32_t nlists, uint32_t nslots, ss_dict* d) {
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
+    SS_TRY((tc_launch_kind<KP, false>(ctx, p, 0, nsingle, smem, false)));
+    SS_TRY((tc_launch_kind<KP, true>(ctx, p, nsingle, nslices - nsingle, smem, nsingle != 0)));
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
     d->scan_timed = true;
     k_tc_merge<KP><<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_tc_partial.p, nlists, nslots, d->d_cand_idx.p, d->d_cand_adist.p);
@@ -967,21 +996,26 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
         const char* e = getenv("SS_DTW_TC_WAVES");
         waves = e ? std::max(1, atoi(e)) : 16;
     }
-    uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->tc_ntiles, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups));
+    // slices: contiguous tile ranges of ONE kind (single-segment tiles come first, paired tiles after), balanced by the
+    // tiles' step-cost estimate; about `waves` CTAs per SM over the two launches (1 resident per SM)
+    const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
     std::vector<uint32_t>& st = d->h_slice_tile;
     st.clear();
-    st.push_back(0);
-    {
-        uint64_t total = 0, acc = 0;
-        for (uint32_t f : d->h_tc_tile_frames) total += f;
-        const uint64_t per = (total + nslices - 1) / nslices;
-        for (uint32_t t = 0; t < d->tc_ntiles; t++) {
-            if (t > 0 && st.size() < nslices && acc >= (uint64_t)st.size() * per) st.push_back(t);
+    uint64_t total = 0;
+    for (uint32_t f : d->h_tc_tile_frames) total += f;
+    const uint64_t per = std::max<uint64_t>(1, (total + want - 1) / want);
+    uint32_t nsingle = 0;
+    for (int kind = 0; kind < 2; kind++) {
+        const uint32_t tb = kind ? d->tc_first_pair_tile : 0, te = kind ? d->tc_ntiles : d->tc_first_pair_tile;
+        uint64_t acc = per;  // forces a slice start at the first tile of the kind
+        for (uint32_t t = tb; t < te; t++) {
+            if (acc >= per) st.push_back(t), acc = 0;
             acc += d->h_tc_tile_frames[t];
         }
+        if (!kind) nsingle = (uint32_t)st.size();
     }
     st.push_back(d->tc_ntiles);
-    nslices = (uint32_t)st.size() - 1;
+    uint32_t nslices = (uint32_t)st.size() - 1;
     SS_TRY(upload(ctx, d->d_slice_tile, st.data(), st.size()));
     const uint32_t nlists = nslices * kTcSlots;
     SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nlists * nslots * kp));
@@ -1001,12 +1035,12 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     p.desc = d->d_tc_desc.p;
     p.slice_tile = d->d_slice_tile.p;
     p.nslices = nslices;
+    p.slice_begin = 0;
     p.partial = d->d_tc_partial.p;
     p.max_len = q->max_len;
     const size_t smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kTcDpThreads * 8 + 1024;
-    const uint32_t grid = q->tc_ngroups * nslices;
-    if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, grid, smem, nlists, nslots, d));
-    else SS_TRY(tc_launch<16>(ctx, p, grid, smem, nlists, nslots, d));
+    if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, nsingle, nslices, smem, nlists, nslots, d));
+    else SS_TRY(tc_launch<16>(ctx, p, nsingle, nslices, smem, nlists, nslots, d));
     // certification bound for fp16 inputs: see k_dtw_finalize (bound_mode 1)
     SS_TRY(dtw_rescore_finalize(d, q, k, kp, nslots, q->d_tc_qid.p, 0.0, q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 1,
                                 q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));

@@ -66,6 +66,7 @@ struct ss_dict {
     bool tc_ready = false;
     uint64_t tc_serial = 0;                  // identifies this build of the tiles (query A blocks are keyed on it)
     uint32_t tc_ntiles = 0;
+    uint32_t tc_first_pair_tile = 0;         // tiles [0, first_pair) hold one segment per slot, the rest two short ones
     float tc_nb_scale = 1.f;                 // power of two s: the |b|^2 columns hold |b|^2 / s
     ss::DevBuf<double> d_mu;                 // per-coefficient mean of the dictionary frames (both sides are centred on it)
     ss::DevBuf<uint16_t> d_tc_tiles;         // ntiles x 4 KB
