@@ -893,12 +893,30 @@ int dtw_tc_dict_build(ss_dict* d) {
 static int tc_queries_build(ss_dict* d, ss_queries* q) {
     ss_ctx* ctx = q->ctx;
     if (q->tc_built && q->tc_dict_serial == d->tc_serial) return SS_OK;  // the A blocks depend on the dictionary's mean frame and scale
-    std::vector<uint32_t> order;
-    order.reserve(q->nq);
-    for (size_t i = 0; i < q->nq; i++)
-        if (q->h_off[i + 1] > q->h_off[i]) order.push_back((uint32_t)i);
+    // queries in descending length order, ties in index order: a counting sort (lengths <= 32 here) - this runs on the host
+    // inside every match of a fresh query batch, with the GPU idle behind it
     auto len_of = [&](uint32_t i) { return (uint32_t)(q->h_off[i + 1] - q->h_off[i]); };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
+    std::vector<uint32_t> order;
+    {
+        const uint32_t ml = q->max_len;
+        std::vector<uint32_t> start(ml + 1, 0);  // bucket ml - len: the longest first; empty queries are left out
+        size_t nonempty = 0;
+        for (size_t i = 0; i < q->nq; i++) {
+            const uint32_t l = len_of((uint32_t)i);
+            if (l) start[ml - l]++, nonempty++;
+        }
+        uint32_t acc = 0;
+        for (uint32_t b = 0; b <= ml; b++) {
+            const uint32_t c = start[b];
+            start[b] = acc;
+            acc += c;
+        }
+        order.resize(nonempty);
+        for (size_t i = 0; i < q->nq; i++) {
+            const uint32_t l = len_of((uint32_t)i);
+            if (l) order[start[ml - l]++] = (uint32_t)i;
+        }
+    }
     // consecutive chunks of 128 queries in length order: a group's queries differ in length by a row or two at most
     // (the scan pads the shorter ones with zero rows and captures every lane's result at its own last row)
     std::vector<uint32_t> glen, gqid, slen;
