@@ -768,6 +768,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 #pragma unroll
         for (int s = 0; s < KP; s++) out[s] = list[s * kTcDpThreads];
     }
+    // a dependent launch may finish its own work before the launch ahead of it has: it must not be seen as complete (the
+    // merge kernel is ordered after THIS grid) until that one is, so every CTA waits for it on the way out. By then all of
+    // the earlier grid's CTAs are at least resident, so nothing is held up; a no-op for a normal launch.
+    if constexpr (PAIRED) asm volatile("griddepcontrol.wait;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == kTcDpWarps) {
