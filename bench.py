@@ -341,7 +341,7 @@ def main():
         line = {
             "metric": "dtw_cell_updates_per_s", "value": total_cells / (ms_step * 1e-3), "unit": "cells/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core cost + f32 DP scan, f64 refine", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (DP scan; local costs from f16 tensor-core products accumulated in f32; winners refined in f64)", "data": "synthetic",
             "config": {"workload": "synthetic 100k-segment dictionary x 10k queries, C=13, L~U{4..32}, DTW top-1 (config 4)",
                        "nd": args.nd, "nq": args.nq, "ncoeffs": C, "k": K, "parallelism": "dictionary sharded x%d, NCCL all-gather top-k merge" % world,
                        "l2": "flushed: a 256 MB buffer is overwritten at the start of every timed step (dictionary resident: %.0f MB fp32 stream + %.0f MB f64)" % (

@@ -3,23 +3,26 @@
 // scan runs.
 //
 // Idea: the local-cost matrix is a K = 13 contraction, c(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j. One tcgen05.mma per
-// (dictionary tile, query row i) computes, for the CTA's 128 queries at once, the costs of row i against the 96 columns
-// of the tile (3 segment slots x 32 columns):
+// (dictionary tile, query row i) computes, for the CTA's 128 queries at once, the costs of row i against the 128 columns
+// of the tile (4 slots x 32 columns):
 //     D[m, n] = sum_k A_i[m, k] * B[n, k],   A_i[m, :] = [-2 a^(m)_i (13), s, s, rd(|a_i|^2 / s)]   (fp16, K-major, no swizzle)
 //                                            B[n, :]   = [ b_n (13), (|b_n|^2/s)_hi, (|b_n|^2/s)_lo, s ]
-// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 96 columns, K = 16 = one MMA). The WHOLE local cost
+// with fp32 accumulation in TMEM (M = 128 lanes = the 128 queries, N = 128 columns, K = 16 = one MMA). The WHOLE local cost
 // comes out of the tensor core: |b|^2 as a hi + lo pair, |a|^2 in the one spare K slot ROUNDED DOWN to fp16, so the scan's
 // cost is <= the cost of the fp16-rounded frames (by at most 2^-10 |a|^2) and the scan distance stays a LOWER bound of
 // their DTW - which is all the certification in k_dtw_finalize needs (a slightly blunter filter, the same proof). TMEM lane
-// m is read back by the threads that own query m (tcgen05.ld 32x32b), which run the DP recurrence for one segment slot
-// each with the row state in registers: FMNMX3 + FADD per cell instead of the fp32 scan's 7 FFMA2 + 2 FADD + FMNMX3.
+// m is read back by the threads that own query m (tcgen05.ld 32x32b), which run the DP recurrence for one slot each with
+// the row state in registers: FMNMX3 + FADD per cell instead of the fp32 scan's 7 FFMA2 + 2 FADD + FMNMX3.
 // Both sides are centred on the dictionary's mean frame before the fp16 conversion (the cost is translation invariant).
 //
-// Warp roles (416 threads, 1 CTA / SM): warps 0-11 = DP (warp w owns TMEM lane quadrant w % 4 and segment slot w / 4);
-// warp 12 = TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and
-// the MMAs. A pipeline step is TWO query rows (two MMAs, one commit) into one of two 192-column TMEM buffers, so the DP
-// warps pay one mbarrier round trip per two rows and advance a two-row band in place (cell (i,j) reads d[j] = row i-1 and
-// feeds cell (i+1,j), which overwrites d[j]): two independent dependency chains per thread and no register copies.
+// Warp roles (640 threads, 1 CTA / SM): warps 0-15 = DP (warp w owns TMEM lane quadrant w % 4 and slot w / 4); warp 16 =
+// TMEM allocator, and its lane 0 issues the TMA bulk copies (A block once, B tiles through a 4-stage ring) and the MMAs;
+// warps 17-19 are idle and only make the producer's warpgroup a donor of registers (setmaxnreg: DP 112, producer 32).
+// A pipeline step is TWO query rows (two MMAs, one commit) into one of two 256-column TMEM buffers, so the DP warps pay
+// one mbarrier round trip per two rows and advance a two-row band in place (cell (i,j) reads d[j] = row i-1 and feeds
+// cell (i+1,j), which overwrites d[j]): two independent dependency chains per thread and no register copies.
+// A slot holds one segment of 17..32 frames, or two of <= 16 frames (the second at column 16) whose bands the thread
+// advances together - the step's fixed cost is then paid once for both; the two tile kinds are separate instantiations.
 // Queries are grouped 128 at a time in length order; a group's queries may differ in length by a row or two (shorter ones
 // are zero-padded and every lane captures its result at its own last row).
 #include <cuda_fp16.h>
@@ -35,28 +38,22 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 
 constexpr int kTcM = 128;          // queries per CTA = MMA M = TMEM lanes
-#ifndef SS_TC_SLOTS
-#define SS_TC_SLOTS 4
-#endif
-constexpr int kTcSlots = SS_TC_SLOTS;  // segment slots per tile (32 columns each): 4 -> 16 DP warps, 3 -> 12 DP warps
-constexpr int kTcN = kTcSlots * 32;  // columns per tile = MMA N
+constexpr int kTcSlots = 4;        // slots per tile (32 columns each) = DP warps per TMEM lane quadrant
+constexpr int kTcN = kTcSlots * 32;  // 128 columns per tile = MMA N
 constexpr int kTcK = 16;           // fp16 elements per row = one MMA K step
 constexpr int kTcATileBytes = kTcM * kTcK * 2;  // 4096: one query row of the CTA's 128 queries
-constexpr int kTcBTileBytes = kTcN * kTcK * 2;  // 3072: one dictionary tile
+constexpr int kTcBTileBytes = kTcN * kTcK * 2;  // 4096: one dictionary tile
 constexpr int kTcStages = 4;       // B-tile ring
-constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows of the tile; two buffers (all 512 TMEM columns at 4 slots)
+constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows of the tile = 256 TMEM columns; two buffers = all 512
 constexpr int kTcMaxLen = 32;
 constexpr int kTcPairCol = 16;     // segments of <= 16 frames share a slot two by two: the second one's columns start here
-constexpr int kTcDpWarps = 4 * kTcSlots;             // warp w: TMEM lane quadrant w % 4, segment slot w / 4
+constexpr int kTcDpWarps = 4 * kTcSlots;             // 16; warp w: TMEM lane quadrant w % 4, slot w / 4
 // The producer warp sits in a warpgroup of its own (three idle warps) that hands its registers to the DP warpgroups
-// (setmaxnreg): 3 slots -> 512 threads, 128 at launch, DP 152 / producer 48; 4 slots -> 640 threads, 96 at launch, DP 112 /
-// producer 32, and the DP step pulls its costs from TMEM in 16-column chunks to fit.
-constexpr int kTcRegsDp = kTcSlots == 3 ? 152 : 112, kTcRegsProd = kTcSlots == 3 ? 48 : 32;
-#ifndef SS_TC_CHUNKED
-#define SS_TC_CHUNKED (SS_TC_SLOTS == 4)
-#endif
-constexpr bool kTcChunked = SS_TC_CHUNKED;
-constexpr int kTcThreads = (kTcDpWarps + 4) * 32;
+// (setmaxnreg): 640 threads, 96 registers at launch, DP 112 / producer group 32 = the whole pool. 112 is why the DP step
+// pulls its costs from TMEM in 16-column chunks (kTcChunked).
+constexpr int kTcRegsDp = 112, kTcRegsProd = 32;
+constexpr bool kTcChunked = true;
+constexpr int kTcThreads = (kTcDpWarps + 4) * 32;    // 640
 constexpr int kTcDpThreads = kTcDpWarps * 32;
 
 // byte offset of element (row, k) inside a ROWS x 16 fp16 K-major no-swizzle UMMA tile: core matrix = 8 rows x 16 B;
@@ -330,7 +327,7 @@ struct TcParams {
     const uint32_t* slice_tile;  // all slices + 1
     uint32_t nslices;            // slices of THIS launch, starting at slice_begin
     uint32_t slice_begin;
-    unsigned long long* partial;  // [nslices * 3 slots][ngroups * 128][KP]
+    unsigned long long* partial;  // [nslices * 4 slots][ngroups * 128][KP]
     uint32_t max_len;
 };
 
@@ -633,7 +630,7 @@ __device__ __forceinline__ void tc_tile_pair(uint32_t L, uint32_t lmin, uint32_t
 template <int KP, bool PAIRED>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
-    // [A tiles: max_len x 4 KB][B ring: 4 x 3 KB][barriers][candidate lists], 128-byte aligned
+    // [A tiles: max_len x 4 KB][B ring: 4 x 4 KB][barriers][candidate lists], 128-byte aligned
     unsigned char* smem = smem_raw + ((128u - (s32(smem_raw) & 127u)) & 127u);
     unsigned char* sA = smem;
     unsigned char* sB = smem + (size_t)p.max_len * kTcATileBytes;
@@ -644,7 +641,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     uint64_t* t_full = bars + 10;
     uint64_t* t_empty = bars + 12;  // = t_full + 16 bytes (TcCursor::release)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][384]
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][512]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x / p.nslices, slice = p.slice_begin + blockIdx.x % p.nslices;
@@ -722,7 +719,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcRegsDp));
         const int q = warp & 3, slot = warp >> 2;
         const int m = q * 32 + lane;
-        unsigned long long* list = topk + threadIdx.x;  // [KP][384] keys, this thread's column
+        unsigned long long* list = topk + threadIdx.x;  // [KP][512] keys, this thread's column
 #pragma unroll
         for (int s = 0; s < KP; s++) list[s * kTcDpThreads] = 0xFFFFFFFFFFFFFFFFull;
         unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
@@ -847,7 +844,7 @@ int dtw_tc_dict_build(ss_dict* d) {
         uint32_t cost = 0;
         for (int sidx = 0; sidx < 4; sidx++) {
             int4 e = make_int4(-1, 0, -1, 0);
-            if (sidx < kTcSlots && (size_t)sidx < take) e.x = (int)order[o + sidx], e.y = len_of(order[o + sidx]);
+            if ((size_t)sidx < take) e.x = (int)order[o + sidx], e.y = len_of(order[o + sidx]);
             if (pair && (size_t)(kTcSlots + sidx) < take) e.z = (int)order[o + kTcSlots + sidx], e.w = len_of(order[o + kTcSlots + sidx]);
             desc.push_back(e);
             cost = std::max<uint32_t>(cost, 32u + 16u * (uint32_t)(pair ? 2 * ((std::max(e.y, e.w) + 3) >> 2) : ((e.y + 3) >> 2)));
