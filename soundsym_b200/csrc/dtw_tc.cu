@@ -272,43 +272,42 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
 #pragma unroll
     for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcN>((int)n, k)) = row[k];
 }
-// one thread per (group, query m), all rows i: A_i[m, :] = [-2 (a_i - mu) (13), s, s, rd(|a_i|^2 / s)]
+// one thread per (group g = blockIdx.x, row i = blockIdx.y, query m): A_i[m, :] = [-2 (a_i - mu) (13), s, s, rd(|a_i|^2 / s)]
+// slot_max_na (per query: max |a_i|^2 over its rows) and max_norm[0] must be zeroed before the launch
 __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
                                  const uint32_t* __restrict__ group_len, const uint64_t* __restrict__ group_off,
                                  const uint32_t* __restrict__ qid, float scale, unsigned char* __restrict__ a_blocks,
                                  float* __restrict__ max_norm, float* __restrict__ slot_max_na) {
-    const uint32_t g = blockIdx.x, m = threadIdx.x;  // blockDim = 128
-    const uint32_t L = group_len[g] & 0xFFFFu;       // longest query of the group; shorter ones are zero-padded
+    const uint32_t g = blockIdx.x, i = blockIdx.y, m = threadIdx.x;  // blockDim = 128
+    const uint32_t L = group_len[g] & 0xFFFFu;                        // longest query of the group; shorter ones are zero-padded
+    if (i >= L) return;
     const uint32_t id = qid[g * kTcM + m];
     const uint32_t Lm = id != 0xFFFFFFFFu ? (uint32_t)(off[id + 1] - off[id]) : 0u;
     unsigned char* blk = a_blocks + group_off[g];
     const float inv_scale = 1.0f / scale;  // power of two: exact
-    float mx = 0.f;
-    for (uint32_t i = 0; i < L; i++) {
-        __half row[kTcK];
+    __half row[kTcK];
 #pragma unroll
-        for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
-        float nrm = 0.f;
-        if (i < Lm) {
-            const double* src = mfcc + (off[id] + i) * c;
-            for (int k = 0; k < c; k++) {
-                const __half h = __float2half_rn((float)(src[k] - mu[k]));
-                const float v = __half2float(h);
-                nrm += v * v;
-                row[k] = __float2half_rn(-2.f * v);  // exact
-            }
-            row[13] = __float2half_rn(scale);
-            row[14] = __float2half_rn(scale);
-            // |a_i|^2 rides in the spare K slot, rounded DOWN: the scan cost never exceeds the cost of the rounded frames
-            // (the host keeps the fp32 scan when max |a|^2 / s would leave the fp16 range)
-            row[15] = __float2half_rd(fminf(nrm * inv_scale, 65504.f));
+    for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
+    float nrm = 0.f;
+    if (i < Lm) {
+        const double* src = mfcc + (off[id] + i) * c;
+        for (int k = 0; k < c; k++) {
+            const __half h = __float2half_rn((float)(src[k] - mu[k]));
+            const float v = __half2float(h);
+            nrm += v * v;
+            row[k] = __float2half_rn(-2.f * v);  // exact
         }
-        unsigned char* base = blk + (size_t)i * kTcATileBytes;
-#pragma unroll
-        for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcM>((int)m, k)) = row[k];
-        mx = fmaxf(mx, nrm);
+        row[13] = __float2half_rn(scale);
+        row[14] = __float2half_rn(scale);
+        // |a_i|^2 rides in the spare K slot, rounded DOWN: the scan cost never exceeds the cost of the rounded frames
+        // (the host keeps the fp32 scan when max |a|^2 / s would leave the fp16 range)
+        row[15] = __float2half_rd(fminf(nrm * inv_scale, 65504.f));
     }
-    slot_max_na[g * kTcM + m] = mx;
+    unsigned char* base = blk + (size_t)i * kTcATileBytes;
+#pragma unroll
+    for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcM>((int)m, k)) = row[k];
+    if (nrm == nrm) atomicMax(reinterpret_cast<unsigned*>(slot_max_na + g * kTcM + m), __float_as_uint(nrm));  // nrm >= 0
+    float mx = nrm;
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((m & 31) == 0 && mx == mx) atomicMax(reinterpret_cast<unsigned*>(max_norm), __float_as_uint(mx));
 }
@@ -327,7 +326,7 @@ struct TcParams {
     const uint32_t* slice_tile;  // all slices + 1
     uint32_t nslices;            // slices of THIS launch, starting at slice_begin
     uint32_t slice_begin;
-    unsigned long long* partial;  // [nslices * 4 slots][ngroups * 128][KP]
+    unsigned long long* partial;  // [nslices][ngroups * 128][KP]
     uint32_t max_len;
 };
 
@@ -344,17 +343,19 @@ __host__ __device__ __forceinline__ uint32_t tc_f2ord(float f) {
 // per-thread candidate list kept in shared memory as packed (ord(dist) << 32 | idx) keys, ascending; only the worst kept
 // key lives in a register for the per-pair test, so the hot loop pays two registers for the list
 template <int KP>
+__device__ __forceinline__ void tc_insert_key(unsigned long long* list, unsigned long long& worst, unsigned long long key) {
+    int s = KP - 1;
+    while (s > 0 && list[(s - 1) * kTcDpThreads] > key) {
+        list[s * kTcDpThreads] = list[(s - 1) * kTcDpThreads];
+        s--;
+    }
+    list[s * kTcDpThreads] = key;
+    worst = list[(KP - 1) * kTcDpThreads];
+}
+template <int KP>
 __device__ __forceinline__ void tc_insert(unsigned long long* list, unsigned long long& worst, float dist, uint32_t idx) {
     const unsigned long long key = ((unsigned long long)tc_f2ord(dist) << 32) | idx;
-    if (key < worst && dist == dist) {
-        int s = KP - 1;
-        while (s > 0 && list[(s - 1) * kTcDpThreads] > key) {
-            list[s * kTcDpThreads] = list[(s - 1) * kTcDpThreads];
-            s--;
-        }
-        list[s * kTcDpThreads] = key;
-        worst = list[(KP - 1) * kTcDpThreads];
-    }
+    if (key < worst && dist == dist) tc_insert_key<KP>(list, worst, key);
 }
 
 // TMEM -> registers: W (8 / 16 / 32) consecutive columns of this thread's lane
@@ -761,9 +762,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 if (seg >= 0 && Lm) tc_insert<KP>(list, worst, __fdividef(res, (float)(Lm + (uint32_t)len)), (uint32_t)seg);
             }
         }
-        unsigned long long* out = p.partial + (((size_t)slice * kTcSlots + slot) * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
+        // the four slots' lists of query m (threads m, m + 128, m + 256, m + 384) are merged by the slot-0 thread: one list per
+        // (slice, query) leaves the CTA
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcDpThreads) : "memory");
+        if (slot == 0) {
+            for (int o = 1; o < kTcSlots; o++) {
+                const unsigned long long* other = list + o * kTcM;
+                for (int s = 0; s < KP; s++) {  // ascending: stop at the first key that does not make the cut
+                    const unsigned long long key = other[s * kTcDpThreads];
+                    if (key >= worst) break;
+                    tc_insert_key<KP>(list, worst, key);
+                }
+            }
+            unsigned long long* out = p.partial + ((size_t)slice * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
 #pragma unroll
-        for (int s = 0; s < KP; s++) out[s] = list[s * kTcDpThreads];
+            for (int s = 0; s < KP; s++) out[s] = list[s * kTcDpThreads];
+        }
     }
     // a dependent launch may finish its own work before the launch ahead of it has: it must not be seen as complete (the
     // merge kernel is ordered after THIS grid) until that one is, so every CTA waits for it on the way out. By then all of
@@ -946,7 +960,8 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
     SS_CUDA(ctx, q->d_tc_max_norm.reserve(1));
     SS_CUDA(ctx, cudaMemsetAsync(q->d_tc_max_norm.p, 0, sizeof(float), ctx->stream));
     if (q->tc_ngroups) {
-        k_tc_query_tiles<<<q->tc_ngroups, kTcM, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, d->d_mu.p, q->d_tc_group_len.p,
+        SS_CUDA(ctx, cudaMemsetAsync(q->d_tc_slot_max_na.p, 0, (size_t)q->tc_ngroups * kTcM * sizeof(float), ctx->stream));
+        k_tc_query_tiles<<<dim3(q->tc_ngroups, q->max_len), kTcM, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, d->d_mu.p, q->d_tc_group_len.p,
                                                                  q->d_tc_group_off.p, q->d_tc_qid.p, d->tc_nb_scale, q->d_tc_a.p,
                                                                  q->d_tc_max_norm.p, q->d_tc_slot_max_na.p);
         SS_LAUNCHED(ctx);
@@ -1036,7 +1051,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     st.push_back(d->tc_ntiles);
     uint32_t nslices = (uint32_t)st.size() - 1;
     SS_TRY(upload(ctx, d->d_slice_tile, st.data(), st.size()));
-    const uint32_t nlists = nslices * kTcSlots;
+    const uint32_t nlists = nslices;  // one candidate list per (slice, query): the four slots are merged inside the CTA
     SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nlists * nslots * kp));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
     SS_CUDA(ctx, d->d_cand_adist.reserve((size_t)nslots * kp));
