@@ -511,11 +511,35 @@ __device__ __forceinline__ float tc_tile(uint32_t L, uint32_t lmin, uint32_t Lm,
     const uint32_t ncap = min((lmin - 1) >> 1, nfull);   // steps before any query of the group can end
     const int r = (len - 1) & 3;             // where column len - 1 sits in the last 4-column group
     uint32_t st = 0;
-#pragma unroll 1
-    for (; st < ncap; st++) {  // no query of the group ends in these steps
+    // no query of the group ends in steps [0, ncap). They run two per iteration on buffer 0 then buffer 1, from cursors
+    // rebuilt out of loop invariants - barrier and TMEM addresses are then constants of the loop and only the parity flips
+    // (once per pair) - after one plain step if the tile happens to start on buffer 1.
+    if (st < ncap && cur.buf) {
         float c0l[4];
         tc_step2<NG>(cur, d, dinit, c0l);
         dinit = INF;
+        st++;
+    }
+    if (st + 2 <= ncap) {
+        const uint32_t full0 = cur.full, taddr0 = cur.taddr;
+        uint32_t par = cur.par;
+#pragma unroll 1
+        for (; st + 2 <= ncap; st += 2) {
+            float c0l[4];
+            TcCursor c0 = {0u, par, full0, taddr0, cur.full_sum, cur.taddr_sum};
+            tc_step2<NG>(c0, d, dinit, c0l);
+            TcCursor c1 = {1u, par, full0 + 8u, taddr0 + (uint32_t)kTcBufCols, cur.full_sum, cur.taddr_sum};
+            tc_step2<NG>(c1, d, INF, c0l);
+            dinit = INF;
+            par ^= 1u;
+        }
+        cur.par = par;
+    }
+    if (st < ncap) {
+        float c0l[4];
+        tc_step2<NG>(cur, d, dinit, c0l);
+        dinit = INF;
+        st++;
     }
 #pragma unroll 1
     for (; st < nfull; st++) {  // only the last step or two of a tile
@@ -597,11 +621,33 @@ __device__ __forceinline__ void tc_tile_pair(uint32_t L, uint32_t lmin, uint32_t
     const uint32_t nfull = L >> 1;
     const uint32_t ncap = min((lmin - 1) >> 1, nfull);
     uint32_t st = 0;
-#pragma unroll 1
-    for (; st < ncap; st++) {  // no query of the group ends in these steps
+    // steps [0, ncap): no query of the group ends; two per iteration on buffers 0, 1 with loop-invariant addresses (tc_tile)
+    if (st < ncap && cur.buf) {
         float e0A, e0B;
         tc_step2_pair<NG, false>(cur, dA, dB, dinit, lenA, lenB, e0A, e0B);
         dinit = INF;
+        st++;
+    }
+    if (st + 2 <= ncap) {
+        const uint32_t full0 = cur.full, taddr0 = cur.taddr;
+        uint32_t par = cur.par;
+#pragma unroll 1
+        for (; st + 2 <= ncap; st += 2) {
+            float e0A, e0B;
+            TcCursor c0 = {0u, par, full0, taddr0, cur.full_sum, cur.taddr_sum};
+            tc_step2_pair<NG, false>(c0, dA, dB, dinit, lenA, lenB, e0A, e0B);
+            TcCursor c1 = {1u, par, full0 + 8u, taddr0 + (uint32_t)kTcBufCols, cur.full_sum, cur.taddr_sum};
+            tc_step2_pair<NG, false>(c1, dA, dB, INF, lenA, lenB, e0A, e0B);
+            dinit = INF;
+            par ^= 1u;
+        }
+        cur.par = par;
+    }
+    if (st < ncap) {
+        float e0A, e0B;
+        tc_step2_pair<NG, false>(cur, dA, dB, dinit, lenA, lenB, e0A, e0B);
+        dinit = INF;
+        st++;
     }
 #pragma unroll 1
     for (; st < nfull; st++) {  // only the last step or two of a tile
