@@ -22,3 +22,38 @@ def test_write_wav_rounding(tmp_path):
     pcm, sr, bits = api._read_wav_pcm(str(tmp_path / "a.wav"))
     assert bits == 32 and sr == 44100.0
     assert pcm.tolist() == [0, 1073741823, -1073741823, 2147483647, -2147483647, 2147483647, -2147483648, 0]
+
+
+def test_bench_sharding_and_algorithmic_bytes():
+    """bench.py's host logic: shards are contiguous, cover every segment once and are balanced by frames (SURVEY.md 8e);
+    the pairwise-streaming byte count is additive over shards."""
+    import importlib.util
+    import os
+    import numpy as np
+    from soundsym_b200 import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    d, doff = synth.segments(5000, 13, seed=7)
+    q, qoff = synth.segments(300, 13, seed=8)
+    whole = bench.algorithmic_bytes(doff, qoff, 0, len(doff) - 1)
+    lens_d, lens_q = np.diff(doff).astype(np.int64), np.diff(qoff).astype(np.int64)
+    assert whole == int((lens_d[:, None] + lens_q[None, :]).sum()) * 13 * 4  # sum over pairs of (Lq + Ld) * C * 4 B
+    for n in (1, 2, 4, 8):
+        cuts = bench.shard_bounds(doff, n)
+        assert cuts[0] == 0 and cuts[-1] == len(doff) - 1 and all(a <= b for a, b in zip(cuts, cuts[1:]))
+        frames = [int(doff[b] - doff[a]) for a, b in zip(cuts, cuts[1:])]
+        assert sum(frames) == int(doff[-1]) and max(frames) - min(frames) <= 2 * 32  # within a segment or two of even
+        assert sum(bench.algorithmic_bytes(doff, qoff, a, b) for a, b in zip(cuts, cuts[1:])) == whole
+
+
+def test_synth_is_seeded():
+    import numpy as np
+    from soundsym_b200 import synth
+    a, ao = synth.segments(50, 13, seed=3)
+    b, bo = synth.segments(50, 13, seed=3)
+    assert np.array_equal(a, b) and np.array_equal(ao, bo) and int(ao[-1]) == a.shape[0]
+    assert np.diff(ao).min() >= 4 and np.diff(ao).max() <= 32
+    x = synth.audio(0.5, seed=1)
+    assert np.array_equal(x, synth.audio(0.5, seed=1)) and x.shape == (22050,) and np.abs(x).max() <= 1.0
