@@ -71,7 +71,7 @@ struct ss_dict {
     ss::DevBuf<double> d_mu;                 // per-coefficient mean of the dictionary frames (both sides are centred on it)
     ss::DevBuf<uint16_t> d_tc_tiles;         // ntiles x 4 KB
     ss::DevBuf<int4> d_tc_desc;              // ntiles x 2 = four {segment, length} pairs per tile
-    std::vector<uint32_t> h_tc_tile_frames;  // sum of the 4 lengths (slice balancing)
+    std::vector<uint32_t> h_tc_tile_frames;  // per tile: instruction estimate of one pipeline step (slice balancing)
     ss::DevBuf<unsigned long long> d_tc_partial;
     ss::DevBuf<float> d_tc_max_norm;         // [0] = max |fp16(b - mu)|^2
     // host-buffer entry point (ss_dict_match): query batch + result buffers reused across calls (grow-only)
