@@ -57,3 +57,31 @@ def test_synth_is_seeded():
     assert np.diff(ao).min() >= 4 and np.diff(ao).max() <= 32
     x = synth.audio(0.5, seed=1)
     assert np.array_equal(x, synth.audio(0.5, seed=1)) and x.shape == (22050,) and np.abs(x).max() <= 1.0
+
+
+def test_cpp_mirror_file_helpers_match_python_mirror(tmp_path):
+    """The C++ mirror's Audacity-label parser, 32-bit WAV writer and PCM reader (include/soundsym.hpp) against the Python
+    mirror's, on the same bytes. Host code only: the binary never creates a context."""
+    import json
+    import os
+    import subprocess
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_helpers")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_helpers.cpp"),
+                           "-o", exe, "-L" + os.path.join(root, "soundsym_b200"), "-lsoundsym_b200",
+                           "-Wl,-rpath," + os.path.join(root, "soundsym_b200")])
+    labels = tmp_path / "labels.txt"
+    labels.write_text("0.7065779155923718\t0.7619218551399829\to\n1.5\t2.25\n\n3\t4\tning ning\nx\t1\tz\n")
+    wav = str(tmp_path / "w.wav")
+    out = json.loads(subprocess.run([exe, str(labels), wav], capture_output=True, text=True, check=True).stdout)
+    py = api.audacity_labels_to_timestamps(str(labels))
+    assert out["n"] == len(py) == 5
+    assert [tuple(s) for s in out["stamps"]] == [tuple(t) for t in py]
+    pcm, sr, bits = api._read_wav_pcm(wav)
+    assert bits == 32 and sr == out["sr"] == 22050.0
+    ref = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 2.0, -2.0, float("nan"), 0.123456789])
+    api._write_wav_i32(str(tmp_path / "p.wav"), ref, 22050)
+    pcm2, _, _ = api._read_wav_pcm(str(tmp_path / "p.wav"))
+    assert np.array_equal(pcm, pcm2)                                   # both writers produce the same samples
+    assert np.array_equal(np.array(out["back"]), pcm.astype(np.float64) / 2147483647.0)  # reader: s / (i32::MAX >> 0)
