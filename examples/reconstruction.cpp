@@ -5,6 +5,7 @@
 // -> partition the target with the source's model -> clone_from_dictionary -> to_sound -> write_file.
 // Prints one JSON line with the segment counts, the match indices and checksums so that a test can compare it with the
 // golden fixtures.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -16,7 +17,8 @@ using namespace soundsym;
 int main(int argc, char** argv) {
     std::string src, tgt, out, model_path;
     size_t depth = 3, threshold = 4;  // examples/reconstruction.rs:44-45
-    bool dtw = false, partition_only = false;
+    bool dtw = false, partition_only = false, morph = false, matcher_loop = false;
+    size_t chain = 6;
     std::string dict_dir, query_dir, splits_dir;  // --matcher <dictionary dir> <query dir>: the flow of examples/matcher.rs
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -30,9 +32,41 @@ int main(int argc, char** argv) {
         else if (a == "--dtw") dtw = true;
         else if (a == "--partition-only") partition_only = true;
         else if (a == "--matcher") dict_dir = next(), query_dir = next();
+        else if (a == "--matcher-loop") dict_dir = next(), query_dir = next(), matcher_loop = true;
+        else if (a == "--morph") morph = true;
+        else if (a == "--chain") chain = std::stoul(next());
         else if (a == "--write-splits") splits_dir = next();
     }
     try {
+        if (matcher_loop) {
+            // examples/matcher.rs:18-56 literally: ONE match_sound (nq = 1) per query file, silence below max_power 0.03, the
+            // matched samples zero-padded / truncated to the query's length and scaled by i16::MAX * 4^max_power
+            auto dictionary = SoundDictionary::from_path(dict_dir);
+            dictionary->mode = dtw ? SS_DTW : SS_COSINE_REF;
+            auto queries = SoundDictionary::from_path(query_dir);  // the directory listing + Sound::from_path of every file
+            std::vector<int16_t> concat;
+            printf("{\"matches\": [");
+            bool first = true;
+            for (auto& phoneme : queries->sounds) {
+                if (phoneme->max_power() < 0.03) {
+                    concat.insert(concat.end(), phoneme->samples().size(), 0);
+                    continue;
+                }
+                auto sound = dictionary->match_sound(phoneme);
+                const std::vector<double>& smp = sound->samples();
+                const double gain = 32767.0 * std::pow(4.0, phoneme->max_power());
+                for (size_t i = 0; i < phoneme->samples().size(); i++) {
+                    const double v = (i < smp.size() ? smp[i] : 0.0) * gain;  // `as i16`: truncate toward zero, saturate, NaN -> 0
+                    concat.push_back(v != v ? 0 : (v >= 32767.0 ? 32767 : (v <= -32768.0 ? -32768 : (int16_t)v)));
+                }
+                printf("%s[\"%s\", \"%s\"]", first ? "" : ",", phoneme->name.value_or("").c_str(), sound->name.value_or("").c_str());
+                first = false;
+            }
+            long long sum = 0;
+            for (int16_t v : concat) sum += v;
+            printf("], \"concat_len\": %zu, \"concat_sum\": %lld}\n", concat.size(), sum);
+            return 0;
+        }
         if (!dict_dir.empty()) {
             // examples/matcher.rs:19-52: a dictionary of whole files, every query file matched against it unless it is
             // quieter than 0.03 (then silence); here the queries are matched in ONE batched call
@@ -70,16 +104,31 @@ int main(int argc, char** argv) {
         auto target = std::make_shared<Sound>(Sound::from_path(tgt));
         partitioner.sound = target;
         const std::vector<size_t> tsplits = partitioner.partition();
-        std::vector<std::shared_ptr<Sound>> segments;  // examples/reconstruction.rs:77-81
-        size_t spos = 0, fpos = 0;
-        for (size_t sp : tsplits) {
-            std::vector<double> samp(target->samples().begin() + spos, target->samples().begin() + spos + sp);
-            std::vector<double> m(target->mfccs().begin() + fpos, target->mfccs().begin() + fpos + sp / HOP * NCOEFFS);
-            spos += sp;
-            fpos += sp / HOP * NCOEFFS;
-            segments.push_back(std::make_shared<Sound>(Sound::from_cut(std::move(samp), target->sample_rate(), std::move(m), target->context())));
-        }
+        std::vector<std::shared_ptr<Sound>> segments = Sound::cut(*target, tsplits, target->context());  // examples/reconstruction.rs:77-81
         SoundSequence sequence(segments);
+        if (morph) {
+            // SoundSequence::morph_to (src/sound.rs:440-449) with target distances spread over the similarity range, and
+            // SoundSequence::from_distances (:405-417): a chain of `chain` nq = 1 matches starting from the first segment
+            auto index_of = [&](const std::shared_ptr<Sound>& s) {
+                for (size_t i = 0; i < dictionary->sounds.size(); i++)
+                    if (dictionary->sounds[i] == s) return (long long)i;
+                return -1ll;
+            };
+            std::vector<double> distances(segments.size());
+            for (size_t i = 0; i < distances.size(); i++) distances[i] = -1e-4 + 2e-4 * (double)i / (double)std::max<size_t>(distances.size() - 1, 1);
+            SoundSequence morphed = sequence.morph_to(distances, *dictionary);
+            std::vector<double> steps(chain);
+            for (size_t i = 0; i < chain; i++) steps[i] = (i % 2 ? -1.0 : 1.0) * 5e-5 * (double)(i + 1) / (double)chain;
+            SoundSequence chained = SoundSequence::from_distances(steps, segments.at(0), *dictionary);
+            printf("{\"morph\": [");
+            for (size_t i = 0; i < morphed.sounds().size(); i++) printf("%s%lld", i ? "," : "", index_of(morphed.sounds()[i]));
+            printf("], \"chain\": [");
+            for (size_t i = 1; i < chained.sounds().size(); i++) printf("%s%lld", i > 1 ? "," : "", index_of(chained.sounds()[i]));
+            printf("], \"chain_distances\": [");
+            for (size_t i = 0; i < chained.distances().size(); i++) printf("%s%.17g", i ? "," : "", chained.distances()[i]);
+            printf("]}\n");
+            return 0;
+        }
         std::vector<uint32_t> idx;
         Sound result = sequence.clone_from_dictionary_to_sound(*dictionary, &idx);
         if (!out.empty()) result.write_file(out);

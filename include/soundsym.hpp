@@ -146,15 +146,41 @@ class Sound {
 
     /// a cut of a longer sound that carries the parent's MFCC rows (add_segments / reconstruction.rs:77-81):
     /// Sound::from_samples(samp, sr, Some(mfccs), None) without re-running the discarded analysis
-    static Sound from_cut(std::vector<double> samples, double sample_rate, std::vector<double> mfccs, Context& ctx) {
+    /// max_power = analyze_max_power of the cut (src/sound.rs:95), computed by the caller for all cuts in one launch
+    static Sound from_cut(std::vector<double> samples, double sample_rate, std::vector<double> mfccs, double max_power, Context& ctx) {
         Sound s;
         s.ctx_ = &ctx;
         s.sample_rate_ = sample_rate;
         s.samples_ = std::move(samples);
         s.mfccs_ = std::move(mfccs);
         s.mean_mfccs_ = mean_of(s.mfccs_);
-        s.max_power_ = std::numeric_limits<double>::quiet_NaN();  // analysed on demand by callers that gate on it
+        s.max_power_ = max_power;
         return s;
+    }
+
+    /// the segment cuts of a longer sound, each carrying the parent's MFCC rows - the loop of add_segments
+    /// (src/sound.rs:330-343) and of examples/reconstruction.rs:77-81: segment i takes seg_i samples and (seg_i / HOP) *
+    /// NCOEFFS MFCC values. Every cut's max power (Sound::from_samples runs analyze_max_power on it, src/sound.rs:95)
+    /// comes from ONE batched launch.
+    static std::vector<std::shared_ptr<Sound>> cut(const Sound& sound, const std::vector<size_t>& segments, Context& ctx) {
+        std::vector<uint64_t> bounds(segments.size() + 1, 0), foff(segments.size() + 1, 0);
+        for (size_t i = 0; i < segments.size(); i++) bounds[i + 1] = std::min<uint64_t>(bounds[i] + segments[i], sound.samples().size());
+        std::vector<double> power(segments.size(), 0.0);
+        if (!segments.empty())
+            ctx.check(ss_sound_analyze_batch(ctx.get(), sound.samples().data(), bounds.data(), segments.size(), sound.sample_rate(), (int)NCOEFFS,
+                                             nullptr, foff.data(), power.data(), nullptr));
+        std::vector<std::shared_ptr<Sound>> out;
+        size_t spos = 0, fpos = 0, i = 0;
+        for (size_t seg : segments) {
+            const size_t ns = std::min(seg, sound.samples().size() - std::min(spos, sound.samples().size()));
+            const size_t nv = std::min(seg / HOP * NCOEFFS, sound.mfccs().size() - std::min(fpos, sound.mfccs().size()));
+            std::vector<double> samp(sound.samples().begin() + spos, sound.samples().begin() + spos + ns);
+            std::vector<double> m(sound.mfccs().begin() + fpos, sound.mfccs().begin() + fpos + nv);
+            spos += ns;
+            fpos += nv;
+            out.push_back(std::make_shared<Sound>(Sound::from_cut(std::move(samp), sound.sample_rate(), std::move(m), power[i++], ctx)));
+        }
+        return out;
     }
 
     /// many sounds analysed in ONE device pass (ss_sound_analyze_batch): what SoundDictionary::from_path and
@@ -224,6 +250,8 @@ class Sound {
         for (size_t k = 0; k < NCOEFFS; k++) out[k] = out[k] / (double)frames;
         return out;
     }
+    /// integer-PCM RIFF/WAVE only (what hound::WavReader yields at src/sound.rs:117): format tag 1 or 0xFFFE with the PCM
+    /// sub-format, 8 (unsigned, offset 128) / 16 / 24 / 32 bits, fmt before data, every chunk inside the file
     static std::vector<int32_t> read_wav_pcm(const std::string& path, int* bits, double* sr) {
         std::ifstream f(path, std::ios::binary);
         if (!f) throw CosError(SS_ERR_INVALID, "cannot open " + path);
@@ -231,30 +259,44 @@ class Sound {
         if (d.size() < 12 || memcmp(d.data(), "RIFF", 4) || memcmp(d.data() + 8, "WAVE", 4)) throw CosError(SS_ERR_INVALID, "not a WAVE file: " + path);
         size_t pos = 12;
         std::vector<int32_t> pcm;
+        bool have_fmt = false, have_data = false;
         while (pos + 8 <= d.size()) {
             uint32_t size;
             memcpy(&size, d.data() + pos + 4, 4);
             const char* body = d.data() + pos + 8;
+            const size_t avail = std::min<size_t>(size, d.size() - pos - 8);
             if (!memcmp(d.data() + pos, "fmt ", 4)) {
+                if (avail < 16) throw CosError(SS_ERR_INVALID, "truncated fmt chunk: " + path);
+                uint16_t tag, b;
                 uint32_t rate;
-                uint16_t b;
+                memcpy(&tag, body, 2);
                 memcpy(&rate, body + 4, 4);
                 memcpy(&b, body + 14, 2);
+                if (tag == 0xFFFE) {
+                    if (avail < 26) throw CosError(SS_ERR_INVALID, "truncated extensible fmt chunk: " + path);
+                    memcpy(&tag, body + 24, 2);
+                }
+                if (tag != 1) throw CosError(SS_ERR_INVALID, "unsupported WAV format tag (integer PCM only): " + path);
+                if (b != 8 && b != 16 && b != 24 && b != 32) throw CosError(SS_ERR_INVALID, "unsupported bits per sample: " + path);
                 *sr = rate;
                 *bits = b;
-            } else if (!memcmp(d.data() + pos, "data", 4)) {
-                const size_t avail = std::min<size_t>(size, d.size() - pos - 8);
+                have_fmt = true;
+            } else if (!memcmp(d.data() + pos, "data", 4) && !have_data) {
+                if (!have_fmt) throw CosError(SS_ERR_INVALID, "data chunk before fmt chunk: " + path);
                 const int bytes = *bits / 8;
                 pcm.resize(avail / bytes);
                 for (size_t i = 0; i < pcm.size(); i++) {
                     int32_t v = 0;
                     memcpy(&v, body + i * bytes, bytes);
-                    if (bytes < 4) v = (v << (32 - *bits)) >> (32 - *bits);  // sign-extend
+                    if (bytes == 1) v = (v & 0xFF) - 128;
+                    else if (bytes < 4) v = (int32_t)((uint32_t)v << (32 - *bits)) >> (32 - *bits);  // sign-extend
                     pcm[i] = v;
                 }
+                have_data = true;
             }
-            pos += 8 + size + (size & 1);
+            pos += 8 + (size_t)size + (size & 1);
         }
+        if (!have_fmt || !have_data) throw CosError(SS_ERR_INVALID, "no fmt / data chunk: " + path);
         return pcm;
     }
     Context* ctx_ = nullptr;
@@ -274,16 +316,7 @@ class SoundDictionary {
 
     /// SoundDictionary::add_segments (src/sound.rs:330-343)
     void add_segments(const Sound& sound, const std::vector<size_t>& segments) {
-        size_t spos = 0, fpos = 0;
-        for (size_t seg : segments) {
-            const size_t ns = std::min(seg, sound.samples().size() - std::min(spos, sound.samples().size()));
-            const size_t nv = std::min(seg / HOP * NCOEFFS, sound.mfccs().size() - std::min(fpos, sound.mfccs().size()));
-            std::vector<double> samp(sound.samples().begin() + spos, sound.samples().begin() + spos + ns);
-            std::vector<double> m(sound.mfccs().begin() + fpos, sound.mfccs().begin() + fpos + nv);
-            spos += ns;
-            fpos += nv;
-            sounds.push_back(std::make_shared<Sound>(Sound::from_cut(std::move(samp), sound.sample_rate(), std::move(m), *ctx_)));
-        }
+        for (auto& c : Sound::cut(sound, segments, *ctx_)) sounds.push_back(std::move(c));
         ss_dict_destroy(dev_);
         dev_ = nullptr;
     }

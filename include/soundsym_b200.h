@@ -182,6 +182,17 @@ uint64_t ss_dict_last_tc_fallback(const ss_dict* dict);
  * entries) and that were therefore matched by exhaustive f64 DTW against every segment. */
 uint64_t ss_dict_last_exhaustive(const ss_dict* dict);
 
+/* ss_dict_debug_tc_scan   measurement hook for the SS_DTW filter stage (no reference counterpart; tests/test_parity_large_gpu.py):
+ *              the RAW distance the tensor-core scan (fp16 products, fp32 accumulation in TMEM, fp32 DP) assigns to EVERY
+ *              (query, segment) pair - out_scan[nq x nseg], NaN where a side is empty - together with the mean frame
+ *              (out_mu, 16 doubles, the first ncoeffs used) both sides were centred on and the power-of-two scale s of the
+ *              norm columns, so that a host can rebuild the fp16 operands exactly and measure |scan - DTW(rounded frames)|
+ *              against the slack the certification assumes. Runs the production scan kernel with one extra
+ *              store per pair compiled in. SS_ERR_INVALID when these inputs would take the fp32 scan instead (a segment or
+ *              query longer than 32 frames, values outside the fp16 range). */
+int ss_dict_debug_tc_scan(ss_dict* dict, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan,
+                          double* out_mu, float* out_scale);
+
 /* ss_resynth   SoundSequence::clone_from_dictionary sample assembly (src/sound.rs:451-472) + to_sound (:475-483):
  *              for target segment t copy min(len) samples of dictionary sound match_idx[t] and zero-pad to
  *              target_lens[t]; segments are concatenated into out_samples (capacity sum(target_lens)). */

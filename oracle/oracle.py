@@ -56,6 +56,7 @@ def lib():
     L.orc_dtw.restype = C.c_double
     L.orc_dtw.argtypes = [_f64p, C.c_size_t, _f64p, C.c_size_t, C.c_int]
     L.orc_dtw_topk.argtypes = [_f64p, _u64p, C.c_size_t, _f64p, _u64p, C.c_size_t, C.c_int, C.c_int, _u32p, _f64p]
+    L.orc_dtw_matrix.argtypes = [_f64p, _u64p, C.c_size_t, _f64p, _u64p, C.c_size_t, C.c_int, _f64p]
     L.orc_standardize.restype = C.c_int
     L.orc_standardize.argtypes = [_f64p, C.c_size_t, C.c_int, _f64p, _f64p, _f64p]
     L.orc_gmm_prepare.restype = C.c_int
@@ -183,6 +184,15 @@ def dtw_topk(dict_flat, dict_off_frames, q_flat, q_off_frames, c, k=1):
     dist = np.empty((nq, k), dtype=np.float64)
     lib().orc_dtw_topk(d, do, do.shape[0] - 1, q, qo, nq, c, k, idx, dist)
     return idx, dist
+
+
+def dtw_matrix(dict_flat, dict_off_frames, q_flat, q_off_frames, c):
+    """every (query, segment) DTW distance, f64 [nq, nseg]"""
+    d, q = _f64(dict_flat).ravel(), _f64(q_flat).ravel()
+    do, qo = _u64(dict_off_frames), _u64(q_off_frames)
+    out = np.empty((qo.shape[0] - 1, do.shape[0] - 1), dtype=np.float64)
+    lib().orc_dtw_matrix(d, do, do.shape[0] - 1, q, qo, qo.shape[0] - 1, c, out)
+    return out
 
 
 def standardize(x):

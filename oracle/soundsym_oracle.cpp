@@ -283,7 +283,8 @@ void orc_cosine_match(const double* dict, const uint64_t* dict_off, size_t nseg,
 // ---- row 20: DTW (A8). frames x c row-major; returns D(Lq-1,Ld-1)/(Lq+Ld); +inf if either side is empty ------------
 double orc_dtw(const double* a, size_t la, const double* b, size_t lb, int c) {
     if (la == 0 || lb == 0) return std::numeric_limits<double>::infinity();
-    std::vector<double> prev(lb), cur(lb);
+    static thread_local std::vector<double> prev, cur;  // row buffers reused across calls (same values, no per-pair allocation)
+    if (prev.size() < lb) prev.resize(lb), cur.resize(lb);
     for (size_t i = 0; i < la; i++) {
         for (size_t j = 0; j < lb; j++) {
             double cost = 0.0;
@@ -301,6 +302,17 @@ double orc_dtw(const double* a, size_t la, const double* b, size_t lb, int c) {
         std::swap(prev, cur);
     }
     return prev[lb - 1] / (double)(la + lb);
+}
+
+// every (query, segment) distance: out[nq x nseg]. Checker for the scan-error measurement (tests/test_parity_large_gpu.py).
+void orc_dtw_matrix(const double* dict, const uint64_t* dict_off, size_t nseg, const double* q, const uint64_t* q_off, size_t nq, int c,
+                    double* out) {
+    parallel_for(nq, 1, [&](size_t qi) {
+        const double* qa = q + q_off[qi] * c;
+        const size_t lq = (size_t)(q_off[qi + 1] - q_off[qi]);
+        for (size_t d = 0; d < nseg; d++)
+            out[qi * nseg + d] = orc_dtw(qa, lq, dict + dict_off[d] * c, (size_t)(dict_off[d + 1] - dict_off[d]), c);
+    });
 }
 
 // top-k DTW match: frame offsets (nseg+1 entries, in FRAMES). For each query the k smallest (distance, index)

@@ -116,6 +116,17 @@ class Context:
                                                    _ptr(foff), _ptr(mp), _ptr(mean)))
         return mfcc, foff, mp, mean
 
+    def max_power_batch(self, samples, sample_offsets):
+        """analyze_max_power (src/sound.rs:244-256) of many cuts of one buffer in one launch -> f64 [ncuts]."""
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        off = np.ascontiguousarray(sample_offsets, dtype=np.uint64)
+        n = off.shape[0] - 1
+        mp = np.zeros(n, dtype=np.float64)
+        foff = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            self.check(self.lib.ss_sound_analyze_batch(self.h, _ptr(samples), _ptr(off), n, 44100.0, NCOEFFS, None, _ptr(foff), _ptr(mp), None))
+        return mp
+
     def mfcc(self, samples, sample_rate=44100.0, ncoeffs=NCOEFFS):
         samples = np.ascontiguousarray(samples, dtype=np.float64)
         frames = C.c_size_t()
@@ -237,6 +248,18 @@ class DeviceDictionary:
         self.ctx.check(self.ctx.lib.ss_dict_match(self.h, _ptr(q), _ptr(qo), nq, int(mode), _ptr(t), int(k), _ptr(idx), _ptr(dist)))
         return idx, dist
 
+    def debug_tc_scan(self, q_flat, q_frame_offsets):
+        """ss_dict_debug_tc_scan: raw tensor-core scan distance of every (query, segment) pair -> (scan f32 [nq, nseg],
+        mean frame f64 [16], norm scale)."""
+        q = np.ascontiguousarray(q_flat, dtype=np.float64)
+        qo = np.ascontiguousarray(q_frame_offsets, dtype=np.uint64)
+        nq = qo.shape[0] - 1
+        scan = np.empty((nq, len(self)), dtype=np.float32)
+        mu = np.zeros(16, dtype=np.float64)
+        scale = C.c_float(0.0)
+        self.ctx.check(self.ctx.lib.ss_dict_debug_tc_scan(self.h, _ptr(q), _ptr(qo), nq, _ptr(scan), _ptr(mu), C.byref(scale)))
+        return scan, mu, float(scale.value)
+
     @property
     def last_work(self):
         return int(self.ctx.lib.ss_dict_last_work(self.h))
@@ -324,7 +347,11 @@ class Sound:
         import os
         ctx = ctx or default_context()
         pcm, sr, bits = _read_wav_pcm(path)
-        samples, m, mp, mean = ctx.analyze_pcm(pcm, bits, sr, NCOEFFS)
+        if bits == 8:  # no integer ingest path for 8-bit: convert (src/sound.rs:118-120, denominator 127) then analyse
+            samples = ctx.decode_pcm(pcm, 8)
+            m, mp, mean = ctx.analyze(samples, sr, NCOEFFS)
+        else:
+            samples, m, mp, mean = ctx.analyze_pcm(pcm, bits, sr, NCOEFFS)
         return cls(samples, sr, m, mp, mean, os.path.splitext(os.path.basename(path))[0], ctx)
 
     def push_samples(self, new_samples):
@@ -370,30 +397,47 @@ class Sound:
 
 
 def _read_wav_pcm(path):
+    """integer-PCM RIFF/WAVE reader (what hound::WavReader accepts at src/sound.rs:117): format tag 1, or 0xFFFE with the
+    PCM sub-format; 8 / 16 / 24 / 32 bits (8-bit is unsigned offset-128, as hound converts it). Anything else raises
+    ValueError, as hound returns Err."""
     with open(path, "rb") as f:
         data = f.read()
-    if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
         raise ValueError("not a RIFF/WAVE file: %s" % path)
     pos, fmt, pcm = 12, None, None
     while pos + 8 <= len(data):
         cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
-        body = data[pos + 8:pos + 8 + size]
+        body = data[pos + 8:min(pos + 8 + size, len(data))]
         if cid == b"fmt ":
-            _, _, sr, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+            if len(body) < 16:
+                raise ValueError("truncated fmt chunk: %s" % path)
+            tag, _, sr, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+            if tag == 0xFFFE:  # WAVE_FORMAT_EXTENSIBLE: the sub-format GUID's first two bytes carry the real tag
+                if len(body) < 26:
+                    raise ValueError("truncated extensible fmt chunk: %s" % path)
+                tag = struct.unpack("<H", body[24:26])[0]
+            if tag != 1:
+                raise ValueError("unsupported WAV format tag %d (integer PCM only): %s" % (tag, path))
+            if bits not in (8, 16, 24, 32):
+                raise ValueError("unsupported bits per sample: %d" % bits)
             fmt = (sr, bits)
-        elif cid == b"data":
+        elif cid == b"data" and pcm is None:
+            if fmt is None:
+                raise ValueError("data chunk before fmt chunk: %s" % path)
             bits = fmt[1]
-            if bits == 16:
-                pcm = np.frombuffer(body, dtype="<i2").astype(np.int32)
+            if bits == 8:
+                pcm = np.frombuffer(body, dtype=np.uint8).astype(np.int32) - 128
+            elif bits == 16:
+                pcm = np.frombuffer(body[: len(body) // 2 * 2], dtype="<i2").astype(np.int32)
             elif bits == 24:
                 b = np.frombuffer(body[: len(body) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
                 v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
                 pcm = np.where(v & 0x800000, v - (1 << 24), v).astype(np.int32)
-            elif bits == 32:
-                pcm = np.frombuffer(body, dtype="<i4").astype(np.int32)
             else:
-                raise ValueError("unsupported bits per sample: %d" % bits)
+                pcm = np.frombuffer(body[: len(body) // 4 * 4], dtype="<i4").astype(np.int32)
         pos += 8 + size + (size & 1)
+    if fmt is None or pcm is None:
+        raise ValueError("no fmt / data chunk: %s" % path)
     return pcm, float(fmt[0]), fmt[1]
 
 
@@ -440,18 +484,22 @@ class SoundDictionary:
         """src/sound.rs:330-343: segment i takes seg_i samples and (seg_i / HOP) * NCOEFFS MFCC values, in order."""
         spos, fpos = 0, 0
         samples, mfccs = sound.samples(), sound.mfcc_arrays()
-        for seg in segments:
-            seg = int(seg)
+        segs = [int(s) for s in segments]
+        # Sound::from_samples(samp, sr, Some(mfccs), None) runs analyze_max_power on every cut (src/sound.rs:95): all cuts
+        # in ONE batched launch (ss_sound_analyze_batch with only the max-power output requested)
+        ctx = sound._ctx or self._ctx
+        bounds = np.zeros(len(segs) + 1, dtype=np.uint64)
+        bounds[1:] = np.minimum(np.cumsum(segs), len(samples))
+        powers = ctx.max_power_batch(samples[:int(bounds[-1])], bounds) if segs else np.zeros(0)
+        for i, seg in enumerate(segs):
             nf = seg // HOP
             samp = samples[spos:spos + seg]
             m = mfccs[fpos:fpos + nf]
             spos += seg
             fpos += nf
-            # Sound::from_samples(samp, sr, Some(mfccs), None): max_power of the cut is analysed lazily here (it is
-            # not on the matcher path); mean of the supplied MFCC rows as analyze_mean_mfccs.
-            with np.errstate(all="ignore"):
+            with np.errstate(all="ignore"):  # mean of the supplied MFCC rows as analyze_mean_mfccs
                 mean = m.sum(axis=0) / m.shape[0] if m.shape[0] else np.full(NCOEFFS, np.nan)
-            self.sounds.append(Sound(samp, sound.sample_rate(), m, None, mean, None, sound._ctx))
+            self.sounds.append(Sound(samp, sound.sample_rate(), m, float(powers[i]), mean, None, ctx))
         self._dev = None
 
     def _device(self):

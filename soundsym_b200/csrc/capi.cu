@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary declared in include/soundsym_b200.h: context, error strings, handle lifetimes and
 // the host-buffer wrappers (H2D, kernels, D2H, stream-synchronised on return). No compute happens on the host.
 #include <cstring>
+#include <limits>
 
 #include "match.cuh"
 #include "sound.cuh"
@@ -276,6 +277,38 @@ int ss_dict_match(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offs
     const int rc = body();
     if (rc != SS_OK) cudaStreamSynchronize(ctx->stream);
     return rc;
+}
+
+int ss_dict_debug_tc_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan, double* out_mu,
+                          float* out_scale) {
+    if (!d) return set_error(nullptr, SS_ERR_INVALID, "dict is NULL");
+    ss_ctx* ctx = d->ctx;
+    if (!out_scan || !out_mu || !out_scale) return set_error(ctx, SS_ERR_INVALID, "output pointers are NULL");
+    if (d->nseg == 0) return set_error(ctx, SS_ERR_EMPTY_DICT, "empty dictionary");
+    SS_TRY(queries_check(ctx, q_mfcc, q_frame_offsets, nq, d->c));
+    SS_CUDA(ctx, cudaSetDevice(ctx->device));
+    ss_queries q;
+    q.ctx = ctx;
+    q.c = d->c;
+    SS_TRY(queries_fill(&q, q_mfcc, q_frame_offsets, nq));
+    const size_t nslots = (nq + 127) / 128 * 128, nseg = d->nseg;
+    DevBuf<float> d_out;
+    SS_CUDA(ctx, d_out.reserve(nslots * nseg));
+    SS_CUDA(ctx, cudaMemsetAsync(d_out.p, 0xFF, nslots * nseg * sizeof(float), ctx->stream));  // NaN = not evaluated
+    std::vector<uint32_t> slot_qid;
+    int rc = dtw_tc_debug_scan(d, &q, d_out.p, &slot_qid, out_mu, out_scale);
+    if (rc != SS_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    for (size_t i = 0; i < nq * nseg; i++) out_scan[i] = std::numeric_limits<float>::quiet_NaN();
+    for (size_t s = 0; s < slot_qid.size(); s++) {  // scan rows are in length-sorted slot order: back to query order
+        const uint32_t qid = slot_qid[s];
+        if (qid == 0xFFFFFFFFu) continue;
+        SS_CUDA(ctx, cudaMemcpyAsync(out_scan + (size_t)qid * nseg, d_out.p + s * nseg, nseg * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
 }
 
 int ss_topk_merge_dev(ss_ctx* ctx, const uint32_t* d_idx, const double* d_dist, int nlists, size_t nq, int k, uint32_t* d_out_idx,

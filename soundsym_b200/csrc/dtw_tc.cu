@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "match.cuh"
 
@@ -328,6 +329,8 @@ struct TcParams {
     uint32_t slice_begin;
     unsigned long long* partial;  // [nslices][ngroups * 128][KP]
     uint32_t max_len;
+    float* dbg;                   // DBG instantiation only: [ngroups * 128][dbg_nseg] raw scan distances (ss_dict_debug_tc_scan)
+    uint32_t dbg_nseg;
 };
 
 __host__ __device__ __forceinline__ uint32_t tc_f2ord(float f) {
@@ -674,7 +677,9 @@ __device__ __forceinline__ void tc_tile_pair(uint32_t L, uint32_t lmin, uint32_t
 
 // PAIRED selects the tile kind the launch covers (the dictionary's tiles are sorted: single-segment slots first, paired
 // slots after; each kind gets its own instantiation so that neither pays for the other's registers and code).
-template <int KP, bool PAIRED>
+// DBG additionally writes every pair's scan distance to p.dbg (the measurement hook behind ss_dict_debug_tc_scan; the
+// product launches never instantiate it).
+template <int KP, bool PAIRED, bool DBG = false>
 __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // [A tiles: max_len x 4 KB][B ring: 4 x 4 KB][barriers][candidate lists], 128-byte aligned
@@ -789,6 +794,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 if (Lm) {
                     if (sl.y > 0) tc_insert<KP>(list, worst, __fdividef(resA, (float)(Lm + (uint32_t)sl.y)), (uint32_t)sl.x);
                     if (sl.w > 0) tc_insert<KP>(list, worst, __fdividef(resB, (float)(Lm + (uint32_t)sl.w)), (uint32_t)sl.z);
+                    if constexpr (DBG) {
+                        float* row = p.dbg + (size_t)(g * kTcM + m) * p.dbg_nseg;
+                        if (sl.y > 0) row[sl.x] = __fdividef(resA, (float)(Lm + (uint32_t)sl.y));
+                        if (sl.w > 0) row[sl.z] = __fdividef(resB, (float)(Lm + (uint32_t)sl.w));
+                    }
                 }
             } else {
                 const int seg = sl.x, len = sl.y;
@@ -806,6 +816,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
                 }
                 // result: D(Lm-1, len-1) / (Lm + len)
                 if (seg >= 0 && Lm) tc_insert<KP>(list, worst, __fdividef(res, (float)(Lm + (uint32_t)len)), (uint32_t)seg);
+                if constexpr (DBG)
+                    if (seg >= 0 && Lm) p.dbg[(size_t)(g * kTcM + m) * p.dbg_nseg + seg] = __fdividef(res, (float)(Lm + (uint32_t)len));
             }
         }
         // the four slots' lists of query m (threads m, m + 128, m + 256, m + 384) are merged by the slot-0 thread: one list per
@@ -890,11 +902,10 @@ int dtw_tc_dict_build(ss_dict* d) {
     // A tile has 4 slots of 32 columns. A segment longer than 16 frames takes a slot of its own; shorter ones share a slot
     // two by two (the second at column 16), so that the per-step hand-off is paid once for both. Per slot the descriptor is
     // {segment A, length A, segment B, length B}, B = -1 when absent.
-    static int pairing = -1;
-    if (pairing < 0) {
+    static const int pairing = [] {  // read once, thread-safe (C++11 static initialisation)
         const char* e = getenv("SS_DTW_TC_PAIR");
-        pairing = e ? atoi(e) : 1;
-    }
+        return e ? atoi(e) : 1;
+    }();
     std::vector<int4> desc;
     d->tc_first_pair_tile = 0xFFFFFFFFu;
     d->h_tc_tile_frames.clear();  // per tile: an instruction-count estimate of one pipeline step (slice balancing)
@@ -945,7 +956,7 @@ int dtw_tc_dict_build(ss_dict* d) {
                                                      reinterpret_cast<unsigned char*>(d->d_tc_tiles.p));
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    static uint64_t serial = 0;
+    static std::atomic<uint64_t> serial{0};  // process-wide: dictionaries of different contexts / host threads never share one
     d->tc_serial = ++serial;
     d->tc_ready = true;
     return SS_OK;
@@ -1022,12 +1033,12 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
     return SS_OK;
 }
 
-template <int KP, bool PAIRED>
+template <int KP, bool PAIRED, bool DBG = false>
 static int tc_launch_kind(ss_ctx* ctx, TcParams p, uint32_t slice_begin, uint32_t nslices, size_t smem, bool dependent) {
     if (!nslices) return SS_OK;
     p.slice_begin = slice_begin;
     p.nslices = nslices;
-    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_tc<KP, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_tc<KP, PAIRED, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.ngroups * nslices);
     cfg.blockDim = dim3(kTcThreads);
@@ -1038,7 +1049,7 @@ static int tc_launch_kind(ss_ctx* ctx, TcParams p, uint32_t slice_begin, uint32_
     attr[0].val.programmaticStreamSerializationAllowed = 1;  // may start while the previous scan launch is still draining
     cfg.attrs = attr;
     cfg.numAttrs = dependent ? 1 : 0;
-    SS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_dtw_scan_tc<KP, PAIRED>, p));
+    SS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_dtw_scan_tc<KP, PAIRED, DBG>, p));
     SS_LAUNCHED(ctx);
     return SS_OK;
 }
@@ -1055,29 +1066,29 @@ static int tc_launch(ss_ctx* ctx, const TcParams& p, uint32_t nsingle, uint32_t 
     return SS_OK;
 }
 
-int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used) {
-    ss_ctx* ctx = d->ctx;
-    *used = false;
-    static int enabled = -1;
-    if (enabled < 0) {
+static bool tc_enabled() {
+    static const int enabled = [] {
         const char* e = getenv("SS_DTW_TC");
-        enabled = e ? atoi(e) : 1;
-    }
-    if (!enabled || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
-    SS_TRY(tc_queries_build(d, q));
-    if (!q->tc_ngroups || !q->tc_ok) return SS_OK;
-    const int kp = k <= 2 ? 8 : 16;  // fp16 products are noisier than the fp32 scan: keep a longer candidate list
-    const uint32_t nslots = q->tc_ngroups * kTcM;
-    d->last_work = d->total_frames * q->total_frames;
-    d->last_uncertified = 0;
-    // slices: contiguous tile ranges balanced by frames; ~2 CTAs per SM in flight order (1 resident per SM)
-    static int waves = 0;
-    if (!waves) {
+        return e ? atoi(e) : 1;
+    }();
+    return enabled != 0;
+}
+
+// slices (contiguous tile ranges of ONE kind - single-segment tiles come first, paired tiles after - balanced by the
+// tiles' step-cost estimate; about `waves` CTAs per SM over the two launches, 1 resident per SM), workspaces and the
+// kernel parameters of one scan of query batch q against dictionary d with candidate lists of kp entries
+struct TcPlan {
+    TcParams p;
+    uint32_t nsingle, nslices, nslots;
+    size_t smem;
+};
+static int tc_plan(ss_dict* d, ss_queries* q, int kp, TcPlan* plan) {
+    ss_ctx* ctx = d->ctx;
+    static const int waves = [] {
         const char* e = getenv("SS_DTW_TC_WAVES");
-        waves = e ? std::max(1, atoi(e)) : 16;
-    }
-    // slices: contiguous tile ranges of ONE kind (single-segment tiles come first, paired tiles after), balanced by the
-    // tiles' step-cost estimate; about `waves` CTAs per SM over the two launches (1 resident per SM)
+        return e ? std::max(1, atoi(e)) : 16;
+    }();
+    const uint32_t nslots = q->tc_ngroups * kTcM;
     const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
     std::vector<uint32_t>& st = d->h_slice_tile;
     st.clear();
@@ -1095,17 +1106,17 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
         if (!kind) nsingle = (uint32_t)st.size();
     }
     st.push_back(d->tc_ntiles);
-    uint32_t nslices = (uint32_t)st.size() - 1;
+    const uint32_t nslices = (uint32_t)st.size() - 1;
     SS_TRY(upload(ctx, d->d_slice_tile, st.data(), st.size()));
-    const uint32_t nlists = nslices;  // one candidate list per (slice, query): the four slots are merged inside the CTA
-    SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nlists * nslots * kp));
+    // one candidate list per (slice, query): the four slots are merged inside the CTA
+    SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nslices * nslots * kp));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
     SS_CUDA(ctx, d->d_cand_adist.reserve((size_t)nslots * kp));
     if (!d->ev_scan0) {
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
     }
-    TcParams p;
+    TcParams& p = plan->p;
     p.a_blocks = q->d_tc_a.p;
     p.group_off = q->d_tc_group_off.p;
     p.group_len = q->d_tc_group_len.p;
@@ -1118,13 +1129,56 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     p.slice_begin = 0;
     p.partial = d->d_tc_partial.p;
     p.max_len = q->max_len;
-    const size_t smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kTcDpThreads * 8 + 1024;
-    if (kp == 8) SS_TRY(tc_launch<8>(ctx, p, nsingle, nslices, smem, nlists, nslots, d));
-    else SS_TRY(tc_launch<16>(ctx, p, nsingle, nslices, smem, nlists, nslots, d));
+    p.dbg = nullptr;
+    p.dbg_nseg = 0;
+    plan->nsingle = nsingle;
+    plan->nslices = nslices;
+    plan->nslots = nslots;
+    plan->smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kTcDpThreads * 8 + 1024;
+    return SS_OK;
+}
+
+int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used) {
+    ss_ctx* ctx = d->ctx;
+    *used = false;
+    if (!tc_enabled() || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
+    SS_TRY(tc_queries_build(d, q));
+    if (!q->tc_ngroups || !q->tc_ok) return SS_OK;
+    const int kp = k <= 2 ? 8 : 16;  // fp16 products are noisier than the fp32 scan: keep a longer candidate list
+    d->last_work = d->total_frames * q->total_frames;
+    d->last_uncertified = 0;
+    TcPlan plan;
+    SS_TRY(tc_plan(d, q, kp, &plan));
+    if (kp == 8) SS_TRY(tc_launch<8>(ctx, plan.p, plan.nsingle, plan.nslices, plan.smem, plan.nslices, plan.nslots, d));
+    else SS_TRY(tc_launch<16>(ctx, plan.p, plan.nsingle, plan.nslices, plan.smem, plan.nslices, plan.nslots, d));
     // certification bound for fp16 inputs: see k_dtw_finalize (bound_mode 1)
-    SS_TRY(dtw_rescore_finalize(d, q, k, kp, nslots, q->d_tc_qid.p, 0.0, q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 1,
+    SS_TRY(dtw_rescore_finalize(d, q, k, kp, plan.nslots, q->d_tc_qid.p, 0.0, q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 1,
                                 q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
     *used = true;
+    return SS_OK;
+}
+
+// ss_dict_debug_tc_scan: the tensor-core scan's raw (filter-stage) distance of EVERY (query, segment) pair, plus the mean
+// frame and norm scale the fp16 operands were built with. d_out: [nq][nseg] floats on the device, pre-filled by the caller
+// (pairs the scan does not evaluate - empty queries / segments - keep that fill). Runs the production kernel with its
+// DBG store compiled in; returns SS_ERR_INVALID if these inputs would not take the tensor-core path.
+int dtw_tc_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale) {
+    ss_ctx* ctx = d->ctx;
+    if (!tc_enabled() || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0)
+        return set_error(ctx, SS_ERR_INVALID, "debug_tc_scan: the tensor-core scan does not apply (segments / queries > %d frames, or disabled)", kTcMaxLen);
+    SS_TRY(tc_queries_build(d, q));
+    if (!q->tc_ngroups || !q->tc_ok) return set_error(ctx, SS_ERR_INVALID, "debug_tc_scan: queries outside the fp16 range");
+    TcPlan plan;
+    SS_TRY(tc_plan(d, q, 8, &plan));
+    plan.p.dbg = d_out;
+    plan.p.dbg_nseg = (uint32_t)d->nseg;
+    SS_TRY((tc_launch_kind<8, false, true>(ctx, plan.p, 0, plan.nsingle, plan.smem, false)));
+    SS_TRY((tc_launch_kind<8, true, true>(ctx, plan.p, plan.nsingle, plan.nslices - plan.nsingle, plan.smem, plan.nsingle != 0)));
+    slot_qid->resize(plan.nslots);
+    SS_CUDA(ctx, cudaMemcpyAsync(slot_qid->data(), q->d_tc_qid.p, plan.nslots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaMemcpyAsync(mu16, d->d_mu.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *scale = d->tc_nb_scale;
     return SS_OK;
 }
 

@@ -126,6 +126,7 @@ int dtw_dict_build(ss_dict* d);       // builds the fp32 stream + strip / tile t
 int dtw_tc_dict_build(ss_dict* d);    // builds the fp16 UMMA tiles (dtw_tc.cu)
 int dtw_queries_build(ss_queries* q, const std::vector<uint32_t>* subset = nullptr); // builds the lane layout (dtw.cu)
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist);
+int dtw_tc_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale);
 int cosine_dict_build(ss_dict* d);    // per-segment norms (cosine.cu)
 int cosine_queries_build(ss_queries* q);
 int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_t* d_out_idx, double* d_out_dist);

@@ -85,3 +85,41 @@ def test_cpp_mirror_file_helpers_match_python_mirror(tmp_path):
     pcm2, _, _ = api._read_wav_pcm(str(tmp_path / "p.wav"))
     assert np.array_equal(pcm, pcm2)                                   # both writers produce the same samples
     assert np.array_equal(np.array(out["back"]), pcm.astype(np.float64) / 2147483647.0)  # reader: s / (i32::MAX >> 0)
+
+
+def test_wav_reader_rejects_what_hound_rejects(tmp_path):
+    """_read_wav_pcm accepts integer PCM only (hound::WavReader at src/sound.rs:117 yields i32 samples; float WAVs, a data
+    chunk before fmt, truncated fmt chunks and odd bit depths are errors), and 8-bit samples are unsigned offset-128."""
+    import struct
+    import numpy as np
+    import pytest
+
+    def wav(chunks):
+        body = b"WAVE" + b"".join(cid + struct.pack("<I", len(b)) + b + (b"\0" if len(b) & 1 else b"") for cid, b in chunks)
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    def fmt(tag, bits, sr=8000, extra=b""):
+        return struct.pack("<HHIIHH", tag, 1, sr, sr * bits // 8, max(bits // 8, 1), bits) + extra
+
+    def load(name, data):
+        p = tmp_path / name
+        p.write_bytes(data)
+        return api._read_wav_pcm(str(p))
+
+    pcm, sr, bits = load("u8.wav", wav([(b"fmt ", fmt(1, 8)), (b"data", bytes([0, 128, 255]))]))
+    assert bits == 8 and sr == 8000.0 and pcm.tolist() == [-128, 0, 127]
+    pcm, _, bits = load("s24.wav", wav([(b"LIST", b"abc"), (b"fmt ", fmt(1, 24)), (b"data", bytes([0xFF, 0xFF, 0xFF, 0x01, 0x00, 0x80]))]))
+    assert bits == 24 and pcm.tolist() == [-1, -8388607]
+    ext = fmt(0xFFFE, 16, extra=struct.pack("<HHI", 22, 16, 4) + struct.pack("<H", 1) + b"\0" * 14)
+    pcm, _, bits = load("ext.wav", wav([(b"fmt ", ext), (b"data", struct.pack("<hh", -2, 7))]))
+    assert bits == 16 and pcm.tolist() == [-2, 7]
+    for name, data in [
+        ("float.wav", wav([(b"fmt ", fmt(3, 32)), (b"data", b"\0" * 8)])),           # IEEE float
+        ("order.wav", wav([(b"data", b"\0" * 8), (b"fmt ", fmt(1, 16))])),           # data before fmt
+        ("short.wav", wav([(b"fmt ", fmt(1, 16)[:10]), (b"data", b"\0" * 8)])),      # truncated fmt
+        ("bits.wav", wav([(b"fmt ", fmt(1, 4)), (b"data", b"\0" * 8)])),             # bits < 8 (was a division by zero)
+        ("nodata.wav", wav([(b"fmt ", fmt(1, 16))])),
+        ("junk.wav", b"RIFFxxxxWAVX"),
+    ]:
+        with pytest.raises(ValueError):
+            load(name, data)
