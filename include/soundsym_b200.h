@@ -159,13 +159,20 @@ int ss_dict_match(ss_dict* dict, const double* q_mfcc, const uint64_t* q_frame_o
 int ss_queries_create(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs,
                       ss_queries** out);
 void ss_queries_destroy(ss_queries* q);
-/* asynchronous on the ctx stream; d_out_idx (u32, nq x k) and d_out_dist (f64, nq x k) are DEVICE pointers */
+/* asynchronous on the ctx stream: the whole match (layout kernel, scan, merge, f64 refine) is enqueued without a host round
+ * trip; d_out_idx (u32, nq x k) and d_out_dist (f64, nq x k) are DEVICE pointers. SS_DTW: whether some query needs a
+ * fallback stage (fp32 scan / exhaustive f64) is only known once the refine has run, so the results in d_out_* are final after
+ * ss_dict_match_finish(dict) - which waits for that one event and, in the rare case, runs the fallback for the queries
+ * concerned. The ss_dict_last_* readers, the next match on the same dictionary and ss_dict_match_sharded* call it
+ * themselves; `q` must stay alive until then. */
 int ss_dict_match_dev(ss_dict* dict, ss_queries* q, int mode, const double* d_targets, int k, uint32_t* d_out_idx,
                       double* d_out_dist);
+int ss_dict_match_finish(ss_dict* dict);
 int ss_topk_merge_dev(ss_ctx* ctx, const uint32_t* d_idx, const double* d_dist, int nlists, size_t nq, int k,
                       uint32_t* d_out_idx, double* d_out_dist);
 /* drops the cached device layouts of a query batch so that the next match rebuilds them (bench.py calls this every
- * step so that the layout kernels are inside the timed region) */
+ * step so that the layout kernels are inside the timed region). Stream-ordered, no synchronisation. The length-sorted
+ * grouping of the batch depends on the offsets only and stays (it is part of ss_queries_create). */
 int ss_queries_invalidate(ss_queries* q);
 /* device time of the dominant kernel (DTW scan / cosine scan) of the last ss_dict_match*(…), measured with CUDA events
  * on the ctx stream; synchronises the stream. Returns a negative value if no match has run. */

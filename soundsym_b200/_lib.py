@@ -19,7 +19,7 @@ SYMBOLS = [
     "ss_ctx_launch_count", "ss_frame_count", "ss_decode_pcm", "ss_sound_analyze", "ss_sound_analyze_pcm", "ss_sound_analyze_batch", "ss_mfcc", "ss_max_power", "ss_mfcc_dev",
     "ss_symbols", "ss_gmm_train", "ss_vote_split", "ss_partition", "ss_dict_create", "ss_dict_destroy", "ss_dict_len", "ss_dict_match",
     "ss_queries_create", "ss_queries_destroy", "ss_dict_match_dev", "ss_topk_merge_dev", "ss_dict_last_work",
-    "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_dict_last_exhaustive", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances", "ss_dict_debug_tc_scan",
+    "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_dict_last_exhaustive", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances", "ss_dict_debug_tc_scan", "ss_dict_match_finish",
 ]
 
 
@@ -87,6 +87,7 @@ def load():
     L.ss_queries_invalidate.argtypes = [vp]
     L.ss_dict_last_scan_ms.argtypes = [vp]
     L.ss_dict_last_scan_ms.restype = dbl
+    L.ss_dict_match_finish.argtypes = [vp]
     L.ss_dict_debug_tc_scan.argtypes = [vp, vp, vp, sz, vp, vp, P(C.c_float)]
     L.ss_resynth.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp]
     L.ss_sequence_distances.argtypes = [vp, vp, sz, i, vp]

@@ -140,38 +140,46 @@ void ss_dict_destroy(ss_dict* d) {
 }
 size_t ss_dict_len(const ss_dict* d) { return d ? d->nseg : 0; }
 uint64_t ss_dict_last_work(const ss_dict* d) { return d ? d->last_work : 0; }
-uint64_t ss_dict_last_tc_fallback(const ss_dict* d) { return d ? d->last_tc_fallback : 0; }
-uint64_t ss_dict_last_exhaustive(const ss_dict* d) { return d ? d->last_exhaustive : 0; }
 
-uint64_t ss_dict_last_uncertified(const ss_dict* dc) {
-    ss_dict* d = const_cast<ss_dict*>(dc);
-    if (!d || !d->d_counters.p) return 0;
-    unsigned long long v = 0;
-    cudaSetDevice(d->ctx->device);
-    if (cudaMemcpyAsync(&v, d->d_counters.p, sizeof(v), cudaMemcpyDeviceToHost, d->ctx->stream) != cudaSuccess) return ~0ull;
-    if (cudaStreamSynchronize(d->ctx->stream) != cudaSuccess) return ~0ull;
-    d->last_uncertified = v;
-    return v;
+int ss_dict_match_finish(ss_dict* d) {
+    if (!d) return set_error(nullptr, SS_ERR_INVALID, "dict is NULL");
+    SS_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
+    return dtw_match_finish(d);
 }
+// the counters of the last match are only final once its fallback decision has been taken
+static bool finished(const ss_dict* dc) {
+    ss_dict* d = const_cast<ss_dict*>(dc);
+    if (!d) return false;
+    cudaSetDevice(d->ctx->device);
+    return dtw_match_finish(d) == SS_OK;
+}
+uint64_t ss_dict_last_tc_fallback(const ss_dict* d) { return finished(d) ? d->last_tc_fallback : ~0ull; }
+uint64_t ss_dict_last_exhaustive(const ss_dict* d) { return finished(d) ? d->last_exhaustive : ~0ull; }
+uint64_t ss_dict_last_uncertified(const ss_dict* d) { return finished(d) ? d->last_uncertified : ~0ull; }
 
 // (re)fills a query batch in place: device buffers are grow-only, so a reused handle does no cudaMalloc / cudaFree
 static int queries_fill(ss_queries* q, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq) {
     ss_ctx* ctx = q->ctx;
     q->nq = nq;
+    q->nonempty = 0;
     q->max_len = 0;
     q->lane_built = false;
     q->cos_built = false;
     q->tc_built = false;
+    q->tc_grouped = false;
     q->h_off.resize(nq + 1);
     const uint64_t base = nq ? q_frame_offsets[0] : 0;
     q->h_off[0] = 0;
     for (size_t i = 0; i < nq; i++) {
         q->h_off[i + 1] = q_frame_offsets[i + 1] - base;
+        q->nonempty += q_frame_offsets[i + 1] > q_frame_offsets[i];
         q->max_len = std::max<uint32_t>(q->max_len, (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, q_frame_offsets[i + 1] - q_frame_offsets[i]));
     }
     q->total_frames = q->h_off[nq];
+    // the frames start crossing PCIe first; the length-sorted grouping of the batch (host work) overlaps that copy
     SS_TRY(upload(ctx, q->d_mfcc, q_mfcc ? q_mfcc + base * q->c : nullptr, (size_t)q->total_frames * q->c));
     SS_TRY(upload(ctx, q->d_off, q->h_off.data(), nq + 1));
+    SS_TRY(dtw_tc_queries_group(q));
     return SS_OK;
 }
 
@@ -204,8 +212,7 @@ int ss_queries_create(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame
 
 int ss_queries_invalidate(ss_queries* q) {
     if (!q) return set_error(nullptr, SS_ERR_INVALID, "queries is NULL");
-    SS_CUDA(q->ctx, cudaSetDevice(q->ctx->device));
-    SS_CUDA(q->ctx, cudaStreamSynchronize(q->ctx->stream));
+    // stream-ordered: the next match rebuilds the layouts behind whatever still reads the old ones; no synchronisation
     q->lane_built = false;
     q->cos_built = false;
     q->tc_built = false;
@@ -238,6 +245,7 @@ int ss_dict_match_dev(ss_dict* d, ss_queries* q, int mode, const double* d_targe
     SS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (mode == SS_COSINE_REF) {
         if (k != 1) return set_error(ctx, SS_ERR_INVALID, "SS_COSINE_REF returns one match per query (k must be 1, got %d)", k);
+        SS_TRY(dtw_match_finish(d));  // a pending SS_DTW match shares the dictionary's workspaces
         return cosine_match_dev(d, q, d_targets, d_out_idx, d_out_dist);
     }
     if (mode == SS_DTW) return dtw_match_dev(d, q, k, d_out_idx, d_out_dist);
@@ -261,17 +269,26 @@ int ss_dict_match(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offs
     }
     ss_queries* q = d->scratch_q;
     auto body = [&]() -> int {
+        SS_TRY(dtw_match_finish(d));  // a pending asynchronous match still owns the workspaces
         SS_TRY(queries_fill(q, q_mfcc, q_frame_offsets, nq));
         SS_CUDA(ctx, d->d_res_idx.reserve(nq * (size_t)k));
         SS_CUDA(ctx, d->d_res_dist.reserve(nq * (size_t)k));
         const bool use_targets = targets && mode == SS_COSINE_REF;
         if (use_targets) SS_TRY(upload(ctx, d->d_res_targets, targets, nq));
         SS_TRY(ss_dict_match_dev(d, q, mode, use_targets ? d->d_res_targets.p : nullptr, k, d->d_res_idx.p, d->d_res_dist.p));
-        if (nq) {
-            SS_CUDA(ctx, cudaMemcpyAsync(out_idx, d->d_res_idx.p, nq * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            SS_CUDA(ctx, cudaMemcpyAsync(out_dist, d->d_res_dist.p, nq * (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        // ONE blocking point per call: the result copies (into the caller's pageable or pinned buffers) queue behind the
+        // match; the uncertified count reaches pinned memory ahead of them, so the fallback decision costs no extra round
+        // trip. Only if a fallback stage had to run are the results copied again.
+        for (int pass = 0; pass < 2; pass++) {
+            if (nq) {
+                SS_CUDA(ctx, cudaMemcpyAsync(out_idx, d->d_res_idx.p, nq * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                SS_CUDA(ctx, cudaMemcpyAsync(out_dist, d->d_res_dist.p, nq * (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (pass || mode != SS_DTW) break;
+            SS_TRY(dtw_match_finish(d));
+            if (!d->last_tc_fallback && !d->last_exhaustive) break;
         }
-        SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return SS_OK;
     };
     const int rc = body();
@@ -296,6 +313,7 @@ int ss_dict_debug_tc_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_fr
     SS_CUDA(ctx, d_out.reserve(nslots * nseg));
     SS_CUDA(ctx, cudaMemsetAsync(d_out.p, 0xFF, nslots * nseg * sizeof(float), ctx->stream));  // NaN = not evaluated
     std::vector<uint32_t> slot_qid;
+    SS_TRY(dtw_match_finish(d));
     int rc = dtw_tc_debug_scan(d, &q, d_out.p, &slot_qid, out_mu, out_scale);
     if (rc != SS_OK) {
         cudaStreamSynchronize(ctx->stream);

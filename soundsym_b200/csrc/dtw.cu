@@ -495,7 +495,7 @@ int dtw_queries_build(ss_queries* q, const std::vector<uint32_t>* subset) {
                                                           q->d_max_norm.p);
         SS_LAUNCHED(ctx);
     }
-    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // (the group tables are staged by cudaMemcpyAsync before it returns: no synchronisation needed for the host vectors)
     q->lane_built = !subset;  // a subset layout is transient
     return SS_OK;
 }
@@ -512,19 +512,28 @@ static int g_scan_rb = 0;  // 0 = default; tools/tests may override through SS_D
 
 static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset);
 
-// reads back which queries the last stage could not certify
+// which queries the last stage could not certify (synchronous; only called once the counter said there are some)
 static int uncertified_subset(ss_dict* d, ss_queries* q, std::vector<uint32_t>* subset) {
     ss_ctx* ctx = d->ctx;
     subset->clear();
-    unsigned long long n_unc = 0;
-    SS_CUDA(ctx, cudaMemcpyAsync(&n_unc, d->d_counters.p, sizeof(n_unc), cudaMemcpyDeviceToHost, ctx->stream));
-    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n_unc == 0) return SS_OK;
     std::vector<uint8_t> flags(q->nq);
     SS_CUDA(ctx, cudaMemcpyAsync(flags.data(), q->d_uncert_flag.p, q->nq, cudaMemcpyDeviceToHost, ctx->stream));
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < q->nq; i++)
         if (flags[i]) subset->push_back((uint32_t)i);
+    return SS_OK;
+}
+
+// the uncertified count of the stage that just ran travels to pinned host memory behind it; ev_done marks its arrival
+static int post_counters(ss_dict* d) {
+    ss_ctx* ctx = d->ctx;
+    if (!d->h_counters) {
+        SS_CUDA(ctx, cudaHostAlloc((void**)&d->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+        SS_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+    }
+    SS_CUDA(ctx, d->d_counters.reserve(4));
+    SS_CUDA(ctx, cudaMemcpyAsync(d->h_counters, d->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaEventRecord(d->ev_done, ctx->stream));
     return SS_OK;
 }
 
@@ -534,28 +543,58 @@ static int uncertified_subset(ss_dict* d, ss_queries* q, std::vector<uint32_t>* 
 //   3. exhaustive f64 DTW against every segment  exact.cu      exact by construction
 // Stage 3 only triggers when more than KP segments are closer to each other than the fp32 scan can resolve (e.g. many
 // near-identical dictionary entries); it guarantees that what ss_dict_match returns is THE f64 top-k.
+//
+// dtw_match_dev enqueues the first applicable stage and returns without a host round trip: the whole step (layout kernel,
+// scan, merge, refine) is in the stream before the GPU has started on it. Whether a later stage is needed is only known
+// once the refine has run; dtw_match_finish waits for that (one event), and runs stages 2 / 3 synchronously for the few
+// queries concerned. Every reader of the results or of the last_* counters goes through dtw_match_finish first.
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
     if (k < 1 || k > SS_MAX_TOPK) return set_error(ctx, SS_ERR_INVALID, "k must be in 1..%d (got %d)", SS_MAX_TOPK, k);
+    SS_TRY(dtw_match_finish(d));  // the previous match shares this dictionary's workspaces
     SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
     SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
     d->last_tc_fallback = 0;
     d->last_exhaustive = 0;
+    d->last_uncertified = 0;
     bool used = false;
     SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
+    if (!used) SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr));
+    SS_TRY(post_counters(d));
+    d->pending.active = true;
+    d->pending.stage = used ? 1 : 2;
+    d->pending.q = q;
+    d->pending.k = k;
+    d->pending.d_out_idx = d_out_idx;
+    d->pending.d_out_dist = d_out_dist;
+    return SS_OK;
+}
+
+int dtw_match_finish(ss_dict* d) {
+    if (!d->pending.active) return SS_OK;
+    ss_ctx* ctx = d->ctx;
+    d->pending.active = false;
+    ss_queries* q = d->pending.q;
+    const int k = d->pending.k;
+    SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
+    unsigned long long n_unc = d->h_counters[0];
     std::vector<uint32_t> subset;
-    if (used) {
+    if (d->pending.stage == 1 && n_unc) {
         SS_TRY(uncertified_subset(d, q, &subset));
         d->last_tc_fallback = subset.size();
-        if (subset.empty()) return SS_OK;
-        SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, &subset));
-    } else {
-        SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr));
+        SS_TRY(dtw_fp32_match(d, q, k, d->pending.d_out_idx, d->pending.d_out_dist, &subset));
+        SS_TRY(post_counters(d));
+        SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
+        n_unc = d->h_counters[0];
     }
-    SS_TRY(uncertified_subset(d, q, &subset));
-    d->last_exhaustive = subset.size();
-    if (subset.empty()) return SS_OK;
-    return dtw_exhaustive_match(d, q, k, subset, d_out_idx, d_out_dist);
+    if (n_unc) {
+        SS_TRY(uncertified_subset(d, q, &subset));
+        d->last_exhaustive = subset.size();
+        SS_TRY(dtw_exhaustive_match(d, q, k, subset, d->pending.d_out_idx, d->pending.d_out_dist));
+        n_unc = 0;  // everything is exact now
+    }
+    d->last_uncertified = n_unc;
+    return SS_OK;
 }
 
 static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset) {

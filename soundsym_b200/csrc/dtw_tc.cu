@@ -273,8 +273,11 @@ __global__ void k_tc_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
 #pragma unroll
     for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcN>((int)n, k)) = row[k];
 }
-// one thread per (group g = blockIdx.x, row i = blockIdx.y, query m): A_i[m, :] = [-2 (a_i - mu) (13), s, s, rd(|a_i|^2 / s)]
-// slot_max_na (per query: max |a_i|^2 over its rows) and max_norm[0] must be zeroed before the launch
+// one thread per (group g = blockIdx.x, row i = blockIdx.y, query m): A_i[m, :] = [-2 (a_i - mu) (13), s, s, rd(|a_i|^2 / s)],
+// written as the two 16-byte K chunks of row m (K-major core matrices). slot_max_na (per query: max |a_i|^2 over its rows)
+// and max_norm[0] must be zeroed before the launch. A query that leaves the fp16 range (a coefficient beyond +-3e4 after
+// centring, or |a_i|^2 / s beyond 60000: far louder than the dictionary) is clamped and gets slot_max_na = +inf: its scan
+// result is then never certified (scan_lower_bound = -inf) and the fp32 scan re-runs it - no host decision needed.
 __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
                                  const uint32_t* __restrict__ group_len, const uint64_t* __restrict__ group_off,
                                  const uint32_t* __restrict__ qid, float scale, unsigned char* __restrict__ a_blocks,
@@ -286,14 +289,17 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
     const uint32_t Lm = id != 0xFFFFFFFFu ? (uint32_t)(off[id + 1] - off[id]) : 0u;
     unsigned char* blk = a_blocks + group_off[g];
     const float inv_scale = 1.0f / scale;  // power of two: exact
-    __half row[kTcK];
+    __align__(16) __half row[kTcK];
 #pragma unroll
     for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
     float nrm = 0.f;
     if (i < Lm) {
         const double* src = mfcc + (off[id] + i) * c;
+        bool clamped = false;
         for (int k = 0; k < c; k++) {
-            const __half h = __float2half_rn((float)(src[k] - mu[k]));
+            float x = (float)(src[k] - mu[k]);
+            if (!(fabsf(x) <= 3.0e4f)) x = x > 0.f ? 3.0e4f : (x < 0.f ? -3.0e4f : 0.f), clamped = true;  // also catches NaN
+            const __half h = __float2half_rn(x);
             const float v = __half2float(h);
             nrm += v * v;
             row[k] = __float2half_rn(-2.f * v);  // exact
@@ -301,16 +307,17 @@ __global__ void k_tc_query_tiles(const double* __restrict__ mfcc, const uint64_t
         row[13] = __float2half_rn(scale);
         row[14] = __float2half_rn(scale);
         // |a_i|^2 rides in the spare K slot, rounded DOWN: the scan cost never exceeds the cost of the rounded frames
-        // (the host keeps the fp32 scan when max |a|^2 / s would leave the fp16 range)
-        row[15] = __float2half_rd(fminf(nrm * inv_scale, 65504.f));
+        if (!(nrm * inv_scale <= 60000.f)) clamped = true;
+        row[15] = __float2half_rd(fminf(nrm * inv_scale, 60000.f));
+        if (clamped) nrm = __int_as_float(0x7f800000);
     }
     unsigned char* base = blk + (size_t)i * kTcATileBytes;
-#pragma unroll
-    for (int k = 0; k < kTcK; k++) *reinterpret_cast<__half*>(base + tc_tile_offset<kTcM>((int)m, k)) = row[k];
-    if (nrm == nrm) atomicMax(reinterpret_cast<unsigned*>(slot_max_na + g * kTcM + m), __float_as_uint(nrm));  // nrm >= 0
-    float mx = nrm;
+    *reinterpret_cast<uint4*>(base + tc_tile_offset<kTcM>((int)m, 0)) = *reinterpret_cast<const uint4*>(&row[0]);
+    *reinterpret_cast<uint4*>(base + tc_tile_offset<kTcM>((int)m, 8)) = *reinterpret_cast<const uint4*>(&row[8]);
+    if (i < Lm) atomicMax(reinterpret_cast<unsigned*>(slot_max_na + g * kTcM + m), __float_as_uint(nrm));  // nrm >= 0 (or +inf)
+    float mx = nrm < __int_as_float(0x7f800000) ? nrm : 0.f;
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((m & 31) == 0 && mx == mx) atomicMax(reinterpret_cast<unsigned*>(max_norm), __float_as_uint(mx));
+    if ((m & 31) == 0) atomicMax(reinterpret_cast<unsigned*>(max_norm), __float_as_uint(mx));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -849,39 +856,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
     }
 }
 
-// per query slot: merge the (slice, half) candidate lists by packed (ord(dist), idx) key
+// per query slot: merge the per-slice candidate lists (each ascending) by packed (ord(dist), idx) key. One WARP per slot:
+// lane l folds lists l, l + 32, .. into its own ascending top-KP (normally one list per lane: a 64-byte load), then KP
+// rounds of "smallest head over the warp" (two redux.sync) pop the merged list, lane r keeping output r.
 template <int KP>
-__global__ void k_tc_merge(const unsigned long long* __restrict__ partial, uint32_t nlists, uint32_t nslots, uint32_t* __restrict__ cand_idx,
-                           float* __restrict__ cand_adist) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_tc_merge(const unsigned long long* __restrict__ partial, uint32_t nlists, uint32_t nslots,
+                                                  uint32_t* __restrict__ cand_idx, float* __restrict__ cand_adist) {
+    const uint32_t slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (slot >= nslots) return;
+    const unsigned long long EMPTY = 0xFFFFFFFFFFFFFFFFull;
     unsigned long long best[KP];
 #pragma unroll
-    for (int s = 0; s < KP; s++) best[s] = 0xFFFFFFFFFFFFFFFFull;
-    for (uint32_t l = 0; l < nlists; l++) {
-        const unsigned long long* src = partial + ((size_t)l * nslots + slot) * KP;
+    for (int s = 0; s < KP; s++) best[s] = EMPTY;
+    for (uint32_t l = lane; l < nlists; l += 32) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(partial + ((size_t)l * nslots + slot) * KP);
+        unsigned long long key[KP];
 #pragma unroll
-        for (int s = 0; s < KP; s++) {
-            const unsigned long long key = src[s];
-            if (key < best[KP - 1]) {
-                best[KP - 1] = key;
+        for (int s = 0; s < KP; s += 2) {
+            const ulonglong2 v = __ldg(src + s / 2);
+            key[s] = v.x, key[s + 1] = v.y;
+        }
+        if (l < 32) {
 #pragma unroll
-                for (int s2 = KP - 1; s2 > 0; s2--)
-                    if (best[s2] < best[s2 - 1]) {
-                        const unsigned long long tmp = best[s2];
-                        best[s2] = best[s2 - 1];
-                        best[s2 - 1] = tmp;
-                    }
+            for (int s = 0; s < KP; s++) best[s] = key[s];
+        } else {
+#pragma unroll
+            for (int s = 0; s < KP; s++) {
+                if (key[s] < best[KP - 1]) {
+                    best[KP - 1] = key[s];
+#pragma unroll
+                    for (int s2 = KP - 1; s2 > 0; s2--)
+                        if (best[s2] < best[s2 - 1]) {
+                            const unsigned long long tmp = best[s2];
+                            best[s2] = best[s2 - 1];
+                            best[s2 - 1] = tmp;
+                        }
+                }
             }
         }
     }
+    unsigned long long mine = EMPTY;
 #pragma unroll
-    for (int s = 0; s < KP; s++) {
-        const bool empty = best[s] == 0xFFFFFFFFFFFFFFFFull;
-        cand_idx[(size_t)slot * KP + s] = empty ? 0xFFFFFFFFu : (uint32_t)best[s];
-        const uint32_t o = (uint32_t)(best[s] >> 32);
-        const uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-        cand_adist[(size_t)slot * KP + s] = empty ? __int_as_float(0x7f800000) : __uint_as_float(b);
+    for (int r = 0; r < KP; r++) {
+        const uint32_t hi = (uint32_t)(best[0] >> 32), lo = (uint32_t)best[0];
+        const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+        const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+        const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+        if (best[0] == m && m != EMPTY) {  // keys are unique (a segment sits in exactly one slice): one lane pops
+#pragma unroll
+            for (int s = 0; s + 1 < KP; s++) best[s] = best[s + 1];
+            best[KP - 1] = EMPTY;
+        }
+        if (lane == r) mine = m;
+    }
+    if (lane < KP) {
+        const bool empty = mine == EMPTY;
+        cand_idx[(size_t)slot * KP + lane] = empty ? 0xFFFFFFFFu : (uint32_t)mine;
+        const uint32_t o = (uint32_t)(mine >> 32);
+        const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        cand_adist[(size_t)slot * KP + lane] = empty ? __int_as_float(0x7f800000) : __uint_as_float(bits);
     }
 }
 
@@ -962,11 +996,15 @@ int dtw_tc_dict_build(ss_dict* d) {
     return SS_OK;
 }
 
-static int tc_queries_build(ss_dict* d, ss_queries* q) {
+// Length-sorted groups of 128 queries (a counting sort on the host: lengths <= 32 here). Depends on the lengths only, so it
+// runs once per batch, when the batch is filled (ss_queries_create / the fill inside ss_dict_match, where it overlaps the
+// host-to-device copy of the frames), not inside the match.
+int dtw_tc_queries_group(ss_queries* q) {
     ss_ctx* ctx = q->ctx;
-    if (q->tc_built && q->tc_dict_serial == d->tc_serial) return SS_OK;  // the A blocks depend on the dictionary's mean frame and scale
-    // queries in descending length order, ties in index order: a counting sort (lengths <= 32 here) - this runs on the host
-    // inside every match of a fresh query batch, with the GPU idle behind it
+    q->tc_grouped = false;
+    q->tc_built = false;
+    q->tc_ngroups = 0;
+    if (q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
     auto len_of = [&](uint32_t i) { return (uint32_t)(q->h_off[i + 1] - q->h_off[i]); };
     std::vector<uint32_t> order;
     {
@@ -1005,13 +1043,24 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
         }
         bytes += (uint64_t)lmax * kTcATileBytes;
     }
+    // (host-to-device copies from pageable memory are staged before cudaMemcpyAsync returns: the vectors may go out of scope)
     SS_TRY(upload(ctx, q->d_tc_slot_len, slen.data(), slen.size()));
     q->tc_ngroups = (uint32_t)glen.size();
     q->h_tc_group_len = glen;
+    q->tc_a_bytes = bytes;
     SS_TRY(upload(ctx, q->d_tc_group_len, glen.data(), glen.size()));
     SS_TRY(upload(ctx, q->d_tc_group_off, goff.data(), goff.size()));
     SS_TRY(upload(ctx, q->d_tc_qid, gqid.data(), gqid.size()));
-    SS_CUDA(ctx, q->d_tc_a.reserve(std::max<uint64_t>(bytes, 16)));
+    q->tc_grouped = true;
+    return SS_OK;
+}
+
+// the fp16 A blocks of a grouped batch for dictionary d (its mean frame and norm scale); asynchronous, no host round trip
+static int tc_queries_build(ss_dict* d, ss_queries* q) {
+    ss_ctx* ctx = q->ctx;
+    if (q->tc_built && q->tc_dict_serial == d->tc_serial) return SS_OK;  // the A blocks depend on the dictionary's mean frame and scale
+    if (!q->tc_grouped) SS_TRY(dtw_tc_queries_group(q));
+    SS_CUDA(ctx, q->d_tc_a.reserve(std::max<uint64_t>(q->tc_a_bytes, 16)));
     SS_CUDA(ctx, q->d_tc_slot_max_na.reserve(std::max<size_t>((size_t)q->tc_ngroups * kTcM, 1)));
     SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
     SS_CUDA(ctx, q->d_tc_max_norm.reserve(1));
@@ -1023,11 +1072,6 @@ static int tc_queries_build(ss_dict* d, ss_queries* q) {
                                                                  q->d_tc_max_norm.p, q->d_tc_slot_max_na.p);
         SS_LAUNCHED(ctx);
     }
-    float qmx = 0.f;
-    SS_CUDA(ctx, cudaMemcpyAsync(&qmx, q->d_tc_max_norm.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
-    // rd(|a|^2 / s) must stay inside the fp16 range (queries far louder than the dictionary keep the fp32 scan)
-    q->tc_ok = qmx / d->tc_nb_scale < 60000.f;
     q->tc_built = true;
     q->tc_dict_serial = d->tc_serial;
     return SS_OK;
@@ -1061,7 +1105,7 @@ static int tc_launch(ss_ctx* ctx, const TcParams& p, uint32_t nsingle, uint32_t 
     SS_TRY((tc_launch_kind<KP, true>(ctx, p, nsingle, nslices - nsingle, smem, nsingle != 0)));
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
     d->scan_timed = true;
-    k_tc_merge<KP><<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_tc_partial.p, nlists, nslots, d->d_cand_idx.p, d->d_cand_adist.p);
+    k_tc_merge<KP><<<ceil_div(nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, nlists, nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
     return SS_OK;
 }
@@ -1089,25 +1133,29 @@ static int tc_plan(ss_dict* d, ss_queries* q, int kp, TcPlan* plan) {
         return e ? std::max(1, atoi(e)) : 16;
     }();
     const uint32_t nslots = q->tc_ngroups * kTcM;
-    const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
-    std::vector<uint32_t>& st = d->h_slice_tile;
-    st.clear();
-    uint64_t total = 0;
-    for (uint32_t f : d->h_tc_tile_frames) total += f;
-    const uint64_t per = std::max<uint64_t>(1, (total + want - 1) / want);
-    uint32_t nsingle = 0;
-    for (int kind = 0; kind < 2; kind++) {
-        const uint32_t tb = kind ? d->tc_first_pair_tile : 0, te = kind ? d->tc_ntiles : d->tc_first_pair_tile;
-        uint64_t acc = per;  // forces a slice start at the first tile of the kind
-        for (uint32_t t = tb; t < te; t++) {
-            if (acc >= per) st.push_back(t), acc = 0;
-            acc += d->h_tc_tile_frames[t];
+    if (d->slice_for_groups != q->tc_ngroups) {  // the slice table only depends on the dictionary and the number of query groups
+        const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
+        std::vector<uint32_t> st;  // (staged by cudaMemcpyAsync before it returns)
+        uint64_t total = 0;
+        for (uint32_t f : d->h_tc_tile_frames) total += f;
+        const uint64_t per = std::max<uint64_t>(1, (total + want - 1) / want);
+        uint32_t nsingle = 0;
+        for (int kind = 0; kind < 2; kind++) {
+            const uint32_t tb = kind ? d->tc_first_pair_tile : 0, te = kind ? d->tc_ntiles : d->tc_first_pair_tile;
+            uint64_t acc = per;  // forces a slice start at the first tile of the kind
+            for (uint32_t t = tb; t < te; t++) {
+                if (acc >= per) st.push_back(t), acc = 0;
+                acc += d->h_tc_tile_frames[t];
+            }
+            if (!kind) nsingle = (uint32_t)st.size();
         }
-        if (!kind) nsingle = (uint32_t)st.size();
+        st.push_back(d->tc_ntiles);
+        d->tc_nsingle = nsingle;
+        d->tc_nslices = (uint32_t)st.size() - 1;
+        SS_TRY(upload(ctx, d->d_tc_slice_tile, st.data(), st.size()));
+        d->slice_for_groups = q->tc_ngroups;
     }
-    st.push_back(d->tc_ntiles);
-    const uint32_t nslices = (uint32_t)st.size() - 1;
-    SS_TRY(upload(ctx, d->d_slice_tile, st.data(), st.size()));
+    const uint32_t nsingle = d->tc_nsingle, nslices = d->tc_nslices;
     // one candidate list per (slice, query): the four slots are merged inside the CTA
     SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nslices * nslots * kp));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
@@ -1124,7 +1172,7 @@ static int tc_plan(ss_dict* d, ss_queries* q, int kp, TcPlan* plan) {
     p.ngroups = q->tc_ngroups;
     p.tiles = reinterpret_cast<const unsigned char*>(d->d_tc_tiles.p);
     p.desc = d->d_tc_desc.p;
-    p.slice_tile = d->d_slice_tile.p;
+    p.slice_tile = d->d_tc_slice_tile.p;
     p.nslices = nslices;
     p.slice_begin = 0;
     p.partial = d->d_tc_partial.p;
@@ -1143,7 +1191,7 @@ int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     *used = false;
     if (!tc_enabled() || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
     SS_TRY(tc_queries_build(d, q));
-    if (!q->tc_ngroups || !q->tc_ok) return SS_OK;
+    if (!q->tc_ngroups) return SS_OK;
     const int kp = k <= 2 ? 8 : 16;  // fp16 products are noisier than the fp32 scan: keep a longer candidate list
     d->last_work = d->total_frames * q->total_frames;
     d->last_uncertified = 0;
@@ -1167,7 +1215,7 @@ int dtw_tc_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint3
     if (!tc_enabled() || !d->tc_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0)
         return set_error(ctx, SS_ERR_INVALID, "debug_tc_scan: the tensor-core scan does not apply (segments / queries > %d frames, or disabled)", kTcMaxLen);
     SS_TRY(tc_queries_build(d, q));
-    if (!q->tc_ngroups || !q->tc_ok) return set_error(ctx, SS_ERR_INVALID, "debug_tc_scan: queries outside the fp16 range");
+    if (!q->tc_ngroups) return set_error(ctx, SS_ERR_INVALID, "debug_tc_scan: no non-empty query");
     TcPlan plan;
     SS_TRY(tc_plan(d, q, 8, &plan));
     plan.p.dbg = d_out;

@@ -259,8 +259,7 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices, nslots,
                                                                   q->d_group_qid.p, d->index_base, d_out_idx, d_out_dist);
     SS_LAUNCHED(ctx);
-    // the slice table is read by the async upload: keep the host vector alive until it has been consumed
-    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // (the slice table was staged by cudaMemcpyAsync before it returned: asynchronous from here)
     return SS_OK;
 }
 
@@ -361,51 +360,18 @@ k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ dof
     exact[pair] = (la && lb) ? last / (double)(la + lb) : kInf;
 }
 
-// The same refine with one WARP per candidate pair, for sequences of <= 32 frames on both sides (the tensor-core scan's
-// domain). Lane j owns dictionary column j: its frame sits in registers, the query rows are broadcast loads, and the
-// local costs of the whole pair go to shared memory first (39 f64 operations per cell, all 32 lanes busy, coalesced
-// loads - the thread-per-pair form spends its time on 13 fully divergent loads per cell). The recurrence then runs as an
-// anti-diagonal wavefront: at step t lane j computes cell (t - j, j) from its own previous value (up), its left
-// neighbour's previous value (left, one 64-bit shuffle) and the value it received a step earlier (diag). Every cell is
-// produced by the same operations in the same order as in k_dtw_rescore, so the distances stay bit-equal to the oracle.
-__global__ void __launch_bounds__(128)
-k_dtw_rescore_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
-                   const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
-                   uint32_t t_begin, uint32_t t_end, int kp, int s_begin, int s_count, RescoreBound rb, double* __restrict__ exact,
-                   unsigned long long* __restrict__ counters) {
-    __shared__ double scost[4][32 * 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t = t_begin + blockIdx.x * 4 + warp;
-    if (t >= t_end) return;  // warp-uniform from here on
-    const uint32_t slot = t / (uint32_t)s_count;
-    const uint32_t pair = slot * (uint32_t)kp + (uint32_t)s_begin + t % (uint32_t)s_count;
-    const uint32_t qid = group_qid[slot];
-    const uint32_t idx = cand_idx[pair];
-    if (qid == 0xFFFFFFFFu || idx == 0xFFFFFFFFu) {
-        if (lane == 0) exact[pair] = kInf;
-        return;
-    }
-    if (rb.cand_adist) {
-        double kth = 0.0;
-        for (int s = 0; s < rb.k; s++) {
-            double e = exact[(size_t)slot * kp + s];
-            if (!(e < kInf)) e = kInf;  // empty slot / NaN: nothing can be ruled out
-            kth = fmax(kth, e);
-        }
-        const double na = rb.slot_max_na ? (double)rb.slot_max_na[slot] : (double)rb.max_na[0];
-        if (scan_lower_bound(rb.cand_adist[pair], na, (double)rb.max_nb[0], rb.eps, rb.bound_mode) > kth) {
-            if (lane == 0) exact[pair] = kInf;  // provably outside the top-k
-            return;
-        }
-        if (lane == 0) atomicAdd(&counters[1], 1ull);
-    }
-    const double* a = qmfcc + qoff[qid] * c;
-    const double* b = dmfcc + doff[idx] * c;
-    const int la = (int)(qoff[qid + 1] - qoff[qid]), lb = (int)(doff[idx + 1] - doff[idx]);  // both <= 32 (host-checked)
+// ---------------------------------------------------------------------------------------------------------------
+// The whole refine of one query slot by ONE warp (sequences of <= 32 frames on both sides): the k best candidates by scan
+// distance unconditionally, the other kp - k only if the scan's error bound cannot rule them out against the k-th exact
+// distance, then the (distance, index) sort, the top-k store and the certification - what k_dtw_rescore_warp (twice) and
+// k_dtw_finalize do in three launches, with the same arithmetic per pair (warp_dtw_exact is k_dtw_rescore_warp's body).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_dtw_exact(const double* __restrict__ a, int la, const double* __restrict__ b, int lb, int c, double* cst,
+                                                 int lane) {
     double br[SS_MAX_NCOEFFS];
 #pragma unroll
     for (int k = 0; k < SS_MAX_NCOEFFS; k++) br[k] = (k < c && lane < lb) ? b[(size_t)lane * c + k] : 0.0;
-    double* cst = scost[warp];
+    __syncwarp();  // the previous pair's costs are no longer read
     for (int i = 0; i < la; i++) {
         double cost = 0.0;
 #pragma unroll
@@ -417,15 +383,15 @@ k_dtw_rescore_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict_
         cst[i * 32 + lane] = cost;
     }
     __syncwarp();
-    double cur = kInf, recv_prev = kInf, result = kInf;  // own last cell D(i-1, j); what the left neighbour sent one step ago
+    double cur = kInf, recv_prev = kInf, result = kInf;
     for (int step = 0; step < la + lb - 1; step++) {
         const double recv = __shfl_up_sync(0xffffffffu, cur, 1);  // left neighbour's last cell = D(i, j-1)
         const int i = step - lane;
         const bool active = lane < lb && i >= 0 && i < la;
         if (active) {
-            const double up = cur;                              // D(i-1, j)  (+inf before the first row)
-            const double left = lane ? recv : kInf;             // D(i, j-1)
-            const double diag = lane ? recv_prev : kInf;        // D(i-1, j-1)
+            const double up = cur;
+            const double left = lane ? recv : kInf;
+            const double diag = lane ? recv_prev : kInf;
             double m;
             if (i == 0 && lane == 0) m = 0.0;
             else m = fmin(fmin(up, left), diag);
@@ -435,7 +401,78 @@ k_dtw_rescore_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict_
         recv_prev = recv;
     }
     result = __shfl_sync(0xffffffffu, result, lb > 0 ? lb - 1 : 0);
-    if (lane == 0) exact[pair] = (la && lb) ? result / (double)(la + lb) : kInf;
+    return (la && lb) ? result / (double)(la + lb) : kInf;
+}
+
+__global__ void __launch_bounds__(128)
+k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                  const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
+                  const float* __restrict__ cand_adist, uint32_t nslots, int kp, int k, uint32_t index_base, const float* __restrict__ max_na,
+                  const float* __restrict__ max_nb, double eps, const float* __restrict__ slot_max_na, int bound_mode,
+                  uint8_t* __restrict__ uncert_flag, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                  unsigned long long* __restrict__ counters) {
+    __shared__ double scost[4][32 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * 4 + warp;
+    if (slot >= nslots) return;  // warp-uniform from here on
+    const uint32_t qid = group_qid[slot];
+    if (qid == 0xFFFFFFFFu) return;
+    const uint32_t my_idx = lane < kp ? cand_idx[(size_t)slot * kp + lane] : 0xFFFFFFFFu;
+    const float my_adist = lane < kp ? cand_adist[(size_t)slot * kp + lane] : __int_as_float(0x7f800000);
+    const double na = slot_max_na ? (double)slot_max_na[slot] : (double)max_na[0];
+    const double nb = (double)max_nb[0];
+    const double* a = qmfcc + qoff[qid] * c;
+    const int la = (int)(qoff[qid + 1] - qoff[qid]);
+    double my_exact = kInf, kth = 0.0;
+    unsigned extra = 0;
+    for (int s = 0; s < kp; s++) {
+        const uint32_t idx = __shfl_sync(0xffffffffu, my_idx, s);
+        if (idx == 0xFFFFFFFFu) {
+            if (s < k) kth = kInf;  // an empty place among the first k: nothing can be ruled out
+            continue;
+        }
+        if (s >= k) {
+            const float adist = __shfl_sync(0xffffffffu, my_adist, s);
+            if (scan_lower_bound(adist, na, nb, eps, bound_mode) > kth) continue;  // provably outside the top-k
+            extra++;
+        }
+        const double e = warp_dtw_exact(a, la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, scost[warp], lane);
+        if (lane == s) my_exact = e;
+        if (s < k) kth = fmax(kth, e < kInf ? e : kInf);
+    }
+    // (distance, index) insertion sort on lane 0; NaN / inf candidates are dropped
+    double dv[kMaxKeep];
+    uint32_t iv[kMaxKeep];
+    int n = 0;
+    for (int s = 0; s < kp; s++) {
+        const double dd = __shfl_sync(0xffffffffu, my_exact, s);
+        const uint32_t ii = __shfl_sync(0xffffffffu, my_idx, s);
+        if (lane != 0 || ii == 0xFFFFFFFFu || !(dd < kInf)) continue;
+        int pos = n;
+        while (pos > 0 && (dd < dv[pos - 1] || (dd == dv[pos - 1] && ii < iv[pos - 1]))) {
+            dv[pos] = dv[pos - 1];
+            iv[pos] = iv[pos - 1];
+            pos--;
+        }
+        dv[pos] = dd;
+        iv[pos] = ii;
+        n++;
+    }
+    const float worst = __shfl_sync(0xffffffffu, my_adist, kp - 1);
+    if (lane == 0) {
+        for (int s = 0; s < k; s++) {
+            out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
+            out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
+        }
+        bool uncertified = false;  // see k_dtw_finalize
+        if (worst < __int_as_float(0x7f800000)) {
+            const double kth_exact = n >= k ? dv[k - 1] : kInf;
+            uncertified = !(scan_lower_bound(worst, na, nb, eps, bound_mode) > kth_exact);
+            if (uncertified) atomicAdd(&counters[0], 1ull);
+        }
+        if (uncert_flag) uncert_flag[qid] = uncertified ? 1 : 0;
+        if (extra) atomicAdd(&counters[1], (unsigned long long)extra);
+    }
 }
 
 __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
@@ -493,7 +530,8 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
                          bool fill, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
-    if (q->nq && fill) {
+    // queries without a frame never reach a slot: their rows keep (inf, 0xFFFFFFFF). Only launched when such queries exist.
+    if (q->nq && fill && q->nonempty < q->nq) {
         k_fill_result<<<ceil_div((long long)q->nq * k, 256), 256, 0, ctx->stream>>>(d_out_idx, d_out_dist, q->nq * (size_t)k,
                                                                                    0xFFFFFFFFu, kInf);
         SS_LAUNCHED(ctx);
@@ -501,9 +539,17 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     SS_CUDA(ctx, d->d_counters.reserve(4));
     SS_CUDA(ctx, cudaMemsetAsync(d->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     if (!nslots || !d->ntiles) return SS_OK;
+    const uint32_t max_ld = std::max<uint32_t>(d->max_len, 1);
+    if (max_ld <= 32 && q->max_len <= 32) {  // one warp per query slot does the whole refine
+        k_dtw_refine_warp<<<ceil_div(nslots, 4), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,
+                                                                        d->d_cand_idx.p, d->d_cand_adist.p, nslots, kp, std::min(k, kp), d->index_base,
+                                                                        d_max_na, d_max_nb, eps, d_slot_max_na, bound_mode, d_uncert_flag,
+                                                                        d_out_idx, d_out_dist, d->d_counters.p);
+        SS_LAUNCHED(ctx);
+        return SS_OK;
+    }
     const uint32_t npairs = nslots * (uint32_t)kp;
     SS_CUDA(ctx, d->d_cand_exact.reserve(npairs));
-    const uint32_t max_ld = std::max<uint32_t>(d->max_len, 1);
     const uint64_t budget = 32ull << 20;  // doubles of DP-row scratch (256 MB)
     const uint32_t batch = (uint32_t)std::min<uint64_t>(npairs, std::max<uint64_t>(1024, budget / max_ld));
     SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)batch * max_ld));
@@ -515,13 +561,6 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
         if (s_count <= 0) continue;
         RescoreBound rb = {phase ? d->d_cand_adist.p : nullptr, d_max_na, d_max_nb, d_slot_max_na, eps, bound_mode, std::min(k, kp)};
         const uint32_t nt = nslots * (uint32_t)s_count;
-        if (max_ld <= 32 && q->max_len <= 32) {  // one warp per pair
-            k_dtw_rescore_warp<<<ceil_div(nt, 4), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,
-                                                                         d->d_cand_idx.p, 0, nt, kp, s_begin, s_count, rb, d->d_cand_exact.p,
-                                                                         d->d_counters.p);
-            SS_LAUNCHED(ctx);
-            continue;
-        }
         for (uint32_t tb = 0; tb < nt; tb += batch) {
             const uint32_t te = std::min<uint32_t>(nt, tb + batch);
             kern<<<ceil_div(te - tb, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,

@@ -74,6 +74,21 @@ struct ss_dict {
     std::vector<uint32_t> h_tc_tile_frames;  // per tile: instruction estimate of one pipeline step (slice balancing)
     ss::DevBuf<unsigned long long> d_tc_partial;
     ss::DevBuf<float> d_tc_max_norm;         // [0] = max |fp16(b - mu)|^2
+    // the last SS_DTW match is asynchronous up to its fallback decision: ss::dtw_match_finish waits for ev_done, reads the
+    // uncertified count from pinned memory and runs the fallback stages for the queries that need them
+    struct Pending {
+        bool active = false;
+        int stage = 0;  // 1 = the tensor-core scan ran, 2 = the fp32 scan ran (for every query)
+        struct ss_queries* q = nullptr;
+        int k = 0;
+        uint32_t* d_out_idx = nullptr;
+        double* d_out_dist = nullptr;
+    } pending;
+    unsigned long long* h_counters = nullptr;  // pinned, 4 entries: [0] uncertified queries, [1] extra candidates refined
+    cudaEvent_t ev_done = nullptr;
+    ss::DevBuf<uint32_t> d_tc_slice_tile;       // the tensor-core scan's own slice table (cached)
+    uint32_t slice_for_groups = 0xFFFFFFFFu;  // tc_ngroups the cached slice table (d_slice_tile / h_slice_tile) was built for
+    uint32_t tc_nsingle = 0, tc_nslices = 0;
     // host-buffer entry point (ss_dict_match): query batch + result buffers reused across calls (grow-only)
     struct ss_queries* scratch_q = nullptr;
     ss::DevBuf<uint32_t> d_res_idx;
@@ -84,6 +99,7 @@ struct ss_dict {
 struct ss_queries {
     ss_ctx* ctx = nullptr;
     size_t nq = 0;
+    size_t nonempty = 0;  // queries with at least one frame
     int c = 0;
     uint64_t total_frames = 0;
     uint32_t max_len = 0;
@@ -101,10 +117,13 @@ struct ss_queries {
     ss::DevBuf<double> d_lane64;                                     // [row*c + e][32] f64 (cosine-ref), built on first use
     bool cos_built = false;
     bool lane_built = false;
-    // tensor-core scan: groups of 128 equal-length queries
+    // tensor-core scan: groups of 128 (nearly) equal-length queries. The grouping only depends on the lengths: it is built
+    // (host counting sort + uploads) when the batch is filled; the fp16 A blocks depend on the dictionary and are built by
+    // the first match against it.
+    bool tc_grouped = false;
     bool tc_built = false;
-    bool tc_ok = false;                      // rd(|a|^2 / s) fits fp16 for every query row
     uint64_t tc_dict_serial = 0;             // ss_dict::tc_serial the A blocks were built for
+    uint64_t tc_a_bytes = 0;
     uint32_t tc_ngroups = 0;
     std::vector<uint32_t> h_tc_group_len;
     ss::DevBuf<uint32_t> d_tc_group_len, d_tc_qid, d_tc_slot_len;  // qid / slot_len: ngroups x 128
@@ -118,6 +137,8 @@ struct ss_queries {
 inline ss_dict::~ss_dict() {
     if (ev_scan0) cudaEventDestroy(ev_scan0);
     if (ev_scan1) cudaEventDestroy(ev_scan1);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (h_counters) cudaFreeHost(h_counters);
     delete scratch_q;
 }
 
@@ -125,7 +146,10 @@ namespace ss {
 int dtw_dict_build(ss_dict* d);       // builds the fp32 stream + strip / tile tables (dtw.cu)
 int dtw_tc_dict_build(ss_dict* d);    // builds the fp16 UMMA tiles (dtw_tc.cu)
 int dtw_queries_build(ss_queries* q, const std::vector<uint32_t>* subset = nullptr); // builds the lane layout (dtw.cu)
+int dtw_tc_queries_group(ss_queries* q);  // length-sorted groups of 128 for the tensor-core scan (dtw_tc.cu); no-op for long queries
+// asynchronous on the ctx stream up to the fallback decision; dtw_match_finish completes it (a no-op when nothing is pending)
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist);
+int dtw_match_finish(ss_dict* d);
 int dtw_tc_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale);
 int cosine_dict_build(ss_dict* d);    // per-segment norms (cosine.cu)
 int cosine_queries_build(ss_queries* q);
