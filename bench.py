@@ -1,20 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the soundsym hot path on B200 (contract in the build brief, section 4).
+"""bench.py — benchmarks of the soundsym hot path on B200 (contract in the build brief, section 4).
 
-Metric (BASELINE.json): DTW cell-updates/s and queries/s, 100k-segment dictionary, on 1/2/4/8 B200.
-Workload (config 4 of BASELINE.json): synthetic dictionary of 100 000 segments x 10 000 query segments,
+Default (what the driver runs) = the headline: BASELINE.json's metric "DTW cell-updates/s and queries/s, 100k-segment
+dictionary, on 1/2/4/8 B200" on config 4: synthetic dictionary of 100 000 segments x 10 000 query segments,
 13-coefficient MFCC frames, lengths ~ U{4..32}; a STEP = one match of the whole query batch against the whole dictionary
-(top-1, SS_DTW). With N GPUs the dictionary is partitioned into N contiguous shards (balanced by frames), every rank
-sees all queries, per-rank top-k are all-gathered over NCCL and merged on every rank  ->  "scaling": "strong".
+(top-1, SS_DTW). With N GPUs the dictionary is partitioned into N contiguous shards (balanced by frames), the exchange
+(query all-gather over NVLink, one ncclAllGather of the per-shard top-k, merge) runs INSIDE the library
+(ss_dict_match_sharded*)  ->  "scaling": "strong". torch.distributed is only used for the barrier, for shipping the 128-byte
+communicator id and for the max-over-ranks of the timings.
 
   value      cells/s with the queries' f64 MFCCs already in HBM: layout kernel + tensor-core scan + merge + f64 refine
-             (+ all-gather + merge for N > 1), CUDA events on the library's stream, max over ranks.
-  e2e        the same through the reference-facing call ss_dict_match with pinned HOST buffers: H2D of the queries and
-             D2H of the results inside the timed region, every step.
-  roofline   the dominant kernel (k_dtw_scan_tc), timed live with CUDA events around its launch (ss_dict_last_scan_ms);
-             algorithmic bytes = sum over pairs of (Lq + Ld) * C * 4 B, peak = MEASURED_PEAKS.json hbm_gbs.
+             (+ exchange for N > 1), CUDA events on the library's stream around the K steps, max over ranks. The L2 flush
+             (a 256 MB fill) at the start of every step is INSIDE the bracket.
+  e2e        the same through the reference-facing call ss_dict_match / ss_dict_match_sharded with pinned HOST buffers:
+             H2D of the queries and D2H of the results inside the timed region, every step.
+  roofline   the dominant kernel (k_dtw_scan_tc), timed live with CUDA events around its launch (ss_dict_last_scan_ms).
+             It is bound by CUDA-core ISSUE of the DP recurrence (one FMNMX3 + one FADD per cell), not by HBM or the tensor
+             pipe: achieved = useful DP cells / clk / SM, peak = the ALU pipe's FMNMX3 rate measured on this chip
+             (tools/microbench_band2.cu: 63.9 lanes / clk / SM; the register-resident band alone reaches 47.3).
+             The pairwise-streaming byte model of SURVEY.md §8d is kept as `effective_hbm_gbs` WITHOUT a fraction.
   cpu_baseline / --impl reference   the f64 CPU oracle ("port": the Rust reference cannot be built here) on a bounded
              sample of the same workload, on the box's host cores.
+
+Other lines (not run by the driver; committed under profiles/bench/):  --config 3 (10k x 1k on 1 GPU, DTW and cosine-ref),
+--config 2 (MFCC + partition of the Section_7_1 fixture, and the MFCC kernel on 1 h of audio against both of its roofs),
+--config 5 (examples/reconstruction.rs on 1 h of synthetic audio, N GPUs).
 """
 import argparse
 import json
@@ -42,6 +52,10 @@ def parse():
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--cpu-sample-queries", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5], help="BASELINE.json config (default 4 = the headline)")
+    ap.add_argument("--probe-queries", type=int, default=256, help="random queries checked against the f64 oracle after the run")
+    ap.add_argument("--seconds", type=float, default=3600.0, help="configs 2 / 5: seconds of synthetic audio")
+    ap.add_argument("--mode", default="dtw", choices=["dtw", "cosine"], help="config 5: matcher")
     return ap.parse_args()
 
 
@@ -156,6 +170,24 @@ def cpu_sample(d, doff, q, qoff, nsample, threads):
     return cells / dt, dt, cells
 
 
+WORKLOADS = {
+    4: "synthetic 100k-segment dictionary x 10k queries, C=13, L~U{4..32}, DTW top-1 (config 4)",
+    3: "synthetic 10k-segment dictionary x 1k queries, C=13, L~U{4..32}, DTW top-1 (config 3)",
+}
+# measured on B200 by tools/microbench_band2.cu (profiles/r2_microbench_band2.log): FMNMX3 issues at 16 lanes / clk / SMSP
+ALU_FMNMX3_LANES_PER_CLK_SM = 63.9
+BAND_CEILING_CELLS_PER_CLK_SM = 47.3  # the register-resident band alone (FMNMX3 + FADD per cell), 16 warps / SM
+
+
+def config_dict(args):
+    """the same object on both arms (the driver compares them): workload, sizes, and how the GPU arm treats L2"""
+    std = (args.nd, args.nq) in ((ND, NQ), (10000, 1000))
+    return {"workload": WORKLOADS.get(args.config, WORKLOADS[4]) if std else
+            "synthetic %d-segment dictionary x %d queries, C=13, L~U{4..32}, DTW top-1" % (args.nd, args.nq),
+            "nd": args.nd, "nq": args.nq, "ncoeffs": C, "k": K,
+            "l2": "GPU arm: flushed, a 256 MB buffer is overwritten at the start of every timed step (inside the bracket)"}
+
+
 def run_reference(args):
     """the reference arm: the CPU path (oracle port; the Rust crate cannot be built in this image) with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -180,19 +212,15 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "dtw_cell_updates_per_s", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 100k-segment dictionary x 10k queries, C=13, L~U{4..32}, DTW top-1 (config 4)",
-                       "nd": args.nd, "nq": args.nq, "ncoeffs": C, "k": K},
+            "config": config_dict(args),
             "queries_per_s": nsample / (ms * 1e-3),
             "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-
+def run_match(args):
+    import ctypes as CT
     import torch
     import torch.distributed as dist
     from soundsym_b200 import api
@@ -201,65 +229,65 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(local)
     n_gpus = world
 
     d, doff, q, qoff = workload(args.nd, args.nq)
     nq = len(qoff) - 1
-    cuts = shard_bounds(doff, world)
-    s0, s1 = cuts[rank], cuts[rank + 1]
     ctx = api.Context(local)
+    lib = ctx.lib
+    cuts = api.shard_bounds(doff, world)
+    assert cuts == shard_bounds(doff, world)
+    s0, s1 = cuts[rank], cuts[rank + 1]
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     shard = api.DeviceDictionary(ctx, d, doff[s0:s1 + 1], C, index_base=s0)
     total_cells = int(doff[-1]) * int(qoff[-1])
+    shard_cells = int(doff[s1] - doff[s0]) * int(qoff[-1])
+
+    comm = None
+    if world > 1:
+        # the library owns the NCCL communicator of the data path; torch only carries its 128-byte id to the other ranks
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(api.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = api.Comm(ctx, world, rank, idt.cpu().numpy().tobytes())
 
     # device-resident queries + outputs
-    qdev = api.DeviceQueries(ctx, q, qoff, C)
+    if world > 1:
+        qh = CT.c_void_p()
+        ctx.check(lib.ss_queries_create_sharded(comm.h, q.ctypes.data, qoff.ctypes.data, nq, C, CT.byref(qh)))
+    else:
+        qdev = api.DeviceQueries(ctx, q, qoff, C)
+        qh = qdev.h
     o_idx = torch.empty((nq, K), dtype=torch.int32, device="cuda")
     o_dist = torch.empty((nq, K), dtype=torch.float64, device="cuda")
-    if world > 1:
-        g_idx = torch.empty((world, nq, K), dtype=torch.int32, device="cuda")
-        g_dist = torch.empty((world, nq, K), dtype=torch.float64, device="cuda")
-        m_idx = torch.empty((nq, K), dtype=torch.int32, device="cuda")
-        m_dist = torch.empty((nq, K), dtype=torch.float64, device="cuda")
     # pinned host buffers for the e2e leg
     hq = torch.from_numpy(q).pin_memory()
     hqoff = torch.from_numpy(qoff.astype(np.int64)).pin_memory()
     h_idx = torch.empty((nq, K), dtype=torch.int32).pin_memory()
     h_dist = torch.empty((nq, K), dtype=torch.float64).pin_memory()
-    h_gidx = torch.empty((world, nq, K), dtype=torch.int32).pin_memory() if world > 1 else None
-
-    def exchange():
-        """all-gather of the per-shard top-k over NCCL + lexicographic merge on every rank."""
-        dist.all_gather_into_tensor(g_idx, o_idx)
-        dist.all_gather_into_tensor(g_dist, o_dist)
-        ctx.check(ctx.lib.ss_topk_merge_dev(ctx.h, g_idx.data_ptr(), g_dist.data_ptr(), world, nq, K, m_idx.data_ptr(), m_dist.data_ptr()))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step_resident():
         flush.zero_()
-        ctx.check(ctx.lib.ss_queries_invalidate(qdev.h))  # layout kernels run inside the step
-        ctx.check(ctx.lib.ss_dict_match_dev(shard.h, qdev.h, SS_DTW, None, K, o_idx.data_ptr(), o_dist.data_ptr()))
+        ctx.check(lib.ss_queries_invalidate(qh))  # the layout kernel runs inside the step
         if world > 1:
-            exchange()
+            ctx.check(lib.ss_dict_match_sharded_dev(shard.h, comm.h, qh, SS_DTW, None, K, o_idx.data_ptr(), o_dist.data_ptr()))
+        else:
+            ctx.check(lib.ss_dict_match_dev(shard.h, qh, SS_DTW, None, K, o_idx.data_ptr(), o_dist.data_ptr()))
 
     def step_e2e():
         flush.zero_()
-        # the reference-facing call: HOST buffers in, HOST buffers out (H2D + D2H inside)
-        ctx.check(ctx.lib.ss_dict_match(shard.h, hq.data_ptr(), hqoff.data_ptr(), nq, SS_DTW, None, K, h_idx.data_ptr(), h_dist.data_ptr()))
+        # the reference-facing call: HOST buffers in, HOST buffers out (H2D + D2H inside; 1/N of the query bytes per GPU)
         if world > 1:
-            o_idx.copy_(h_idx, non_blocking=True)
-            o_dist.copy_(h_dist, non_blocking=True)
-            exchange()
-            h_idx.copy_(m_idx, non_blocking=True)
-            h_dist.copy_(m_dist, non_blocking=True)
-            stream.synchronize()
+            ctx.check(lib.ss_dict_match_sharded(shard.h, comm.h, hq.data_ptr(), hqoff.data_ptr(), nq, SS_DTW, None, K, h_idx.data_ptr(), h_dist.data_ptr()))
+        else:
+            ctx.check(lib.ss_dict_match(shard.h, hq.data_ptr(), hqoff.data_ptr(), nq, SS_DTW, None, K, h_idx.data_ptr(), h_dist.data_ptr()))
 
     def barrier():
         ctx.sync()
@@ -275,6 +303,7 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             fn()
+        ctx.check(lib.ss_dict_match_finish(shard.h))  # the last step's fallback decision belongs to the step
         e1.record(stream)
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -295,41 +324,50 @@ def main():
         launches0 = ctx.launches
         ms_step, _ = timed(step_resident, args.steps)
         launches = ctx.launches - launches0
-        scan_ms = float(ctx.lib.ss_dict_last_scan_ms(shard.h))
-        tc_fallback = shard.last_tc_fallback
+        scan_ms = float(lib.ss_dict_last_scan_ms(shard.h))
+        tc_fallback, exhaustive, uncert = shard.last_tc_fallback, shard.last_exhaustive, shard.last_uncertified
         clocks = sampler.stop() if rank == 0 else None
-        uncert = shard.last_uncertified
         for _ in range(2):
             step_e2e()
         # e2e blocks on the host every step (the call returns results in host memory): wall clock == device time here
         _, ms_e2e = timed(step_e2e, args.steps)
+    res_idx = o_idx.cpu().numpy().view(np.uint32)
+    res_dist = o_dist.cpu().numpy()
+    assert np.array_equal(res_idx, h_idx.numpy().view(np.uint32)) and np.array_equal(res_dist, h_dist.numpy()), "e2e and resident paths disagree"
+    assert uncert == 0, "%d queries left uncertified" % uncert
 
-    # correctness guard on a few queries against the oracle (outside every timed region)
-    ok = None
+    # correctness gate against the oracle on a random sample of queries (outside every timed region); a wrong match must not
+    # produce a normal bench line
+    probe = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.set_threads(O.hardware_threads())
-        res_idx = (m_idx if world > 1 else o_idx).cpu().numpy().astype(np.uint32)
-        res_dist = (m_dist if world > 1 else o_dist).cpu().numpy()
-        probe = 4
-        oi, od = O.dtw_topk(d, doff, q[: int(qoff[probe])], qoff[: probe + 1], C, K)
-        ok = bool(np.array_equal(oi, res_idx[:probe]) and np.allclose(od, res_dist[:probe], rtol=1e-12, atol=0))
-        assert np.array_equal(res_idx, h_idx.numpy().astype(np.uint32)), "e2e and resident paths disagree"
+        ids = np.sort(np.random.default_rng(2026).choice(nq, size=min(args.probe_queries, nq), replace=False))
+        rows = np.concatenate([np.arange(int(qoff[i]), int(qoff[i + 1])) for i in ids])
+        so = np.zeros(len(ids) + 1, dtype=np.uint64)
+        so[1:] = np.cumsum((qoff[1:] - qoff[:-1])[ids])
+        oi, od = O.dtw_topk(d, doff, np.ascontiguousarray(q[rows]), so, C, K)
+        ok = bool(np.array_equal(oi, res_idx[ids]) and np.allclose(od, res_dist[ids], rtol=1e-12, atol=0))
+        assert ok, "GPU match differs from the f64 oracle on the probe sample"
+        probe = {"queries": int(len(ids)), "indices_equal": True, "max_rel_dist_err": float(np.max(np.abs(od - res_dist[ids]) / od))}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg = algorithmic_bytes(doff, qoff, s0, s1)
-        achieved = alg / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
-        scan_kernel = "k_dtw_scan_tc (tcgen05 fp16 cost + CUDA-core DP)" if os.environ.get("SS_DTW_TC", "1") != "0" else "k_dtw_scan (fp32)"
-        traffic = None
+        tc = os.environ.get("SS_DTW_TC", "1") != "0"
+        scan_kernel = "k_dtw_scan_tc (tcgen05 fp16 cost matrix in TMEM + CUDA-core DP)" if tc else "k_dtw_scan (fp32)"
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "dtw_scan_traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            traffic = tj.get("tc" if "tc" in scan_kernel else "fp32", {}).get("dram_bytes_per_launch") if world == 1 else None
+        if os.path.exists(tp) and world == 1 and args.nd == ND and args.nq == NQ:
+            tj = json.load(open(tp)).get("tc" if tc else "fp32", {})
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        sm_mhz = ((clocks or {}).get("sm_mhz") or 1965.0)
+        sms = 148.0
+        cells_clk_sm = shard_cells / (scan_ms * 1e-3) / sms / (sm_mhz * 1e6) if scan_ms > 0 else None
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import oracle as O
@@ -337,43 +375,57 @@ def main():
             nsample = args.cpu_sample_queries or max(4 * threads, 64)
             rate, dt, cells = cpu_sample(d, doff, q, qoff, nsample, threads)
             cpu = {"value": rate, "unit": "cells/s", "cores": threads, "kind": "port",
-                   "sample": "%d of %d queries x full %d-segment dictionary (%.3e cells, %.1f s), f64 oracle port" % (nsample, nq, args.nd, cells, dt)}
+                   "sample": "%d of %d queries x full %d-segment dictionary (%.3e cells, %.1f s), scalar f64 oracle port" % (nsample, nq, args.nd, cells, dt)}
         line = {
             "metric": "dtw_cell_updates_per_s", "value": total_cells / (ms_step * 1e-3), "unit": "cells/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (DP scan; local costs from f16 tensor-core products accumulated in f32; winners refined in f64)", "data": "synthetic",
-            "config": {"workload": "synthetic 100k-segment dictionary x 10k queries, C=13, L~U{4..32}, DTW top-1 (config 4)",
-                       "nd": args.nd, "nq": args.nq, "ncoeffs": C, "k": K, "parallelism": "dictionary sharded x%d, NCCL all-gather top-k merge" % world,
-                       "l2": "flushed: a 256 MB buffer is overwritten at the start of every timed step (dictionary resident: %.0f MB fp32 stream + %.0f MB f64)" % (
-                           int(doff[s1] - doff[s0]) * 64 / 1e6, int(doff[s1] - doff[s0]) * C * 8 / 1e6)},
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (DP scan; local costs from f16 tensor-core products accumulated in f32; winners refined in f64)", "data": "synthetic",
+            "config": config_dict(args),
+            "parallelism": "dictionary sharded x%d inside the library: queries 1/N per GPU over PCIe + NVLink all-gather, one ncclAllGather of the "
+                           "per-shard top-k, merge on every rank" % world,
+            "resident_per_gpu_mb": {"fp16_tiles": int(doff[s1] - doff[s0]) * 32 * 1.4 / 1e6, "f64_frames": int(doff[s1] - doff[s0]) * C * 8 / 1e6},
             "queries_per_s": nq / (ms_step * 1e-3),
             "e2e": {"value": total_cells / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(q.nbytes + qoff.nbytes), "d2h_bytes_per_step": int(nq * K * 12),
+                    "h2d_bytes_per_step": int((q.nbytes + world - 1) // world + qoff.nbytes), "d2h_bytes_per_step": int(nq * K * 12),
                     "queries_per_s": nq / (ms_e2e * 1e-3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": alg,
-                         "note": "EFFECTIVE bandwidth of the pairwise-streaming model of SURVEY.md §8d (bytes the CPU path streams per pair); "
-                                 "operands stay on chip (one dictionary tile serves 128 queries), so compulsory DRAM traffic is ~0.1 GB and "
-                                 "frac can exceed 1. The kernel is bound by CUDA-core issue of the DP recurrence (DESIGN.md §3.1), not by HBM "
-                                 "or the tensor pipe",
-                         "issue_bound": {"cells_per_clk_per_sm": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) / 148.0
-                                         / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) if scan_ms > 0 else None,
-                                         "ceiling_cells_per_clk_per_sm": 45.3,
-                                         "ceiling_note": "the register-resident band alone (FMNMX3 + FADD per cell, no TMEM, no barriers) measured on "
-                                                         "B200 with 16 warps / SM: tools/microbench_band.cu, profiles/r1_microbench_band.log"},
-                         "cells_per_s_kernel": (int(doff[s1] - doff[s0]) * int(qoff[-1])) / (scan_ms * 1e-3) if scan_ms > 0 else None},
+            "roofline": {"bound": "issue", "kernel": scan_kernel, "achieved": cells_clk_sm, "peak": ALU_FMNMX3_LANES_PER_CLK_SM,
+                         "unit": "DP cells/clk/SM", "frac": (cells_clk_sm / ALU_FMNMX3_LANES_PER_CLK_SM) if cells_clk_sm else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "measured on B200: the ALU pipe issues FMNMX3 (one per DP cell) at 63.9 lanes/clk/SM (tools/microbench_band2.cu, "
+                                        "profiles/r2_microbench_band2.log); SM clock = median sampled under load",
+                         "band_ceiling": BAND_CEILING_CELLS_PER_CLK_SM,
+                         "frac_of_band_ceiling": (cells_clk_sm / BAND_CEILING_CELLS_PER_CLK_SM) if cells_clk_sm else None,
+                         "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step if ms_step else None,
+                         "cells_per_s_kernel": shard_cells / (scan_ms * 1e-3) if scan_ms > 0 else None,
+                         "effective_hbm_gbs": alg / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                         "algorithmic_bytes_per_launch": alg,
+                         "note": "effective_hbm_gbs is the pairwise-streaming model of SURVEY.md 8d (bytes the CPU path streams per pair): operands stay "
+                                 "on chip (one dictionary tile serves 128 queries from shared memory / TMEM), so it is NOT a roofline fraction; "
+                                 "`traffic` is the physical DRAM traffic of one launch from ncu"},
             "cpu_baseline": cpu,
-            "uncertified_queries": int(uncert),
-            "tc_fallback_queries": int(tc_fallback),
-            "oracle_probe_ok": ok,
+            "uncertified_queries": int(uncert), "tc_fallback_queries": int(tc_fallback), "exhaustive_queries": int(exhaustive),
+            "oracle_probe": probe,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.config == 3 and (args.nd, args.nq) == (ND, NQ):
+        args.nd, args.nq = 10000, 1000
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.config in (3, 4):
+        return run_match(args)
+    from tools import bench_configs
+    return bench_configs.run(args)
 
 
 if __name__ == "__main__":

@@ -189,6 +189,52 @@ uint64_t ss_dict_last_tc_fallback(const ss_dict* dict);
  * entries) and that were therefore matched by exhaustive f64 DTW against every segment. */
 uint64_t ss_dict_last_exhaustive(const ss_dict* dict);
 
+/* ---- the matcher across the GPUs of one box ------------------------------------------------------------
+ * The dictionary is partitioned into contiguous shards balanced by frames (ss_shard_bounds), one ss_dict per GPU created with
+ * index_base = the shard's first global index. A match then runs on every GPU against its shard; the query frames cross PCIe
+ * once (1 / nranks per GPU) and are all-gathered over NVLink; the per-shard top-k lists are exchanged with ONE ncclAllGather
+ * and merged on every rank by (distance, index) - the first-minimum rule of the reference's strict-'<' scan
+ * (src/sound.rs:361-366) across shards, so the result equals the single-GPU result bit for bit.
+ *
+ * Two front ends:
+ *   single process   ss_dict_create_sharded(ctxs, nctx, ...) / ss_sharded_dict_match(...): same arguments as ss_dict_create /
+ *                    ss_dict_match; the library owns the shards, an NCCL communicator per GPU (ncclCommInitAll) and one
+ *                    worker thread per GPU. This is what SoundDictionary::match_sound / at_distance (src/sound.rs:346-370)
+ *                    bind to when more than one GPU is given.
+ *   one rank per process (torchrun, MPI): ss_comm_unique_id on rank 0, ship the SS_COMM_ID_BYTES to the other ranks by any
+ *                    means, ss_comm_create on every rank, then the rank-local calls ss_queries_create_sharded /
+ *                    ss_dict_match_sharded[_dev] with this rank's shard - collective: every rank must make the same call.
+ * NCCL is bound at run time (dlopen of libnccl.so.2); without it these calls return SS_ERR_CUDA and nothing else is affected. */
+#define SS_COMM_ID_BYTES 128
+typedef struct ss_comm ss_comm;                 /* this rank's end of a communicator: one ctx (GPU), rank, nranks */
+typedef struct ss_sharded_dict ss_sharded_dict; /* a dictionary partitioned across the GPUs of one process */
+
+int ss_shard_bounds(const uint64_t* frame_offsets, size_t nseg, int nshards, uint64_t* out_cuts /* nshards + 1 */);
+int ss_comm_unique_id(void* out_id /* SS_COMM_ID_BYTES */);
+int ss_comm_create(ss_ctx* ctx, int nranks, int rank, const void* id, ss_comm** out);
+int ss_comm_create_all(ss_ctx* const* ctxs, int nctx, ss_comm** out /* nctx entries */);
+void ss_comm_destroy(ss_comm* comm);
+int ss_comm_rank(const ss_comm* comm);
+int ss_comm_nranks(const ss_comm* comm);
+/* the query batch resident on this rank's GPU, its frames uploaded 1 / nranks per rank and all-gathered over NVLink */
+int ss_queries_create_sharded(ss_comm* comm, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs,
+                              ss_queries** out);
+/* local match against `shard`, exchange, merge: d_out_* (device) hold the GLOBAL top-k on every rank. Stream-ordered, but the
+ * host waits for the shard's fallback decision (ss_dict_match_finish) before it enqueues the exchange. */
+int ss_dict_match_sharded_dev(ss_dict* shard, ss_comm* comm, ss_queries* q, int mode, const double* d_targets, int k,
+                              uint32_t* d_out_idx, double* d_out_dist);
+/* the same with HOST buffers in and out (ss_dict_match's contract) */
+int ss_dict_match_sharded(ss_dict* shard, ss_comm* comm, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int mode,
+                          const double* targets, int k, uint32_t* out_idx, double* out_dist);
+/* SoundDictionary::from_segments / add_segments + match_sound / at_distance over several GPUs of ONE process */
+int ss_dict_create_sharded(ss_ctx* const* ctxs, int nctx, const double* mfcc_flat, const uint64_t* frame_offsets, size_t nseg,
+                           int ncoeffs, ss_sharded_dict** out);
+int ss_sharded_dict_match(ss_sharded_dict* dict, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int mode,
+                          const double* targets, int k, uint32_t* out_idx, double* out_dist);
+void ss_sharded_dict_destroy(ss_sharded_dict* dict);
+size_t ss_sharded_dict_len(const ss_sharded_dict* dict);
+int ss_sharded_dict_nshards(const ss_sharded_dict* dict);
+
 /* ss_dict_debug_tc_scan   measurement hook for the SS_DTW filter stage (no reference counterpart; tests/test_parity_large_gpu.py):
  *              the RAW distance the tensor-core scan (fp16 products, fp32 accumulation in TMEM, fp32 DP) assigns to EVERY
  *              (query, segment) pair - out_scan[nq x nseg], NaN where a side is empty - together with the mean frame

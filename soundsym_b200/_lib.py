@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("SS_B200_LIB") or os.path.join(_HERE, "libsoundsym_b20
 SS_OK, SS_ERR_INVALID, SS_ERR_CUDA, SS_ERR_NOMEM, SS_ERR_NOT_TRAINED, SS_ERR_EMPTY_DICT, SS_ERR_TOO_FEW_ROWS = 0, -1, -2, -3, -4, -5, -6
 SS_COSINE_REF, SS_DTW = 0, 1
 SS_MAX_TOPK = 8
+SS_COMM_ID_BYTES = 128
 
 # every symbol include/soundsym_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
@@ -20,6 +21,9 @@ SYMBOLS = [
     "ss_symbols", "ss_gmm_train", "ss_vote_split", "ss_partition", "ss_dict_create", "ss_dict_destroy", "ss_dict_len", "ss_dict_match",
     "ss_queries_create", "ss_queries_destroy", "ss_dict_match_dev", "ss_topk_merge_dev", "ss_dict_last_work",
     "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_dict_last_exhaustive", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances", "ss_dict_debug_tc_scan", "ss_dict_match_finish",
+    "ss_shard_bounds", "ss_comm_unique_id", "ss_comm_create", "ss_comm_create_all", "ss_comm_destroy", "ss_comm_rank", "ss_comm_nranks",
+    "ss_queries_create_sharded", "ss_dict_match_sharded_dev", "ss_dict_match_sharded", "ss_dict_create_sharded", "ss_sharded_dict_match",
+    "ss_sharded_dict_destroy", "ss_sharded_dict_len", "ss_sharded_dict_nshards",
 ]
 
 
@@ -88,6 +92,24 @@ def load():
     L.ss_dict_last_scan_ms.argtypes = [vp]
     L.ss_dict_last_scan_ms.restype = dbl
     L.ss_dict_match_finish.argtypes = [vp]
+    L.ss_shard_bounds.argtypes = [vp, sz, i, vp]
+    L.ss_comm_unique_id.argtypes = [vp]
+    L.ss_comm_create.argtypes = [vp, i, i, vp, P(vp)]
+    L.ss_comm_create_all.argtypes = [P(vp), i, P(vp)]
+    L.ss_comm_destroy.argtypes = [vp]
+    L.ss_comm_destroy.restype = None
+    L.ss_comm_rank.argtypes = [vp]
+    L.ss_comm_nranks.argtypes = [vp]
+    L.ss_queries_create_sharded.argtypes = [vp, vp, vp, sz, i, P(vp)]
+    L.ss_dict_match_sharded_dev.argtypes = [vp, vp, vp, i, vp, i, vp, vp]
+    L.ss_dict_match_sharded.argtypes = [vp, vp, vp, vp, sz, i, vp, i, vp, vp]
+    L.ss_dict_create_sharded.argtypes = [P(vp), i, vp, vp, sz, i, P(vp)]
+    L.ss_sharded_dict_match.argtypes = [vp, vp, vp, sz, i, vp, i, vp, vp]
+    L.ss_sharded_dict_destroy.argtypes = [vp]
+    L.ss_sharded_dict_destroy.restype = None
+    L.ss_sharded_dict_len.argtypes = [vp]
+    L.ss_sharded_dict_len.restype = sz
+    L.ss_sharded_dict_nshards.argtypes = [vp]
     L.ss_dict_debug_tc_scan.argtypes = [vp, vp, vp, sz, vp, vp, P(C.c_float)]
     L.ss_resynth.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp]
     L.ss_sequence_distances.argtypes = [vp, vp, sz, i, vp]

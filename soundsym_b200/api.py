@@ -277,6 +277,103 @@ class DeviceDictionary:
         return int(self.ctx.lib.ss_dict_last_exhaustive(self.h))
 
 
+def shard_bounds(frame_offsets, nshards):
+    """ss_shard_bounds: contiguous segment ranges balanced by frames -> nshards + 1 cut positions (host arithmetic only)."""
+    off = np.ascontiguousarray(frame_offsets, dtype=np.uint64)
+    cuts = np.zeros(int(nshards) + 1, dtype=np.uint64)
+    L = _lib.load()
+    rc = L.ss_shard_bounds(_ptr(off), off.shape[0] - 1, int(nshards), _ptr(cuts))
+    if rc != 0:
+        raise SoundsymError(rc, L.ss_last_error(None).decode())
+    return [int(c) for c in cuts]
+
+
+class Comm:
+    """ss_comm: this rank's end of an NCCL communicator owned by the library (one rank per process). Rank 0 calls
+    Comm.unique_id() and ships the bytes to the other ranks (any transport); every rank then constructs Comm(ctx, n, rank, id)."""
+
+    def __init__(self, ctx, nranks, rank, id_bytes):
+        self.ctx = ctx
+        buf = (C.c_char * _lib.SS_COMM_ID_BYTES).from_buffer_copy(bytes(id_bytes))
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ss_comm_create(ctx.h, int(nranks), int(rank), buf, C.byref(h)))
+        self.h, self.nranks, self.rank = h, int(nranks), int(rank)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * _lib.SS_COMM_ID_BYTES)()
+        L = _lib.load()
+        rc = L.ss_comm_unique_id(buf)
+        if rc != 0:
+            raise SoundsymError(rc, L.ss_last_error(None).decode())
+        return bytes(buf.raw)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.ss_comm_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def match(self, shard, q_flat, q_frame_offsets, mode=SS_DTW, k=1, targets=None):
+        """ss_dict_match_sharded (collective: every rank calls it with the same queries and its own shard)
+        -> the GLOBAL (idx u32 [nq, k], dist f64 [nq, k]) on every rank."""
+        q = np.ascontiguousarray(q_flat, dtype=np.float64)
+        qo = np.ascontiguousarray(q_frame_offsets, dtype=np.uint64)
+        nq = qo.shape[0] - 1
+        idx = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float64)
+        t = np.ascontiguousarray(targets, dtype=np.float64) if targets is not None else None
+        self.ctx.check(self.ctx.lib.ss_dict_match_sharded(shard.h, self.h, _ptr(q), _ptr(qo), nq, int(mode), _ptr(t), int(k), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+
+class ShardedDictionary:
+    """ss_sharded_dict: one dictionary partitioned across the GPUs of THIS process (one Context per GPU); match() has
+    ss_dict_match's contract and returns the same bits as a single-GPU DeviceDictionary."""
+
+    def __init__(self, ctxs, mfcc_flat, frame_offsets, ncoeffs=None):
+        self.ctxs = list(ctxs)
+        mfcc_flat = np.ascontiguousarray(mfcc_flat, dtype=np.float64)
+        off = np.ascontiguousarray(frame_offsets, dtype=np.uint64)
+        if ncoeffs is None:
+            ncoeffs = mfcc_flat.shape[1]
+        arr = (C.c_void_p * len(self.ctxs))(*[c.h for c in self.ctxs])
+        h = C.c_void_p()
+        lib = self.ctxs[0].lib
+        self.ctxs[0].check(lib.ss_dict_create_sharded(arr, len(self.ctxs), _ptr(mfcc_flat), _ptr(off), off.shape[0] - 1, int(ncoeffs), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctxs[0].h:
+            self.ctxs[0].lib.ss_sharded_dict_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.ctxs[0].lib.ss_sharded_dict_len(self.h))
+
+    def match(self, q_flat, q_frame_offsets, mode=SS_DTW, k=1, targets=None):
+        q = np.ascontiguousarray(q_flat, dtype=np.float64)
+        qo = np.ascontiguousarray(q_frame_offsets, dtype=np.uint64)
+        nq = qo.shape[0] - 1
+        idx = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float64)
+        t = np.ascontiguousarray(targets, dtype=np.float64) if targets is not None else None
+        lib = self.ctxs[0].lib
+        self.ctxs[0].check(lib.ss_sharded_dict_match(self.h, _ptr(q), _ptr(qo), nq, int(mode), _ptr(t), int(k), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+
 class DeviceQueries:
     """ss_queries: a prepared query batch resident in HBM."""
 

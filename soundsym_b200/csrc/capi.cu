@@ -28,6 +28,48 @@ static int check_offsets(ss_ctx* ctx, const uint64_t* off, size_t n, const char*
     return SS_OK;
 }
 
+// host-side bookkeeping of a (re)filled batch: offsets rebased to 0, lengths, cached layouts dropped
+int queries_prepare(ss_queries* q, const uint64_t* q_frame_offsets, size_t nq) {
+    q->nq = nq;
+    q->nonempty = 0;
+    q->max_len = 0;
+    q->lane_built = false;
+    q->cos_built = false;
+    q->tc_built = false;
+    q->tc_grouped = false;
+    q->h_off.resize(nq + 1);
+    const uint64_t base = nq ? q_frame_offsets[0] : 0;
+    q->h_off[0] = 0;
+    for (size_t i = 0; i < nq; i++) {
+        q->h_off[i + 1] = q_frame_offsets[i + 1] - base;
+        q->nonempty += q_frame_offsets[i + 1] > q_frame_offsets[i];
+        q->max_len = std::max<uint32_t>(q->max_len, (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, q_frame_offsets[i + 1] - q_frame_offsets[i]));
+    }
+    q->total_frames = q->h_off[nq];
+    return SS_OK;
+}
+
+// (re)fills a query batch in place: device buffers are grow-only, so a reused handle does no cudaMalloc / cudaFree
+int queries_fill(ss_queries* q, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq) {
+    ss_ctx* ctx = q->ctx;
+    SS_TRY(queries_prepare(q, q_frame_offsets, nq));
+    const uint64_t base = nq ? q_frame_offsets[0] : 0;
+    // the frames start crossing PCIe first; the length-sorted grouping of the batch (host work) overlaps that copy
+    SS_TRY(upload(ctx, q->d_mfcc, q_mfcc ? q_mfcc + base * q->c : nullptr, (size_t)q->total_frames * q->c));
+    SS_TRY(upload(ctx, q->d_off, q->h_off.data(), nq + 1));
+    SS_TRY(dtw_tc_queries_group(q));
+    return SS_OK;
+}
+
+int queries_check(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs) {
+    if (ncoeffs < 1 || ncoeffs > SS_MAX_NCOEFFS) return set_error(ctx, SS_ERR_INVALID, "ncoeffs must be in 1..%d (got %d)", SS_MAX_NCOEFFS, ncoeffs);
+    if (nq > 0x7FFFFFF0ull) return set_error(ctx, SS_ERR_INVALID, "too many queries");
+    SS_TRY(check_offsets(ctx, q_frame_offsets, nq, "queries"));
+    if (nq && q_frame_offsets[nq] > q_frame_offsets[0] && !q_mfcc) return set_error(ctx, SS_ERR_INVALID, "q_mfcc is NULL");
+    return SS_OK;
+}
+
+
 }  // namespace ss
 
 using namespace ss;
@@ -156,40 +198,6 @@ static bool finished(const ss_dict* dc) {
 uint64_t ss_dict_last_tc_fallback(const ss_dict* d) { return finished(d) ? d->last_tc_fallback : ~0ull; }
 uint64_t ss_dict_last_exhaustive(const ss_dict* d) { return finished(d) ? d->last_exhaustive : ~0ull; }
 uint64_t ss_dict_last_uncertified(const ss_dict* d) { return finished(d) ? d->last_uncertified : ~0ull; }
-
-// (re)fills a query batch in place: device buffers are grow-only, so a reused handle does no cudaMalloc / cudaFree
-static int queries_fill(ss_queries* q, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq) {
-    ss_ctx* ctx = q->ctx;
-    q->nq = nq;
-    q->nonempty = 0;
-    q->max_len = 0;
-    q->lane_built = false;
-    q->cos_built = false;
-    q->tc_built = false;
-    q->tc_grouped = false;
-    q->h_off.resize(nq + 1);
-    const uint64_t base = nq ? q_frame_offsets[0] : 0;
-    q->h_off[0] = 0;
-    for (size_t i = 0; i < nq; i++) {
-        q->h_off[i + 1] = q_frame_offsets[i + 1] - base;
-        q->nonempty += q_frame_offsets[i + 1] > q_frame_offsets[i];
-        q->max_len = std::max<uint32_t>(q->max_len, (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, q_frame_offsets[i + 1] - q_frame_offsets[i]));
-    }
-    q->total_frames = q->h_off[nq];
-    // the frames start crossing PCIe first; the length-sorted grouping of the batch (host work) overlaps that copy
-    SS_TRY(upload(ctx, q->d_mfcc, q_mfcc ? q_mfcc + base * q->c : nullptr, (size_t)q->total_frames * q->c));
-    SS_TRY(upload(ctx, q->d_off, q->h_off.data(), nq + 1));
-    SS_TRY(dtw_tc_queries_group(q));
-    return SS_OK;
-}
-
-static int queries_check(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs) {
-    if (ncoeffs < 1 || ncoeffs > SS_MAX_NCOEFFS) return set_error(ctx, SS_ERR_INVALID, "ncoeffs must be in 1..%d (got %d)", SS_MAX_NCOEFFS, ncoeffs);
-    if (nq > 0x7FFFFFF0ull) return set_error(ctx, SS_ERR_INVALID, "too many queries");
-    SS_TRY(check_offsets(ctx, q_frame_offsets, nq, "queries"));
-    if (nq && q_frame_offsets[nq] > q_frame_offsets[0] && !q_mfcc) return set_error(ctx, SS_ERR_INVALID, "q_mfcc is NULL");
-    return SS_OK;
-}
 
 int ss_queries_create(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs, ss_queries** out) {
     if (!ctx) return set_error(nullptr, SS_ERR_INVALID, "ctx is NULL");

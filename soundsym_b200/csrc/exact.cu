@@ -176,6 +176,13 @@ __global__ void k_fill_result(uint32_t* __restrict__ idx, double* __restrict__ d
     }
 }
 
+int fill_result(ss_ctx* ctx, uint32_t* d_idx, double* d_dist, size_t n) {
+    if (!n) return SS_OK;
+    k_fill_result<<<ceil_div((long long)n, 256), 256, 0, ctx->stream>>>(d_idx, d_dist, n, 0xFFFFFFFFu, kInf);
+    SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+
 int cosine_dict_build(ss_dict* d) {
     ss_ctx* ctx = d->ctx;
     SS_CUDA(ctx, d->d_norm.reserve(std::max<size_t>(d->nseg, 1)));
@@ -363,10 +370,15 @@ k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ dof
 // ---------------------------------------------------------------------------------------------------------------
 // The whole refine of one query slot by ONE warp (sequences of <= 32 frames on both sides): the k best candidates by scan
 // distance unconditionally, the other kp - k only if the scan's error bound cannot rule them out against the k-th exact
-// distance, then the (distance, index) sort, the top-k store and the certification - what k_dtw_rescore_warp (twice) and
-// k_dtw_finalize do in three launches, with the same arithmetic per pair (warp_dtw_exact is k_dtw_rescore_warp's body).
+// distance, then the (distance, index) sort, the top-k store and the certification - what k_dtw_rescore (twice) and
+// k_dtw_finalize do in three launches for longer sequences, with the same arithmetic per cell. Lane j owns dictionary column
+// j; the pair's local costs go to shared memory first (39 f64 operations per cell on 32 busy lanes), then the recurrence runs
+// as an anti-diagonal wavefront: at step t lane j computes cell (t - j, j) from its own previous value (up), its left
+// neighbour's (one 64-bit shuffle) and the one it received a step earlier (diag).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_dtw_exact(const double* __restrict__ a, int la, const double* __restrict__ b, int lb, int c, double* cst,
+// `sa` holds the query's frames (staged once per slot, coalesced); lane j keeps dictionary frame j in registers (its 13 loads
+// are issued back to back: one memory latency per pair). cst = the pair's local costs, [row][lane].
+__device__ __forceinline__ double warp_dtw_exact(const double* __restrict__ sa, int la, const double* __restrict__ b, int lb, int c, double* cst,
                                                  int lane) {
     double br[SS_MAX_NCOEFFS];
 #pragma unroll
@@ -377,7 +389,7 @@ __device__ __forceinline__ double warp_dtw_exact(const double* __restrict__ a, i
 #pragma unroll
         for (int k = 0; k < SS_MAX_NCOEFFS; k++)
             if (k < c) {
-                const double dlt = a[(size_t)i * c + k] - br[k];
+                const double dlt = sa[i * c + k] - br[k];
                 cost = cost + dlt * dlt;
             }
         cst[i * 32 + lane] = cost;
@@ -412,6 +424,7 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
                   uint8_t* __restrict__ uncert_flag, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
                   unsigned long long* __restrict__ counters) {
     __shared__ double scost[4][32 * 32];
+    __shared__ double squery[4][32 * SS_MAX_NCOEFFS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t slot = blockIdx.x * 4 + warp;
     if (slot >= nslots) return;  // warp-uniform from here on
@@ -423,6 +436,8 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
     const double nb = (double)max_nb[0];
     const double* a = qmfcc + qoff[qid] * c;
     const int la = (int)(qoff[qid + 1] - qoff[qid]);
+    for (int e = lane; e < la * c; e += 32) squery[warp][e] = a[e];  // the query's frames: one coalesced pass (la <= 32)
+    __syncwarp();
     double my_exact = kInf, kth = 0.0;
     unsigned extra = 0;
     for (int s = 0; s < kp; s++) {
@@ -436,7 +451,7 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
             if (scan_lower_bound(adist, na, nb, eps, bound_mode) > kth) continue;  // provably outside the top-k
             extra++;
         }
-        const double e = warp_dtw_exact(a, la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, scost[warp], lane);
+        const double e = warp_dtw_exact(squery[warp], la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, scost[warp], lane);
         if (lane == s) my_exact = e;
         if (s < k) kth = fmax(kth, e < kInf ? e : kInf);
     }

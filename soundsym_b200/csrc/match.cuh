@@ -151,6 +151,10 @@ int dtw_tc_queries_group(ss_queries* q);  // length-sorted groups of 128 for the
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist);
 int dtw_match_finish(ss_dict* d);
 int dtw_tc_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale);
+int queries_check(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs);  // capi.cu
+int queries_prepare(ss_queries* q, const uint64_t* q_frame_offsets, size_t nq);
+int queries_fill(ss_queries* q, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq);
+int fill_result(ss_ctx* ctx, uint32_t* d_idx, double* d_dist, size_t n);  // (inf, 0xFFFFFFFF) rows (exact.cu)
 int cosine_dict_build(ss_dict* d);    // per-segment norms (cosine.cu)
 int cosine_queries_build(ss_queries* q);
 int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_t* d_out_idx, double* d_out_dist);
