@@ -245,6 +245,14 @@ int ss_sharded_dict_nshards(const ss_sharded_dict* dict);
  *              query longer than 32 frames, values outside the fp16 range). */
 int ss_dict_debug_tc_scan(ss_dict* dict, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan,
                           double* out_mu, float* out_scale);
+/* the same for the packed-half scan (fp16 products with an F16 accumulator, DP in half2: the default first stage); out_s = its
+ * power-of-two cost scale S (the operands are A = S [-2 a~, s, s, rd(|a~|^2 / s)], the scan value is D16 / (S (Lq + Ld))) */
+int ss_dict_debug_h2_scan(ss_dict* dict, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan,
+                          double* out_mu, float* out_scale, float* out_s);
+/* test / A-B hook: which filter stage an SS_DTW match STARTS with when all of them apply. 0 (default) = packed-half tensor-core
+ * scan, 1 = fp32-DP tensor-core scan, 2 = fp32 CUDA-core scan. The results are identical by construction (every stage is
+ * followed by the f64 refine + certification); only the speed differs. */
+int ss_dict_set_scan(ss_dict* dict, int first_stage);
 
 /* ss_resynth   SoundSequence::clone_from_dictionary sample assembly (src/sound.rs:451-472) + to_sound (:475-483):
  *              for target segment t copy min(len) samples of dictionary sound match_idx[t] and zero-pad to

@@ -260,6 +260,21 @@ class DeviceDictionary:
         self.ctx.check(self.ctx.lib.ss_dict_debug_tc_scan(self.h, _ptr(q), _ptr(qo), nq, _ptr(scan), _ptr(mu), C.byref(scale)))
         return scan, mu, float(scale.value)
 
+    def debug_h2_scan(self, q_flat, q_frame_offsets):
+        """ss_dict_debug_h2_scan: raw packed-half scan distance of every pair -> (scan f32 [nq, nseg], mean frame, norm scale s, cost scale S)."""
+        q = np.ascontiguousarray(q_flat, dtype=np.float64)
+        qo = np.ascontiguousarray(q_frame_offsets, dtype=np.uint64)
+        nq = qo.shape[0] - 1
+        scan = np.empty((nq, len(self)), dtype=np.float32)
+        mu = np.zeros(16, dtype=np.float64)
+        scale, s = C.c_float(0.0), C.c_float(0.0)
+        self.ctx.check(self.ctx.lib.ss_dict_debug_h2_scan(self.h, _ptr(q), _ptr(qo), nq, _ptr(scan), _ptr(mu), C.byref(scale), C.byref(s)))
+        return scan, mu, float(scale.value), float(s.value)
+
+    def set_scan(self, first_stage):
+        """ss_dict_set_scan: 0 = packed-half tensor-core scan first (default), 1 = fp32-DP tensor-core scan, 2 = fp32 CUDA-core scan"""
+        self.ctx.check(self.ctx.lib.ss_dict_set_scan(self.h, int(first_stage)))
+
     @property
     def last_work(self):
         return int(self.ctx.lib.ss_dict_last_work(self.h))

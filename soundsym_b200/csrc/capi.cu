@@ -36,6 +36,7 @@ int queries_prepare(ss_queries* q, const uint64_t* q_frame_offsets, size_t nq) {
     q->lane_built = false;
     q->cos_built = false;
     q->tc_built = false;
+    q->h2_built = false;
     q->tc_grouped = false;
     q->h_off.resize(nq + 1);
     const uint64_t base = nq ? q_frame_offsets[0] : 0;
@@ -165,6 +166,7 @@ int ss_dict_create(ss_ctx* ctx, const double* mfcc_flat, const uint64_t* frame_o
     if (rc == SS_OK) rc = cosine_dict_build(d);
     if (rc == SS_OK) rc = dtw_dict_build(d);
     if (rc == SS_OK) rc = dtw_tc_dict_build(d);
+    if (rc == SS_OK) rc = dtw_h2_dict_build(d);
     if (rc == SS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_error(ctx, SS_ERR_CUDA, "dictionary build failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != SS_OK) {
         delete d;
@@ -224,6 +226,7 @@ int ss_queries_invalidate(ss_queries* q) {
     q->lane_built = false;
     q->cos_built = false;
     q->tc_built = false;
+    q->h2_built = false;
     return SS_OK;
 }
 
@@ -304,8 +307,31 @@ int ss_dict_match(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offs
     return rc;
 }
 
+int ss_dict_set_scan(ss_dict* d, int first_stage) {
+    if (!d) return set_error(nullptr, SS_ERR_INVALID, "dict is NULL");
+    if (first_stage < 0 || first_stage > 2) return set_error(d->ctx, SS_ERR_INVALID, "first_stage must be 0, 1 or 2");
+    SS_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
+    SS_TRY(dtw_match_finish(d));
+    d->scan_pref = first_stage;
+    return SS_OK;
+}
+
+static int debug_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan, double* out_mu,
+                      float* out_scale, float* out_s);
+
 int ss_dict_debug_tc_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan, double* out_mu,
                           float* out_scale) {
+    return debug_scan(d, q_mfcc, q_frame_offsets, nq, out_scan, out_mu, out_scale, nullptr);
+}
+int ss_dict_debug_h2_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan, double* out_mu,
+                          float* out_scale, float* out_s) {
+    if (!out_s) return set_error(d ? d->ctx : nullptr, SS_ERR_INVALID, "out_s is NULL");
+    return debug_scan(d, q_mfcc, q_frame_offsets, nq, out_scan, out_mu, out_scale, out_s);
+}
+
+// out_s == NULL: the fp32-DP tensor-core scan; else the packed-half scan (and its cost scale S)
+static int debug_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan, double* out_mu,
+                      float* out_scale, float* out_s) {
     if (!d) return set_error(nullptr, SS_ERR_INVALID, "dict is NULL");
     ss_ctx* ctx = d->ctx;
     if (!out_scan || !out_mu || !out_scale) return set_error(ctx, SS_ERR_INVALID, "output pointers are NULL");
@@ -322,7 +348,7 @@ int ss_dict_debug_tc_scan(ss_dict* d, const double* q_mfcc, const uint64_t* q_fr
     SS_CUDA(ctx, cudaMemsetAsync(d_out.p, 0xFF, nslots * nseg * sizeof(float), ctx->stream));  // NaN = not evaluated
     std::vector<uint32_t> slot_qid;
     SS_TRY(dtw_match_finish(d));
-    int rc = dtw_tc_debug_scan(d, &q, d_out.p, &slot_qid, out_mu, out_scale);
+    int rc = out_s ? dtw_h2_debug_scan(d, &q, d_out.p, &slot_qid, out_mu, out_scale, out_s) : dtw_tc_debug_scan(d, &q, d_out.p, &slot_qid, out_mu, out_scale);
     if (rc != SS_OK) {
         cudaStreamSynchronize(ctx->stream);
         return rc;

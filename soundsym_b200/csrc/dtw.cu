@@ -382,6 +382,7 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used);
+int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used);
 int dtw_exhaustive_match(ss_dict* d, ss_queries* q, int k, const std::vector<uint32_t>& subset, uint32_t* d_out_idx, double* d_out_dist);
 }
 
@@ -538,7 +539,8 @@ static int post_counters(ss_dict* d) {
 }
 
 // Three stages, each only for the queries the previous one could not certify:
-//   1. tensor-core scan (fp16 products)          dtw_tc.cu     bound: triangle inequality on the rounded frames
+//   1. tensor-core scan (fp16 products)          dtw_h2.cu (packed-half DP) or dtw_tc.cu (fp32 DP)
+//                                                              bound: triangle inequality on the rounded frames
 //   2. fp32 scan                                 k_dtw_scan    bound: 4e-6 (max|a|^2 + max|b|^2)
 //   3. exhaustive f64 DTW against every segment  exact.cu      exact by construction
 // Stage 3 only triggers when more than KP segments are closer to each other than the fp32 scan can resolve (e.g. many
@@ -558,7 +560,8 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
     d->last_exhaustive = 0;
     d->last_uncertified = 0;
     bool used = false;
-    SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
+    SS_TRY(dtw_h2_match_dev(d, q, k, d_out_idx, d_out_dist, &used));                 // packed-half tensor-core scan
+    if (!used) SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));      // fp32-DP tensor-core scan
     if (!used) SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr));
     SS_TRY(post_counters(d));
     d->pending.active = true;

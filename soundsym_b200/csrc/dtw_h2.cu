@@ -1,0 +1,708 @@
+// dtw_h2.cu — the FIRST filter stage of the DTW matcher when every segment and query has <= 32 frames: the tensor-core scan
+// with the DP recurrence in PACKED HALF precision, two dictionary segments per register.
+//
+// Why: the fp32 scan (dtw_tc.cu) is bound by CUDA-core issue of one FMNMX3 + one FADD per cell; FMNMX3 issues at 16 lanes /
+// clk / SMSP, so 64 cells / clk / SM is its hard ceiling (47.3 measured for the band alone, tools/microbench_band2.cu).
+// VHMNMX (three-input min on half2) and HADD2 issue at the same instruction rate and carry two values each: the same band on
+// half2 registers reaches 80-86 cells / clk / SM. The tensor core delivers the local costs already in that form: with an F16
+// accumulator (instruction-descriptor c_format = 0) tcgen05.mma writes rn_f16(exact sum of the 16 products) - measured
+// bit for bit on 16 384 operand pairs shaped like ours, tools/microbench_f16acc.cu - one 16-bit value per TMEM column, and
+// tcgen05.ld ... .pack::16b returns two ADJACENT columns in one register. The dictionary tiles therefore interleave the
+// columns of two segments (column 2t = frame t of the first, 2t + 1 = frame t of the second), so a register holds the same
+// cell of two independent DTW problems and one VHMNMX + one HADD2 advance both.
+//
+// What the scan value means (the certification in exact.cu, bound_mode 2, rests on exactly this):
+//   operands  A_i[m, :] = S [-2 a~ (13), s, s, rd(|a~|^2 / s)],  B[n, :] = [b~ (13), hi, lo, s]  (a~, b~ = fp16-rounded centred
+//             frames, S a power of two that keeps path sums inside the fp16 range), so the exact contraction is S c'(i, j) with
+//             c' <= c~ = |a~ - b~|^2 (by at most 2^-10 |a~|^2, from the round-down of |a~|^2);
+//   cost      h(i, j) = rn16(S c')                         <= S c~ (1 + u) + eta16,        u = 2^-11
+//   DP        D16(i, j) = rn16(h + min3(...))              <= (h + min3)(1 + u) + eta16     (min is exact, rn is monotone)
+//   so along the optimal path of the rounded-frame DTW (<= Lq + Ld - 1 cells):  D16 <= S DTW~ (1 + u)^(Lq + Ld) + (Lq + Ld) 2 eta16,
+//   i.e.  DTW~ / (Lq + Ld) >= [ D16 / (S (Lq + Ld)) - 2 eta16 / S ] (1 + u)^-(Lq + Ld): a pair dropped from a candidate list whose
+//   worst entry is w has rounded-frame distance >= (w - eta)(1 + u)^-(Lq + 32). eta16 = 2^-25 covers fp16 subnormals (cost
+//   operands scaled by S, running sums); an overflow to +inf only happens above 65504 / S and is capped in the bound.
+//
+// Geometry: 128 queries per CTA (= MMA M = TMEM lanes), MMA N = 128 TMEM columns per row = 2 slots x 64 columns, K = 16,
+// two rows per pipeline step, two 256-column TMEM buffers. 8 DP warps (warp w: lane quadrant w % 4, slot w / 4) + 1 producer
+// warp (TMEM allocation, bulk-TMA of the A block and the B-tile ring, MMA issue). A DP thread owns one query x one slot: NB
+// bands of 2 interleaved segments each - NB = 1 (segments of 17..32 frames), 2 (9..16) or 4 (<= 8): every step is
+// 2 rows x 64 columns = 128 cells per thread whatever the segment length, so the hand-off cost per cell is the same for
+// short and long segments (the fp32 scan's paired tiles spent 4.5 instructions per cell on short segments).
+#include <algorithm>
+#include <atomic>
+
+#include "match.cuh"
+#include "tc_common.cuh"
+
+namespace ss {
+
+int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, double eps,
+                         const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
+                         bool fill, uint32_t* d_out_idx, double* d_out_dist);
+
+constexpr int kH2Slots = 2;
+constexpr int kH2SlotCols = 64;                       // TMEM columns per slot and row
+constexpr int kH2DpWarps = 4 * kH2Slots;              // 8
+constexpr int kH2DpThreads = kH2DpWarps * 32;         // 256
+constexpr int kH2Threads = (kH2DpWarps + 1) * 32;     // 288
+constexpr int kH2DescInt4 = 3;                        // per (tile, slot): {seg 0..3}, {seg 4..7}, {len 0..3 bytes, len 4..7 bytes, ng, 0}
+
+struct H2Params {
+    const unsigned char* a_blocks;
+    const uint64_t* group_off;
+    const uint32_t* group_len;   // longest | shortest << 16 query length of each group of 128
+    const uint32_t* slot_len;    // per query slot: its own length (0 = padding lane)
+    uint32_t ngroups;
+    const unsigned char* tiles;  // ntiles x 4 KB, K-major no-swizzle, interleaved segment columns
+    const int4* desc;            // [ntiles][2 slots][3]
+    const uint32_t* slice_tile;  // all slices + 1
+    uint32_t nslices, slice_begin;
+    unsigned long long* partial;  // [nslices][ngroups * 128][KP]
+    uint32_t max_len;
+    float inv_s;                  // 1 / S
+    float* dbg;                   // DBG instantiation only: [ngroups * 128][dbg_nseg]
+    uint32_t dbg_nseg;
+};
+
+// ---- packed TMEM loads: N registers <- 2 N adjacent columns ---------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void h2_ld(uint32_t taddr, __half2* v);
+template <>
+__device__ __forceinline__ void h2_ld<4>(uint32_t taddr, __half2* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.pack::16b.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<__half2*>(&r[i]);
+}
+template <>
+__device__ __forceinline__ void h2_ld<8>(uint32_t taddr, __half2* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = *reinterpret_cast<__half2*>(&r[i]);
+}
+template <>
+__device__ __forceinline__ void h2_ld<16>(uint32_t taddr, __half2* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = *reinterpret_cast<__half2*>(&r[i]);
+}
+// the 4 NG registers (8 NG columns) of one band row, as 16 / 8 / 4-register pieces
+template <int NG>
+__device__ __forceinline__ void h2_ld_row(uint32_t taddr, __half2 (&v)[4 * NG]) {
+    constexpr int N = 4 * NG;
+    int done = 0;
+    if constexpr (N >= 32) {
+        h2_ld<16>(taddr, v);
+        h2_ld<16>(taddr + 32, v + 16);
+        done = 32;
+    } else if constexpr (N >= 16) {
+        h2_ld<16>(taddr, v);
+        done = 16;
+    }
+    if constexpr ((N & 8) != 0) {
+        h2_ld<8>(taddr + 2 * done, v + done);
+        done += 8;
+    }
+    if constexpr ((N & 4) != 0) h2_ld<4>(taddr + 2 * done, v + done);
+}
+
+__device__ __forceinline__ __half2 h2_min3(__half2 a, __half2 b, __half2 c) { return __hmin2(__hmin2(a, b), c); }  // one VHMNMX
+__device__ __forceinline__ __half2 h2_inf() {
+    const uint32_t bits = 0x7C007C00u;
+    return *reinterpret_cast<const __half2*>(&bits);
+}
+__device__ __forceinline__ __half2 h2_zero() {
+    const uint32_t bits = 0u;
+    return *reinterpret_cast<const __half2*>(&bits);
+}
+// low half of a, high half of b
+__device__ __forceinline__ __half2 h2_combine(__half2 a, __half2 b) {
+    const uint32_t r = __byte_perm(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), 0x7610);
+    return *reinterpret_cast<const __half2*>(&r);
+}
+__device__ __forceinline__ __half2 h2_pick4(const __half2* v, int r) { return r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3])); }
+
+// TWO rows (i, i + 1) of one band (two interleaved segments), row state in place: per half2 cell VHMNMX + HADD2.
+// c0l receives row i's values of the last 4-column group (row i + 1's stay in d[4 NG - 4 ..]).
+template <int NG>
+__device__ __forceinline__ void h2_band(const __half2 (&tm0)[4 * NG], const __half2 (&tm1)[4 * NG], __half2 (&d)[4 * NG], __half2 dinit, __half2 (&c0l)[4]) {
+    __half2 left0 = h2_inf(), diag0 = dinit, left1 = h2_inf();
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const __half2 up0 = d[j];
+        const __half2 c0 = __hadd2(tm0[j], h2_min3(left0, up0, diag0));
+        const __half2 c1 = __hadd2(tm1[j], h2_min3(left1, c0, left0));  // up = D(i, j), diag = D(i, j-1)
+        diag0 = up0;
+        left0 = c0;
+        left1 = c1;
+        d[j] = c1;
+        if (j >= 4 * (NG - 1)) c0l[j - 4 * (NG - 1)] = c0;
+    }
+}
+template <int NG>
+__device__ __forceinline__ void h2_band_row(const __half2 (&tm)[4 * NG], __half2 (&d)[4 * NG], __half2 dinit) {
+    __half2 left = h2_inf(), diag = dinit;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const __half2 up = d[j];
+        const __half2 cur = __hadd2(tm[j], h2_min3(left, up, diag));
+        diag = up;
+        left = cur;
+        d[j] = cur;
+    }
+}
+
+// one pipeline step for one thread: wait for the step's MMAs, pull the NB bands' columns of both rows, hand the buffer back,
+// advance the bands
+template <int NB, int NG>
+__device__ __forceinline__ void h2_step2(TcCursor& cur, __half2 (&d)[NB][4 * NG], __half2 dinit, __half2 (&c0l)[NB][4]) {
+    constexpr int kBandCols = kH2SlotCols / NB;
+    cur.wait();
+    const uint32_t taddr = cur.taddr;
+    __half2 tm0[NB][4 * NG], tm1[NB][4 * NG];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        h2_ld_row<NG>(taddr + b * kBandCols, tm0[b]);
+        h2_ld_row<NG>(taddr + kTcN + b * kBandCols, tm1[b]);
+    }
+    tc_wait_ld();
+    cur.release();
+#pragma unroll
+    for (int b = 0; b < NB; b++) h2_band<NG>(tm0[b], tm1[b], d[b], dinit, c0l[b]);
+}
+
+// One dictionary tile for one thread (= one query x one slot = 2 NB segments). ra / rb: position of column len - 1 inside the
+// last 4-column group, for the band's first (low halves) and second (high halves) segment. res[b] = D(Lm - 1, len - 1) of both.
+template <int NB, int NG>
+__device__ __forceinline__ void h2_tile(uint32_t L, uint32_t lmin, uint32_t Lm, const int (&ra)[NB], const int (&rb)[NB], TcCursor& cur,
+                                        __half2 (&res)[NB]) {
+    __half2 d[NB][4 * NG];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+#pragma unroll
+        for (int j = 0; j < 4 * NG; j++) d[b][j] = h2_inf();
+        res[b] = h2_inf();
+    }
+    __half2 dinit = h2_zero();
+    const uint32_t nfull = L >> 1;                       // steps that carry two rows
+    const uint32_t ncap = min((lmin - 1) >> 1, nfull);   // steps before any query of the group can end
+    uint32_t st = 0;
+    // steps [0, ncap): no query of the group ends; two per iteration on buffers 0, 1 with loop-invariant addresses
+    if (st < ncap && cur.buf) {
+        __half2 c0l[NB][4];
+        h2_step2<NB, NG>(cur, d, dinit, c0l);
+        dinit = h2_inf();
+        st++;
+    }
+    if (st + 2 <= ncap) {
+        const uint32_t full0 = cur.full, taddr0 = cur.taddr;
+        uint32_t par = cur.par;
+#pragma unroll 1
+        for (; st + 2 <= ncap; st += 2) {
+            __half2 c0l[NB][4];
+            TcCursor c0 = {0u, par, full0, taddr0, cur.full_sum, cur.taddr_sum};
+            h2_step2<NB, NG>(c0, d, dinit, c0l);
+            TcCursor c1 = {1u, par, full0 + 8u, taddr0 + (uint32_t)kTcBufCols, cur.full_sum, cur.taddr_sum};
+            h2_step2<NB, NG>(c1, d, h2_inf(), c0l);
+            dinit = h2_inf();
+            par ^= 1u;
+        }
+        cur.par = par;
+    }
+    if (st < ncap) {
+        __half2 c0l[NB][4];
+        h2_step2<NB, NG>(cur, d, dinit, c0l);
+        dinit = h2_inf();
+        st++;
+    }
+#pragma unroll 1
+    for (; st < nfull; st++) {  // only the last step or two of a tile: some query of the group can end here
+        __half2 c0l[NB][4];
+        h2_step2<NB, NG>(cur, d, dinit, c0l);
+        dinit = h2_inf();
+        const bool end0 = 2 * st + 1 == Lm, end1 = 2 * st + 2 == Lm;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const __half2 e0 = h2_combine(h2_pick4(c0l[b], ra[b]), h2_pick4(c0l[b], rb[b]));
+            const __half2 e1 = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra[b]), h2_pick4(&d[b][4 * (NG - 1)], rb[b]));
+            res[b] = end0 ? e0 : (end1 ? e1 : res[b]);
+        }
+    }
+    if (L & 1) {  // odd group length: the last step carries one row
+        constexpr int kBandCols = kH2SlotCols / NB;
+        cur.wait();
+        __half2 tm0[NB][4 * NG];
+#pragma unroll
+        for (int b = 0; b < NB; b++) h2_ld_row<NG>(cur.taddr + b * kBandCols, tm0[b]);
+        tc_wait_ld();
+        cur.release();
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            h2_band_row<NG>(tm0[b], d[b], dinit);
+            const __half2 e = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra[b]), h2_pick4(&d[b][4 * (NG - 1)], rb[b]));
+            res[b] = (L == Lm) ? e : res[b];
+        }
+    }
+}
+
+// NB selects the tile kind the launch covers (the dictionary's tiles are sorted: NB = 1 tiles first, then 2, then 4).
+template <int KP, int NB, bool DBG = false>
+__global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    // [A tiles: max_len x 4 KB][B ring: 4 x 4 KB][barriers][candidate lists], 128-byte aligned
+    unsigned char* smem = smem_raw + ((128u - (s32(smem_raw) & 127u)) & 127u);
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + (size_t)p.max_len * kTcATileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcBTileBytes);
+    uint64_t* a_full = bars;
+    uint64_t* b_full = bars + 1;
+    uint64_t* b_empty = b_full + kTcStages;
+    uint64_t* t_full = bars + 10;
+    uint64_t* t_empty = bars + 12;  // = t_full + 16 bytes (TcCursor::release)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x / p.nslices, slice = p.slice_begin + blockIdx.x % p.nslices;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next tile kind's launch may start filling SMs
+    const uint32_t glen = p.group_len[g];
+    const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;
+    const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
+    const uint32_t ntiles = t1 - t0;
+
+    if (threadIdx.x == 0) {
+        mb_init(a_full, 1);
+        for (int s = 0; s < kTcStages; s++) mb_init(&b_full[s], 1), mb_init(&b_empty[s], 1);
+        for (int s = 0; s < 2; s++) mb_init(&t_full[s], 1), mb_init(&t_empty[s], kH2DpWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kH2DpWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == kH2DpWarps) {
+        if (lane == 0 && ntiles) {
+            // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------------
+            const uint32_t bars_s = s32(bars), sA_s = s32(sA), sB_s = s32(sB);
+            const uint32_t a_full_s = bars_s, b_full_s = bars_s + 8, b_empty_s = bars_s + 8 + 8 * kTcStages, t_full_s = bars_s + 80,
+                           t_empty_s = bars_s + 96;
+            mbs_expect_tx(a_full_s, L * kTcATileBytes);
+            tmas_g2s(sA_s, p.a_blocks + p.group_off[g], L * kTcATileBytes, a_full_s);
+            const unsigned char* tile_src = p.tiles + (size_t)t0 * kTcBTileBytes;
+            for (uint32_t n = 0; n < ntiles && n < (uint32_t)kTcStages; n++) {
+                mbs_expect_tx(b_full_s + 8 * n, kTcBTileBytes);
+                tmas_g2s(sB_s + n * kTcBTileBytes, tile_src + (size_t)n * kTcBTileBytes, kTcBTileBytes, b_full_s + 8 * n);
+            }
+            tile_src += (size_t)kTcStages * kTcBTileBytes;
+            mbs_wait_sleep(a_full_s, 0);
+            // f16 x f16 -> F16 accumulator (c_format = 0), K-major both, N = 128, M = 128
+            const uint32_t idesc = (0u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+            const uint64_t adesc0 = tc_smem_desc_s<kTcM>(sA_s);
+            uint32_t cnt = 0, stage = 0, sphase = 0;
+            for (uint32_t n = 0; n < ntiles; n++) {
+                mbs_wait_sleep(b_full_s + 8 * stage, sphase);
+                const uint64_t bdesc = tc_smem_desc_s<kTcN>(sB_s + stage * kTcBTileBytes);
+                uint64_t adesc = adesc0;
+                for (uint32_t row = 0; row < L; row += 2, cnt++) {
+                    const uint32_t buf = cnt & 1;
+                    if (cnt >= 2) mbs_wait_sleep(t_empty_s + 8 * buf, ((cnt >> 1) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tm = tmem_base + buf * kTcBufCols;
+                    tc_mma_f16(tm, adesc, bdesc, idesc);
+                    if (row + 1 < L) tc_mma_f16(tm + kTcN, adesc + (kTcATileBytes >> 4), bdesc, idesc);
+                    tcs_commit(t_full_s + 8 * buf);
+                    adesc += 2 * (kTcATileBytes >> 4);
+                }
+                tcs_commit(b_empty_s + 8 * stage);
+                if (n + kTcStages < ntiles) {
+                    mbs_wait_sleep(b_empty_s + 8 * stage, sphase);
+                    mbs_expect_tx(b_full_s + 8 * stage, kTcBTileBytes);
+                    tmas_g2s(sB_s + stage * kTcBTileBytes, tile_src, kTcBTileBytes, b_full_s + 8 * stage);
+                    tile_src += kTcBTileBytes;
+                }
+                if (++stage == (uint32_t)kTcStages) stage = 0, sphase ^= 1;
+            }
+        }
+    } else {
+        // ---- DP warps ---------------------------------------------------------------------------------------------------
+        const int q = warp & 3, slot = warp >> 2;
+        const int m = q * 32 + lane;
+        unsigned long long* list = topk + threadIdx.x;  // [KP][256] keys, this thread's column
+#pragma unroll
+        for (int s = 0; s < KP; s++) list[s * kH2DpThreads] = 0xFFFFFFFFFFFFFFFFull;
+        unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * kH2SlotCols;
+        const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
+        TcCursor cur;
+        cur.init(s32(t_full), lane_addr);
+        for (uint32_t n = 0; n < ntiles; n++) {
+            const int4* dp = p.desc + ((size_t)(t0 + n) * kH2Slots + slot) * kH2DescInt4;
+            const int4 sa = __ldg(dp), sb = __ldg(dp + 1), sc = __ldg(dp + 2);
+            const int segs[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            const int ng = sc.z;
+            int lens[2 * NB], ra[NB], rb[NB];
+#pragma unroll
+            for (int e = 0; e < 2 * NB; e++) lens[e] = (int)((((e < 4) ? (uint32_t)sc.x : (uint32_t)sc.y) >> (8 * (e & 3))) & 0xFFu);
+#pragma unroll
+            for (int b = 0; b < NB; b++) ra[b] = (lens[2 * b] - 1) & 3, rb[b] = (lens[2 * b + 1] - 1) & 3;
+            __half2 res[NB];
+            // every segment of a tile has the same number of 4-column groups: straight-line code over 4 NG registers per band
+            if constexpr (NB == 1) {
+                switch (ng) {
+                    case 5: h2_tile<1, 5>(L, lmin, Lm, ra, rb, cur, res); break;
+                    case 6: h2_tile<1, 6>(L, lmin, Lm, ra, rb, cur, res); break;
+                    case 7: h2_tile<1, 7>(L, lmin, Lm, ra, rb, cur, res); break;
+                    default: h2_tile<1, 8>(L, lmin, Lm, ra, rb, cur, res); break;
+                }
+            } else if constexpr (NB == 2) {
+                if (ng == 3) h2_tile<2, 3>(L, lmin, Lm, ra, rb, cur, res);
+                else h2_tile<2, 4>(L, lmin, Lm, ra, rb, cur, res);
+            } else {
+                if (ng == 1) h2_tile<4, 1>(L, lmin, Lm, ra, rb, cur, res);
+                else h2_tile<4, 2>(L, lmin, Lm, ra, rb, cur, res);
+            }
+            if (Lm) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+#pragma unroll
+                    for (int hsel = 0; hsel < 2; hsel++) {
+                        const int e = 2 * b + hsel;
+                        if (segs[e] < 0) continue;
+                        const float v = hsel ? __high2float(res[b]) : __low2float(res[b]);
+                        // D16 / (S (Lq + Ld)); an overflowed path sum stays +inf and is never inserted
+                        const float dist = __fdividef(v * p.inv_s, (float)(Lm + (uint32_t)lens[e]));
+                        tc_insert<KP, kH2DpThreads>(list, worst, dist, (uint32_t)segs[e]);
+                        if constexpr (DBG) p.dbg[(size_t)(g * kTcM + m) * p.dbg_nseg + segs[e]] = dist;
+                    }
+                }
+            }
+        }
+        // the two slots' lists of query m (threads m, m + 128) are merged by the slot-0 thread
+        asm volatile("bar.sync 1, %0;" ::"n"(kH2DpThreads) : "memory");
+        if (slot == 0) {
+            const unsigned long long* other = list + kTcM;
+            for (int s = 0; s < KP; s++) {  // ascending: stop at the first key that does not make the cut
+                const unsigned long long key = other[s * kH2DpThreads];
+                if (key >= worst) break;
+                tc_insert_key<KP, kH2DpThreads>(list, worst, key);
+            }
+            unsigned long long* out = p.partial + ((size_t)slice * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
+#pragma unroll
+            for (int s = 0; s < KP; s++) out[s] = list[s * kH2DpThreads];
+        }
+    }
+    if constexpr (NB != 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // see k_dtw_scan_tc: not complete before the launch ahead is
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kH2DpWarps) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// one thread per (tile, TMEM column n): writes row n of the tile's B operand. Slot = n / 64; inside the slot band = column /
+// (64 / NB), and inside the band column 2 t + w is frame t of the band's segment w.
+__global__ void k_h2_dict_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
+                                const int4* __restrict__ desc, const uint8_t* __restrict__ tile_nb, uint32_t ntiles, float scale,
+                                unsigned char* __restrict__ tiles) {
+    const uint32_t t = blockIdx.x, n = threadIdx.x;  // blockDim = 128
+    if (t >= ntiles) return;
+    const int nb = tile_nb[t];
+    const int slot = (int)n / kH2SlotCols, col = (int)n % kH2SlotCols;
+    const int band_cols = kH2SlotCols / nb;
+    const int e = 2 * (col / band_cols) + (col & 1), j = (col % band_cols) >> 1;
+    const int4* dp = desc + ((size_t)t * kH2Slots + slot) * kH2DescInt4;
+    const int4 sa = dp[0], sb = dp[1], sc = dp[2];
+    const int segs[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const int seg = segs[e];
+    const int len = (int)((((e < 4) ? (uint32_t)sc.x : (uint32_t)sc.y) >> (8 * (e & 3))) & 0xFFu);
+    __align__(16) __half row[kTcK];
+#pragma unroll
+    for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
+    if (seg >= 0 && j < len) {
+        const double* src = mfcc + (off[seg] + j) * c;
+        float nrm = 0.f;
+        for (int k = 0; k < c; k++) {
+            const __half h = __float2half_rn((float)(src[k] - mu[k]));
+            row[k] = h;
+            const float v = __half2float(h);
+            nrm += v * v;
+        }
+        const float sn = nrm * (1.0f / scale);  // s is a power of two: exact
+        const __half hi = __float2half_rn(sn);
+        row[13] = hi;
+        row[14] = __float2half_rn(sn - __half2float(hi));
+        row[15] = __float2half_rn(scale);
+    }
+    unsigned char* base = tiles + (size_t)t * kTcBTileBytes;
+    *reinterpret_cast<uint4*>(base + tc_tile_offset<kTcN>((int)n, 0)) = *reinterpret_cast<const uint4*>(&row[0]);
+    *reinterpret_cast<uint4*>(base + tc_tile_offset<kTcN>((int)n, 8)) = *reinterpret_cast<const uint4*>(&row[8]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+// needs dtw_tc_dict_build to have run (mean frame, norm scale, max norms)
+int dtw_h2_dict_build(ss_dict* d) {
+    ss_ctx* ctx = d->ctx;
+    d->h2_ready = false;
+    if (!d->tc_ready) return SS_OK;
+    std::vector<uint32_t> order;
+    order.reserve(d->nseg);
+    for (size_t s = 0; s < d->nseg; s++)
+        if (d->h_off[s + 1] > d->h_off[s]) order.push_back((uint32_t)s);
+    auto len_of = [&](uint32_t s) { return (int)(d->h_off[s + 1] - d->h_off[s]); };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
+    // tiles: all segments of a tile share ng = ceil(len / 4) (and hence the kind NB: ng 5..8 -> 1 band per thread, 3..4 -> 2,
+    // 1..2 -> 4); a tile holds 2 slots x 2 NB segments. Element e of a slot = band e / 2, half e % 2. Consecutive segments in
+    // length order go to the SAME half-pair first, so the two halves of a register carry nearly equal lengths.
+    std::vector<int4> desc;
+    std::vector<uint8_t> tile_nb;
+    d->h_h2_tile_cost.clear();
+    d->h2_first_tile[0] = 0;
+    int cur_kind = 1;
+    for (size_t o = 0; o < order.size();) {
+        const int ng = (len_of(order[o]) + 3) >> 2;
+        const int nb = ng >= 5 ? 1 : (ng >= 3 ? 2 : 4);
+        while (cur_kind < nb) {  // kinds in launch order 1, 2, 4
+            d->h2_first_tile[cur_kind == 1 ? 1 : 2] = (uint32_t)tile_nb.size();
+            cur_kind *= 2;
+        }
+        const size_t cap = (size_t)kH2Slots * 2 * nb;
+        size_t take = 0;
+        while (take < cap && o + take < order.size() && ((len_of(order[o + take]) + 3) >> 2) == ng) take++;
+        for (int slot = 0; slot < kH2Slots; slot++) {
+            int segs[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+            uint32_t lens[2] = {0, 0};
+            for (int e = 0; e < 2 * nb; e++) {
+                const size_t pos = (size_t)slot * 2 * nb + e;
+                if (pos < take) {
+                    segs[e] = (int)order[o + pos];
+                    lens[e >> 2] |= (uint32_t)len_of(order[o + pos]) << (8 * (e & 3));
+                }
+            }
+            desc.push_back(make_int4(segs[0], segs[1], segs[2], segs[3]));
+            desc.push_back(make_int4(segs[4], segs[5], segs[6], segs[7]));
+            desc.push_back(make_int4((int)lens[0], (int)lens[1], ng, 0));
+        }
+        tile_nb.push_back((uint8_t)nb);
+        d->h_h2_tile_cost.push_back(24u + 16u * (uint32_t)(nb * ng));
+        o += take;
+    }
+    while (cur_kind < 4) {
+        d->h2_first_tile[cur_kind == 1 ? 1 : 2] = (uint32_t)tile_nb.size();
+        cur_kind *= 2;
+    }
+    d->h2_first_tile[3] = (uint32_t)tile_nb.size();
+    const uint32_t ntiles = (uint32_t)tile_nb.size();
+    d->h2_ntiles = ntiles;
+    if (!ntiles) return SS_OK;
+    SS_TRY(upload(ctx, d->d_h2_desc, desc.data(), desc.size()));
+    DevBuf<uint8_t> d_nb;
+    SS_TRY(upload(ctx, d_nb, tile_nb.data(), tile_nb.size()));
+    SS_CUDA(ctx, d->d_h2_tiles.reserve((size_t)ntiles * kTcBTileBytes / 2));
+    k_h2_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_h2_desc.p, d_nb.p, ntiles, d->tc_nb_scale,
+                                                     reinterpret_cast<unsigned char*>(d->d_h2_tiles.p));
+    SS_LAUNCHED(ctx);
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // d_nb is released on return
+    // cost scale S: S |b|^2_max <= 4096, so that a path of 64 typical cells stays far below 65504 (an overflow is not an error:
+    // the pair reads +inf and the bound is capped, see the header)
+    float mx[2] = {0, 0};
+    SS_CUDA(ctx, cudaMemcpy(mx, d->d_tc_max_norm.p, sizeof(mx), cudaMemcpyDeviceToHost));
+    float S = 1.0f;
+    while (S * mx[0] > 4096.f) S *= 0.5f;
+    while (S * mx[0] < 2048.f && S < 64.f) S *= 2.0f;
+    d->h2_s = S;
+    d->h2_bmax = mx[1];
+    d->h2_ready = true;
+    return SS_OK;
+}
+
+static int h2_queries_build(ss_dict* d, ss_queries* q) {
+    ss_ctx* ctx = q->ctx;
+    if (q->h2_built && q->h2_dict_serial == d->tc_serial) return SS_OK;
+    if (!q->tc_grouped) SS_TRY(dtw_tc_queries_group(q));
+    SS_CUDA(ctx, q->d_h2_a.reserve(std::max<uint64_t>(q->tc_a_bytes, 16)));
+    SS_CUDA(ctx, q->d_tc_slot_max_na.reserve(std::max<size_t>((size_t)q->tc_ngroups * kTcM, 1)));
+    SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
+    SS_CUDA(ctx, q->d_tc_max_norm.reserve(1));
+    SS_CUDA(ctx, cudaMemsetAsync(q->d_tc_max_norm.p, 0, sizeof(float), ctx->stream));
+    if (q->tc_ngroups) {
+        SS_CUDA(ctx, cudaMemsetAsync(q->d_tc_slot_max_na.p, 0, (size_t)q->tc_ngroups * kTcM * sizeof(float), ctx->stream));
+        k_tc_query_tiles<<<dim3(q->tc_ngroups, q->max_len), kTcM, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, d->d_mu.p, q->d_tc_group_len.p,
+                                                                 q->d_tc_group_off.p, q->d_tc_qid.p, d->tc_nb_scale, d->h2_s, q->d_h2_a.p,
+                                                                 q->d_tc_max_norm.p, q->d_tc_slot_max_na.p);
+        SS_LAUNCHED(ctx);
+    }
+    q->h2_built = true;
+    q->h2_dict_serial = d->tc_serial;
+    return SS_OK;
+}
+
+template <int KP, int NB, bool DBG = false>
+static int h2_launch_kind(ss_ctx* ctx, H2Params p, uint32_t slice_begin, uint32_t nslices, size_t smem, bool dependent) {
+    if (!nslices) return SS_OK;
+    p.slice_begin = slice_begin;
+    p.nslices = nslices;
+    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_h2<KP, NB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.ngroups * nslices);
+    cfg.blockDim = dim3(kH2Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = dependent ? 1 : 0;
+    SS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_dtw_scan_h2<KP, NB, DBG>, p));
+    SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+
+struct H2Plan {
+    H2Params p;
+    uint32_t kind_begin[4];  // first slice of each kind (1, 2, 4) and the total
+    uint32_t nslots;
+    size_t smem;
+};
+static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
+    ss_ctx* ctx = d->ctx;
+    static const int waves = [] {
+        const char* e = getenv("SS_DTW_H2_WAVES");
+        return e ? std::max(1, atoi(e)) : 16;
+    }();
+    const uint32_t nslots = q->tc_ngroups * kTcM;
+    if (d->h2_slice_for_groups != q->tc_ngroups) {
+        const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
+        std::vector<uint32_t> st;
+        uint64_t total = 0;
+        for (uint32_t f : d->h_h2_tile_cost) total += f;
+        const uint64_t per = std::max<uint64_t>(1, (total + want - 1) / want);
+        for (int kind = 0; kind < 3; kind++) {
+            d->h2_kind_slice[kind] = (uint32_t)st.size();
+            uint64_t acc = per;  // forces a slice start at the first tile of the kind
+            for (uint32_t t = d->h2_first_tile[kind]; t < d->h2_first_tile[kind + 1]; t++) {
+                if (acc >= per) st.push_back(t), acc = 0;
+                acc += d->h_h2_tile_cost[t];
+            }
+        }
+        d->h2_kind_slice[3] = (uint32_t)st.size();
+        st.push_back(d->h2_ntiles);
+        SS_TRY(upload(ctx, d->d_h2_slice_tile, st.data(), st.size()));
+        d->h2_slice_for_groups = q->tc_ngroups;
+    }
+    const uint32_t nslices = d->h2_kind_slice[3];
+    SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nslices * nslots * kp));
+    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
+    SS_CUDA(ctx, d->d_cand_adist.reserve((size_t)nslots * kp));
+    if (!d->ev_scan0) {
+        SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
+        SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
+    }
+    H2Params& p = plan->p;
+    p.a_blocks = q->d_h2_a.p;
+    p.group_off = q->d_tc_group_off.p;
+    p.group_len = q->d_tc_group_len.p;
+    p.slot_len = q->d_tc_slot_len.p;
+    p.ngroups = q->tc_ngroups;
+    p.tiles = reinterpret_cast<const unsigned char*>(d->d_h2_tiles.p);
+    p.desc = d->d_h2_desc.p;
+    p.slice_tile = d->d_h2_slice_tile.p;
+    p.nslices = nslices;
+    p.slice_begin = 0;
+    p.partial = d->d_tc_partial.p;
+    p.max_len = q->max_len;
+    p.inv_s = 1.0f / d->h2_s;
+    p.dbg = nullptr;
+    p.dbg_nseg = 0;
+    for (int i = 0; i < 4; i++) plan->kind_begin[i] = d->h2_kind_slice[i];
+    plan->nslots = nslots;
+    plan->smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kH2DpThreads * 8 + 1024;
+    return SS_OK;
+}
+
+template <int KP, bool DBG>
+static int h2_launch_all(ss_ctx* ctx, const H2Plan& plan) {
+    bool dep = false;
+    const uint32_t* kb = plan.kind_begin;
+    SS_TRY((h2_launch_kind<KP, 1, DBG>(ctx, plan.p, kb[0], kb[1] - kb[0], plan.smem, dep)));
+    dep = dep || kb[1] > kb[0];
+    SS_TRY((h2_launch_kind<KP, 2, DBG>(ctx, plan.p, kb[1], kb[2] - kb[1], plan.smem, dep)));
+    dep = dep || kb[2] > kb[1];
+    SS_TRY((h2_launch_kind<KP, 4, DBG>(ctx, plan.p, kb[2], kb[3] - kb[2], plan.smem, dep)));
+    return SS_OK;
+}
+
+static bool h2_enabled() {
+    static const int enabled = [] {
+        const char* e = getenv("SS_DTW_H2");
+        return e ? atoi(e) : 1;
+    }();
+    return enabled != 0;
+}
+
+// eta of the bound (true units, per normalised distance): fp16 subnormal roundings of the S-scaled operands and sums
+static double h2_eta(const ss_dict* d) { return (13.0 * (double)d->h2_bmax + 4.0) * 5.9604644775390625e-08 /* 2^-24 */ / (double)d->h2_s; }
+
+int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used) {
+    ss_ctx* ctx = d->ctx;
+    *used = false;
+    if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
+    SS_TRY(h2_queries_build(d, q));
+    if (!q->tc_ngroups) return SS_OK;
+    const int kp = k <= 2 ? 8 : 16;
+    d->last_work = d->total_frames * q->total_frames;
+    d->last_uncertified = 0;
+    H2Plan plan;
+    SS_TRY(h2_plan(d, q, kp, &plan));
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
+    if (kp == 8) SS_TRY((h2_launch_all<8, false>(ctx, plan)));
+    else SS_TRY((h2_launch_all<16, false>(ctx, plan)));
+    SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
+    d->scan_timed = true;
+    if (kp == 8) k_tc_merge<8><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
+    else k_tc_merge<16><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
+    SS_LAUNCHED(ctx);
+    // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S
+    d->h2_bound_inv_s = 1.0 / (double)d->h2_s;
+    SS_TRY(dtw_rescore_finalize(d, q, k, kp, plan.nslots, q->d_tc_qid.p, h2_eta(d), q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 2,
+                                q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
+    *used = true;
+    return SS_OK;
+}
+
+// ss_dict_debug_tc_scan's half-precision counterpart: the raw scan distance of every pair (see dtw_tc_debug_scan)
+int dtw_h2_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale, float* s_out) {
+    ss_ctx* ctx = d->ctx;
+    if (!h2_enabled() || !d->h2_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0)
+        return set_error(ctx, SS_ERR_INVALID, "debug_h2_scan: the packed-half scan does not apply (segments / queries > %d frames, or disabled)", kTcMaxLen);
+    SS_TRY(h2_queries_build(d, q));
+    if (!q->tc_ngroups) return set_error(ctx, SS_ERR_INVALID, "debug_h2_scan: no non-empty query");
+    H2Plan plan;
+    SS_TRY(h2_plan(d, q, 8, &plan));
+    plan.p.dbg = d_out;
+    plan.p.dbg_nseg = (uint32_t)d->nseg;
+    SS_TRY((h2_launch_all<8, true>(ctx, plan)));
+    slot_qid->resize(plan.nslots);
+    SS_CUDA(ctx, cudaMemcpyAsync(slot_qid->data(), q->d_tc_qid.p, plan.nslots * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaMemcpyAsync(mu16, d->d_mu.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *scale = d->tc_nb_scale;
+    *s_out = d->h2_s;
+    return SS_OK;
+}
+
+}  // namespace ss

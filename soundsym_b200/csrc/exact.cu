@@ -276,10 +276,21 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
 // ---------------------------------------------------------------------------------------------------------------
 // Lower bound on the EXACT distance of any pair whose scan distance is >= w (see k_dtw_finalize for the derivation):
 //   bound_mode 0 (fp32 scan):  |scan - exact| <= eps (max|a|^2 + max|b|^2)
-//   bound_mode 1 (fp16 scan):  exact >= w - 2 delta sqrt(w) - E32,  delta = 2^-11 (|a| + |b|)
-__device__ __forceinline__ double scan_lower_bound(float scan, double na, double nb, double eps, int bound_mode) {
+//   bound_mode 1 (fp16 products, fp32 DP):  exact >= w - 2 delta sqrt(w) - E32,  delta = 2^-11 (|a| + |b|)
+//   bound_mode 2 (fp16 products AND packed-half DP, dtw_h2.cu): the scan is at most the rounded-frame DTW times (1 + 2^-11) per
+//     rounding on the path (cost + running sum per cell, <= Lq + Ld cells, Ld <= 32) plus eta (fp16 subnormals; `eps` carries
+//     it), and a path sum beyond the fp16 range reads +inf: w is capped at 60000 / (S (Lq + 32)). Then the same input-rounding
+//     step as mode 1:  exact >= t - 2 delta sqrt(t),  t = (min(w, cap) - eta) (1 + 2^-11)^-(Lq + 34)
+__device__ __forceinline__ double scan_lower_bound(float scan, double na, double nb, double eps, int bound_mode, int la = 0, double inv_s = 0.0) {
     if (bound_mode == 0) return (double)scan - eps * (na + nb);
     const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
+    if (bound_mode == 2) {
+        const double cap = 60000.0 * inv_s / (double)(la + 32);
+        double w = scan > 0.f ? (double)scan : 0.0;  // (+inf stays +inf)
+        w = fmin(w, cap) - eps;
+        const double t = w > 0.0 ? w * exp(-(double)(la + 34) * 4.8816207e-4 /* > ln(1 + 2^-11) */) : 0.0;
+        return t - 2.0 * delta * sqrt(t);
+    }
     const double w = scan > 0.f ? (double)scan : 0.0;
     // E32: fp32 accumulation of the 16 products in the tensor core (<= 16 ulp of na + nb + 2 sqrt(na nb), truncating)
     // plus <= Lq + Ld <= 64 roundings of the running sum along the path
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(128)
 k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
                   const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
                   const float* __restrict__ cand_adist, uint32_t nslots, int kp, int k, uint32_t index_base, const float* __restrict__ max_na,
-                  const float* __restrict__ max_nb, double eps, const float* __restrict__ slot_max_na, int bound_mode,
+                  const float* __restrict__ max_nb, double eps, const float* __restrict__ slot_max_na, int bound_mode, double inv_s,
                   uint8_t* __restrict__ uncert_flag, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
                   unsigned long long* __restrict__ counters) {
     __shared__ double scost[4][32 * 32];
@@ -448,7 +459,7 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
         }
         if (s >= k) {
             const float adist = __shfl_sync(0xffffffffu, my_adist, s);
-            if (scan_lower_bound(adist, na, nb, eps, bound_mode) > kth) continue;  // provably outside the top-k
+            if (scan_lower_bound(adist, na, nb, eps, bound_mode, la, inv_s) > kth) continue;  // provably outside the top-k
             extra++;
         }
         const double e = warp_dtw_exact(squery[warp], la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, scost[warp], lane);
@@ -480,9 +491,11 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
             out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
         }
         bool uncertified = false;  // see k_dtw_finalize
-        if (worst < __int_as_float(0x7f800000)) {
+        // (bound_mode 2: a list that is not full does NOT mean every pair is in it - overflowed pairs read +inf and are never
+        // inserted - so the bound is evaluated anyway, at its cap)
+        if (bound_mode == 2 || worst < __int_as_float(0x7f800000)) {
             const double kth_exact = n >= k ? dv[k - 1] : kInf;
-            uncertified = !(scan_lower_bound(worst, na, nb, eps, bound_mode) > kth_exact);
+            uncertified = !(scan_lower_bound(worst, na, nb, eps, bound_mode, la, inv_s) > kth_exact);
             if (uncertified) atomicAdd(&counters[0], 1ull);
         }
         if (uncert_flag) uncert_flag[qid] = uncertified ? 1 : 0;
@@ -558,8 +571,8 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     if (max_ld <= 32 && q->max_len <= 32) {  // one warp per query slot does the whole refine
         k_dtw_refine_warp<<<ceil_div(nslots, 4), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid,
                                                                         d->d_cand_idx.p, d->d_cand_adist.p, nslots, kp, std::min(k, kp), d->index_base,
-                                                                        d_max_na, d_max_nb, eps, d_slot_max_na, bound_mode, d_uncert_flag,
-                                                                        d_out_idx, d_out_dist, d->d_counters.p);
+                                                                        d_max_na, d_max_nb, eps, d_slot_max_na, bound_mode, d->h2_bound_inv_s,
+                                                                        d_uncert_flag, d_out_idx, d_out_dist, d->d_counters.p);
         SS_LAUNCHED(ctx);
         return SS_OK;
     }

@@ -74,6 +74,20 @@ struct ss_dict {
     std::vector<uint32_t> h_tc_tile_frames;  // per tile: instruction estimate of one pipeline step (slice balancing)
     ss::DevBuf<unsigned long long> d_tc_partial;
     ss::DevBuf<float> d_tc_max_norm;         // [0] = max |fp16(b - mu)|^2
+    // packed-half tensor-core scan (dtw_h2.cu): tiles of 2 slots x 64 TMEM columns, two interleaved segments per register
+    bool h2_ready = false;
+    uint32_t h2_ntiles = 0;
+    uint32_t h2_first_tile[4] = {0, 0, 0, 0};   // first tile of the kinds NB = 1, 2, 4 (launch order) and the total
+    uint32_t h2_kind_slice[4] = {0, 0, 0, 0};   // the same for the cached slice table
+    uint32_t h2_slice_for_groups = 0xFFFFFFFFu;
+    float h2_s = 1.f;                           // power-of-two cost scale S
+    float h2_bmax = 0.f;                        // max |fp16(b - mu)| (bound's eta)
+    double h2_bound_inv_s = 1.0;
+    std::vector<uint32_t> h_h2_tile_cost;
+    ss::DevBuf<uint16_t> d_h2_tiles;
+    ss::DevBuf<int4> d_h2_desc;
+    ss::DevBuf<uint32_t> d_h2_slice_tile;
+    int scan_pref = 0;  // test / A-B hook (ss_dict_set_scan): 0 = packed-half scan first, 1 = start at the fp32 tensor-core scan, 2 = fp32 CUDA-core scan
     // the last SS_DTW match is asynchronous up to its fallback decision: ss::dtw_match_finish waits for ev_done, reads the
     // uncertified count from pinned memory and runs the fallback stages for the queries that need them
     struct Pending {
@@ -124,6 +138,9 @@ struct ss_queries {
     bool tc_built = false;
     uint64_t tc_dict_serial = 0;             // ss_dict::tc_serial the A blocks were built for
     uint64_t tc_a_bytes = 0;
+    bool h2_built = false;                   // the packed-half scan's A blocks (the same rows scaled by S)
+    uint64_t h2_dict_serial = 0;
+    ss::DevBuf<unsigned char> d_h2_a;
     uint32_t tc_ngroups = 0;
     std::vector<uint32_t> h_tc_group_len;
     ss::DevBuf<uint32_t> d_tc_group_len, d_tc_qid, d_tc_slot_len;  // qid / slot_len: ngroups x 128
@@ -150,6 +167,8 @@ int dtw_tc_queries_group(ss_queries* q);  // length-sorted groups of 128 for the
 // asynchronous on the ctx stream up to the fallback decision; dtw_match_finish completes it (a no-op when nothing is pending)
 int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist);
 int dtw_match_finish(ss_dict* d);
+int dtw_h2_dict_build(ss_dict* d);    // builds the interleaved fp16 tiles of the packed-half scan (dtw_h2.cu; after dtw_tc_dict_build)
+int dtw_h2_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale, float* s_out);
 int dtw_tc_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale);
 int queries_check(ss_ctx* ctx, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, int ncoeffs);  // capi.cu
 int queries_prepare(ss_queries* q, const uint64_t* q_frame_offsets, size_t nq);

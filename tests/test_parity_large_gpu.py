@@ -54,17 +54,23 @@ def shard_bounds(doff, n):
     return [0] + [int(np.searchsorted(doff, total * r // n, side="left")) for r in range(1, n)] + [len(doff) - 1]
 
 
-def test_config3_every_query_vs_oracle(ctx):
+@pytest.mark.parametrize("first_stage", [0, 1, 2])
+def test_config3_every_query_vs_oracle(ctx, first_stage):
+    """first_stage: 0 = packed-half tensor-core scan (the default), 1 = fp32-DP tensor-core scan, 2 = fp32 CUDA-core scan -
+    every filter is followed by the f64 refine + certification, so all three must return the oracle's answer"""
     d, doff = synth.segments(10000, C, seed=1234)
     q, qoff = synth.segments(1000, C, seed=5678)
     O.set_threads(O.hardware_threads())
     dev = api.DeviceDictionary(ctx, d, doff)
+    dev.set_scan(first_stage)
     for k in (1, 8):
         idx, dist = dev.match(q, qoff, SS_DTW, k)
         oidx, odist = O.dtw_topk(d, doff, q, qoff, C, k)
         check(idx, dist, oidx, odist)
         assert dev.last_uncertified == 0 and dev.last_exhaustive == 0
         assert dev.last_work == int(doff[-1]) * int(qoff[-1])
+        if first_stage == 0:
+            assert dev.last_tc_fallback <= 10  # the packed-half filter certifies (nearly) every query on its own
 
 
 def test_config4_sampled_queries_one_and_eight_shards_vs_oracle(ctx, config4):
@@ -136,6 +142,49 @@ def test_tensor_core_scan_error_vs_certification_slack(ctx, config4, nd, nsample
     assert over <= 0.25, "tensor-core scan exceeds the rounded-frame DTW by %.3f of the E32 slack the certification assumes" % over
     assert under <= 1.0, "scan is lower than the rounded-frame DTW by more than the rd(|a|^2) budget"
     # and the end result on the same sample is the oracle's
+    idx, dist = dev.match(sq, sqoff, SS_DTW, 1)
+    oidx, odist = O.dtw_topk(d, doff, sq, sqoff, C, 1)
+    check(idx, dist, oidx, odist)
+    assert dev.last_uncertified == 0
+
+
+@pytest.mark.parametrize("nd,nsample", [(10000, 256), (100000, 128)])
+def test_packed_half_scan_is_a_lower_bound_of_the_rounded_frame_dtw(ctx, config4, nd, nsample):
+    """The certification of the packed-half scan (exact.cu scan_lower_bound, bound_mode 2) rests on
+        (scan - eta) (1 + 2^-11)^-(Lq + Ld + 2)  <=  DTW of the fp16-ROUNDED frames
+    (every rounding of the F16 accumulator and of the half2 running sums is round-to-nearest, one per cost and one per cell on
+    the path; a path sum beyond the fp16 range reads +inf). Measured here on every pair of a sample: the property must hold
+    with room to spare, and the scan must stay tight enough to be a useful filter (printed)."""
+    d, doff, q, qoff = config4
+    if nd != 100000:
+        d, doff = synth.segments(nd, C, seed=1234)
+    nq = len(qoff) - 1
+    O.set_threads(O.hardware_threads())
+    ids = np.sort(np.random.default_rng(11).choice(nq, size=nsample, replace=False))
+    sq, sqoff = subset(q, qoff, ids)
+    dev = api.DeviceDictionary(ctx, d, doff)
+    scan, mu, scale, S = dev.debug_h2_scan(sq, sqoff)
+    assert scan.shape == (nsample, nd) and not np.any(np.isnan(scan))
+    dr, qr = rounded_operands(d, mu[:C]), rounded_operands(sq, mu[:C])
+    ref = O.dtw_matrix(dr, doff, qr, sqoff, C)
+    lq = (sqoff[1:] - sqoff[:-1]).astype(np.float64)[:, None]
+    ld = (doff[1:] - doff[:-1]).astype(np.float64)[None, :]
+    u = 2.0 ** -11
+    eta = (13.0 * float(np.max(np.abs(dr))) + 4.0) * 2.0 ** -24 / S
+    fin = np.isfinite(scan)
+    lower = (scan.astype(np.float64) - eta) * (1.0 + u) ** -(lq + ld + 2.0)
+    ratio = np.max(lower[fin] / ref[fin])
+    rel = scan.astype(np.float64)[fin] / ref[fin] - 1.0
+    budget = ((1.0 + u) ** (lq + ld + 2.0) - 1.0 + 0 * ref)[fin]
+    print("\npacked-half scan over %d pairs (nd=%d, S=%g): scan/DTW_rounded - 1 in [%.3e, %.3e] (mean %.2e); worst use of the rounding budget "
+          "(1+u)^(Lq+Ld+2)-1: %.3f; max lower/ref = %.6f; %d pairs read +inf" % (scan.size, nd, S, rel.min(), rel.max(), rel.mean(),
+                                                                                 float(np.max(rel / budget)), ratio, int((~fin).sum())))
+    assert ratio <= 1.0, "the packed-half scan's certified lower bound exceeds the rounded-frame DTW"
+    assert np.max(rel / budget) <= 0.5, "roundings use more than half of the worst-case budget: the bound has no margin"
+    assert rel.min() >= -0.05  # the filter stays within 5 % below (|a|^2 rides rounded down; roundings cancel)
+    # a pair may only read +inf if its path sum really is beyond the fp16 range
+    if (~fin).any():
+        assert np.all(ref[~fin] * (lq + ld + 0 * ref)[~fin] * S * (1.0 + u) ** (lq + ld + 2.0 + 0 * ref)[~fin] >= 65504.0 * 0.999)
     idx, dist = dev.match(sq, sqoff, SS_DTW, 1)
     oidx, odist = O.dtw_topk(d, doff, sq, sqoff, C, 1)
     check(idx, dist, oidx, odist)
