@@ -92,7 +92,8 @@ struct ss_dict {
     // uncertified count from pinned memory and runs the fallback stages for the queries that need them
     struct Pending {
         bool active = false;
-        int stage = 0;  // 1 = the tensor-core scan ran, 2 = the fp32 scan ran (for every query)
+        int stage = 0;  // 1 = a tensor-core scan ran, 2 = the fp32 scan ran (for every query)
+        bool h2 = false;  // stage 1 was the packed-half scan
         struct ss_queries* q = nullptr;
         int k = 0;
         uint32_t* d_out_idx = nullptr;
@@ -103,6 +104,10 @@ struct ss_dict {
     ss::DevBuf<uint32_t> d_tc_slice_tile;       // the tensor-core scan's own slice table (cached)
     uint32_t slice_for_groups = 0xFFFFFFFFu;  // tc_ngroups the cached slice table (d_slice_tile / h_slice_tile) was built for
     uint32_t tc_nsingle = 0, tc_nslices = 0;
+    // the few queries a first stage could not certify, as a batch of their own (dtw.cu dtw_rerun_subset)
+    struct ss_queries* sub_q = nullptr;
+    ss::DevBuf<uint32_t> d_sub_ids, d_sub_idx;
+    ss::DevBuf<double> d_sub_dist;
     // host-buffer entry point (ss_dict_match): query batch + result buffers reused across calls (grow-only)
     struct ss_queries* scratch_q = nullptr;
     ss::DevBuf<uint32_t> d_res_idx;
@@ -157,6 +162,7 @@ inline ss_dict::~ss_dict() {
     if (ev_done) cudaEventDestroy(ev_done);
     if (h_counters) cudaFreeHost(h_counters);
     delete scratch_q;
+    delete sub_q;
 }
 
 namespace ss {

@@ -220,7 +220,12 @@ def test_tc_scan_declines_loud_queries_and_rekeys_query_blocks_per_dictionary(ct
     o_dist = torch.empty((nq, 2), dtype=torch.float64, device="cuda")
     for dd, dv in ((d, dev), (d2, dev2), (d, dev)):
         ctx.check(ctx.lib.ss_dict_match_dev(dv.h, qs.h, SS_DTW, None, 2, o_idx.data_ptr(), o_dist.data_ptr()))
+        ctx.check(ctx.lib.ss_dict_match_finish(dv.h))  # the device results are final after the fallback decision
         ctx.sync()
         oidx, odist = O.dtw_topk(dd, doff, q, qoff, 13, 2)
         check_dtw(o_idx.cpu().numpy().astype(np.uint32), o_dist.cpu().numpy(), oidx, odist, 2)
-        assert dv.last_uncertified == 0 and dv.last_tc_fallback == 0
+        assert dv.last_uncertified == 0
+        # (against d2 the queries sit far from the dictionary's mean frame: the packed-half filter's range is exceeded for
+        # most pairs and it hands those queries on; against d it certifies them itself)
+        if dv is dev:
+            assert dv.last_tc_fallback == 0
