@@ -18,6 +18,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <chrono>
+
 #include "match.cuh"
 
 namespace ss {
@@ -574,6 +576,27 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
     return SS_OK;
 }
 
+// SS_DTW_TRACE=1: wall-clock of the fallback path's steps on stderr (each step is followed by a stream synchronisation)
+static bool dtw_trace() {
+    static const bool on = [] {
+        const char* e = getenv("SS_DTW_TRACE");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+struct TraceTimer {
+    ss_ctx* ctx;
+    std::chrono::steady_clock::time_point t0;
+    explicit TraceTimer(ss_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!dtw_trace()) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ss dtw trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // ---- re-running a few queries through the slower stages -------------------------------------------------------------------
 // The queries a first stage could not certify are gathered (on the device) into a small batch of their own, which then runs
 // the remaining stages - fp32-DP tensor-core scan, fp32 CUDA-core scan, exhaustive f64 - synchronously; their rows are
@@ -603,10 +626,13 @@ static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t
     SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
     bool used = false;
     std::vector<uint32_t> subset;
+    TraceTimer tt(ctx);
     SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
     if (used) {
         SS_TRY(post_counters(d));
         SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
+        tt.lap("  fp32-DP tensor-core stage");
+        if (dtw_trace()) fprintf(stderr, "[ss dtw trace]   -> %llu of %zu still uncertified\n", d->h_counters[0], q->nq);
         if (!d->h_counters[0]) return SS_OK;
         SS_TRY(uncertified_subset(d, q, &subset));
         SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, &subset));
@@ -615,6 +641,8 @@ static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t
     }
     SS_TRY(post_counters(d));
     SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
+    tt.lap("  fp32 CUDA-core stage");
+    if (dtw_trace()) fprintf(stderr, "[ss dtw trace]   -> %llu still uncertified\n", d->h_counters[0]);
     if (!d->h_counters[0]) return SS_OK;
     SS_TRY(uncertified_subset(d, q, &subset));
     *n_exhaustive += subset.size();
@@ -623,6 +651,7 @@ static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t
 
 static int dtw_rerun_subset(ss_dict* d, ss_queries* q, int k, const std::vector<uint32_t>& subset, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
+    TraceTimer tt(ctx);
     if (!d->sub_q) {
         d->sub_q = new (std::nothrow) ss_queries();
         if (!d->sub_q) return set_error(ctx, SS_ERR_NOMEM, "out of host memory");
@@ -640,11 +669,13 @@ static int dtw_rerun_subset(ss_dict* d, ss_queries* q, int k, const std::vector<
     k_gather_query_rows<<<(unsigned)ns, 128, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, d->d_sub_ids.p, sub->d_off.p, q->c, sub->d_mfcc.p);
     SS_LAUNCHED(ctx);
     SS_TRY(dtw_tc_queries_group(sub));
+    tt.lap("rerun: gather + group");
     SS_CUDA(ctx, d->d_sub_idx.reserve(ns * (size_t)k));
     SS_CUDA(ctx, d->d_sub_dist.reserve(ns * (size_t)k));
     const uint64_t work = d->last_work;  // the stages below account their own (partial) work: keep the whole match's figure
     SS_TRY(dtw_match_remaining_stages(d, sub, k, d->d_sub_idx.p, d->d_sub_dist.p, &d->last_exhaustive));
     d->last_work = work;
+    tt.lap("rerun: remaining stages");
     k_scatter_topk<<<ceil_div((long long)ns * k, 128), 128, 0, ctx->stream>>>(d->d_sub_idx.p, d->d_sub_dist.p, d->d_sub_ids.p, (uint32_t)ns, k, d_out_idx,
                                                                               d_out_dist);
     SS_LAUNCHED(ctx);

@@ -663,18 +663,19 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
     SS_TRY(h2_queries_build(d, q));
     if (!q->tc_ngroups) return SS_OK;
-    const int kp = k <= 2 ? 8 : 16;
+    // k > 2: the k-th and the kp-th neighbour must be further apart than the filter's ~4 % margin: a longer list
+    const int kp = k <= 2 ? 8 : 32;
     d->last_work = d->total_frames * q->total_frames;
     d->last_uncertified = 0;
     H2Plan plan;
     SS_TRY(h2_plan(d, q, kp, &plan));
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     if (kp == 8) SS_TRY((h2_launch_all<8, false>(ctx, plan)));
-    else SS_TRY((h2_launch_all<16, false>(ctx, plan)));
+    else SS_TRY((h2_launch_all<32, false>(ctx, plan)));
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
     d->scan_timed = true;
     if (kp == 8) k_tc_merge<8><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
-    else k_tc_merge<16><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
+    else k_tc_merge<32><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
     // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S
     d->h2_bound_inv_s = 1.0 / (double)d->h2_s;

@@ -12,7 +12,7 @@ constexpr int kStrip = 32;        // DP columns held in registers per strip
 constexpr int kTileFrames = 128;  // frames per TMA tile (8 KB)
 constexpr int kStages = 3;        // tile ring depth
 constexpr int kWarpsPerCta = 4;
-constexpr int kMaxKeep = 16;      // largest candidate list per query kept by the scan
+constexpr int kMaxKeep = 32;      // largest candidate list per query kept by a scan
 
 struct StripDesc {  // 16 B, read as int4
     uint32_t frame_begin;  // first frame of the strip in the shard's frame stream

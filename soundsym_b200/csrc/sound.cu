@@ -26,6 +26,12 @@ struct SoundTables {
     DevBuf<double2> d_tw;     // exp(-2 pi i j / 1024), j = 0..1023
     DevBuf<double> d_dct;     // c x c: cos(pi k (2n+1) / (2c))
     DevBuf<int> d_bins;       // c + 2
+    // triangle weights of the mel bank, one run per half band (2 f = rising part of band f, 2 f + 1 = falling part): the
+    // values (double)i / width and 1.0 - (double)i / width the CPU path forms per element, computed once on the host with
+    // the same IEEE operations. d_half: per half band {first bin, count, offset into d_melw}.
+    DevBuf<double> d_melw;
+    DevBuf<int> d_half;       // 2 c x 3 ints (padded to 4)
+    int melw_count = 0;
 };
 
 struct SoundState {
@@ -93,7 +99,20 @@ static int get_tables(ss_ctx* ctx, double sample_rate, int c, SoundTables** out)
     }
     for (int k = 0; k < c; k++)
         for (int n = 0; n < c; n++) dct[(size_t)k * c + n] = std::cos(kPi * (double)k * (2.0 * (double)n + 1.0) / (2.0 * (double)c));
+    std::vector<double> melw;
+    std::vector<int> half;
+    for (int f = 0; f < c; f++) {
+        const int b0 = t->bins[f], b1 = t->bins[f + 1], b2 = t->bins[f + 2];
+        const double up = (double)(b1 - b0), down = (double)(b2 - b1);
+        half.insert(half.end(), {b0, b1 - b0, (int)melw.size(), 0});
+        for (int i = 0; i < b1 - b0; i++) melw.push_back((double)i / up);
+        half.insert(half.end(), {b1, b2 - b1, (int)melw.size(), 0});
+        for (int i = 0; i < b2 - b1; i++) melw.push_back(1.0 - (double)i / down);
+    }
+    t->melw_count = (int)melw.size();
     int rc = upload(ctx, t->d_win, win.data(), win.size());
+    if (rc == SS_OK) rc = upload(ctx, t->d_melw, melw.data(), melw.size());
+    if (rc == SS_OK) rc = upload(ctx, t->d_half, half.data(), half.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_tw, tw.data(), tw.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_dct, dct.data(), dct.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_bins, t->bins, (size_t)c + 2);
@@ -162,8 +181,9 @@ __device__ __forceinline__ uint32_t seg_of(const uint64_t* __restrict__ off, uin
 
 __global__ void __launch_bounds__(kMfccWarps * 32)
 k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restrict__ win, const double2* __restrict__ tw,
-       const double* __restrict__ dctm, const int* __restrict__ bins, int c, double energy_floor, double* __restrict__ out,
-       const uint64_t* __restrict__ frame_off = nullptr, const uint64_t* __restrict__ samp_off = nullptr, uint32_t nsounds = 0) {
+       const double* __restrict__ dctm, const int* __restrict__ bins, const double* __restrict__ melw, const int4* __restrict__ halfband, int c,
+       double energy_floor, double* __restrict__ out, const uint64_t* __restrict__ frame_off = nullptr,
+       const uint64_t* __restrict__ samp_off = nullptr, uint32_t nsounds = 0) {
     extern __shared__ __align__(16) unsigned char mfcc_smem[];
     double2* s_buf = reinterpret_cast<double2*>(mfcc_smem);                                   // [warps][512]  32 KB
     double* s_pw = reinterpret_cast<double*>(mfcc_smem + sizeof(double2) * kMfccWarps * kHalf);  // [warps][512]  16 KB
@@ -173,6 +193,9 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
     double* pw = s_pw + warp * kHalf;          // power spectrum of the bins the bank reads
     double* s_le = s_le_all + warp * 16;
     const int kb0 = bins[0], kb1 = bins[c + 1];
+    // lane h < 2 c sums half band h (rising or falling part of band h / 2) sequentially, in the CPU path's element order
+    const int4 hb = lane < 2 * c ? __ldg(&halfband[lane]) : make_int4(0, 0, 0, 0);
+    const double* hw = melw + hb.z;
 
     for (size_t f = (size_t)blockIdx.x * kMfccWarps + warp; f < frames; f += (size_t)gridDim.x * kMfccWarps) {
         // one sound: frame f starts at sample f * HOP. Batch (ss_sound_analyze_batch): frame f belongs to the sound whose
@@ -242,14 +265,15 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
         }
         __syncwarp();
         // ---- triangular bands (un-normalised; rise starts at 0, fall starts at 1), log10 with the A4 floor ------------
-        if (lane < c) {
-            const int b0 = bins[lane], b1 = bins[lane + 1], b2 = bins[lane + 2];
-            const double up = (double)(b1 - b0), down = (double)(b2 - b1);
-            double up_sum = 0.0, down_sum = 0.0;
-            for (int k = b0, i = 0; k < b1; k++, i++) up_sum = up_sum + pw[k] * ((double)i / up);
-            for (int k = b1, i = 0; k < b2; k++, i++) down_sum = down_sum + pw[k] * (1.0 - (double)i / down);
-            const double e = up_sum + down_sum;
-            s_le[lane] = log10(e > energy_floor ? e : energy_floor);
+        // 2 c lanes each fold one half band (weights from the table: no division in the loop), then band f = rise + fall
+        {
+            double part = 0.0;
+            for (int i = 0; i < hb.y; i++) part = part + pw[hb.x + i] * __ldg(&hw[i]);
+            const double up_sum = __shfl_sync(0xffffffffu, part, (2 * lane) & 31), down_sum = __shfl_sync(0xffffffffu, part, (2 * lane + 1) & 31);
+            if (lane < c) {
+                const double e = up_sum + down_sum;
+                s_le[lane] = log10(e > energy_floor ? e : energy_floor);
+            }
         }
         __syncwarp();
         // ---- DCT-II x 2 ---------------------------------------------------------------------------------------------
@@ -351,7 +375,8 @@ static int mfcc_launch(ss_ctx* ctx, const double* d_samples, size_t n, double sa
     const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 16);
     const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * 16);
     SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(d_samples, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, c, 1e-10, d_out);
+    k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(d_samples, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, t->d_melw.p,
+                                                         reinterpret_cast<const int4*>(t->d_half.p), c, 1e-10, d_out);
     SS_LAUNCHED(ctx);
     (void)n;
     return SS_OK;
@@ -572,8 +597,9 @@ int ss_sound_analyze_batch(ss_ctx* ctx, const double* samples, const uint64_t* s
         const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 16);
         const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * 16);
         SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(st->d_samples.p, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, ncoeffs,
-                                                             1e-10, st->d_mfcc.p, st->d_off_b.p, st->d_off_a.p, (uint32_t)nsounds);
+        k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(st->d_samples.p, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, t->d_melw.p,
+                                                             reinterpret_cast<const int4*>(t->d_half.p), ncoeffs, 1e-10, st->d_mfcc.p, st->d_off_b.p,
+                                                             st->d_off_a.p, (uint32_t)nsounds);
         SS_LAUNCHED(ctx);
         if (out_mfcc)
             SS_CUDA(ctx, cudaMemcpyAsync(out_mfcc, st->d_mfcc.p, frames * (size_t)ncoeffs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -70,7 +70,7 @@ def test_config3_every_query_vs_oracle(ctx, first_stage):
         assert dev.last_uncertified == 0 and dev.last_exhaustive == 0
         assert dev.last_work == int(doff[-1]) * int(qoff[-1])
         if first_stage == 0:
-            assert dev.last_tc_fallback <= 10  # the packed-half filter certifies (nearly) every query on its own
+            assert dev.last_tc_fallback <= 50  # the packed-half filter certifies all but a few per cent of the queries on its own
 
 
 def test_config4_sampled_queries_one_and_eight_shards_vs_oracle(ctx, config4):
