@@ -692,6 +692,11 @@ int dtw_match_finish(ss_dict* d) {
     SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
     unsigned long long n_unc = d->h_counters[0];
     std::vector<uint32_t> subset;
+    struct Guard {  // the stages below are fallbacks: they do not touch the first stage's scan-time events
+        ss_dict* d;
+        explicit Guard(ss_dict* dd) : d(dd) { d->in_fallback = true; }
+        ~Guard() { d->in_fallback = false; }
+    } guard(d);
     if (d->pending.stage == 1 && n_unc) {
         SS_TRY(uncertified_subset(d, q, &subset));
         d->last_tc_fallback = subset.size();
@@ -786,10 +791,12 @@ static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx,
         }
 #define SS_SCAN_CASE(RBV, KPV)                                       \
     if (g_scan_rb == RBV && kp == KPV) {                              \
-        SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));      \
+        if (!d->in_fallback) SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream)); \
         SS_TRY((launch_scan<RBV, KPV>(ctx, p, grid)));                \
-        SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));      \
-        d->scan_timed = true;                                         \
+        if (!d->in_fallback) {                                        \
+            SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));  \
+            d->scan_timed = true;                                     \
+        }                                                             \
         k_dtw_merge<KPV><<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_partial.p, nslices, nslots, d->d_cand_idx.p, \
                                                                         d->d_cand_adist.p);                                \
         SS_LAUNCHED(ctx);                                             \

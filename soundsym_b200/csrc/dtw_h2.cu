@@ -586,7 +586,10 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     }();
     const uint32_t nslots = q->tc_ngroups * kTcM;
     if (d->h2_slice_for_groups != q->tc_ngroups) {
-        const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
+        // about `waves` CTAs per SM, but never slices of fewer than ~12 tiles: a small batch (nq = 1: one group) would
+        // otherwise pay a CTA's fixed cost (TMEM allocation, the A-block copy, list merge) two thousand times
+        const uint32_t want = std::max<uint32_t>(1, std::min<uint32_t>(((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups,
+                                                                       std::max<uint32_t>((uint32_t)ctx->sm_count, d->h2_ntiles / 12)));
         std::vector<uint32_t> st;
         uint64_t total = 0;
         for (uint32_t f : d->h_h2_tile_cost) total += f;

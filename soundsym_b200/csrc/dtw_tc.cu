@@ -782,11 +782,13 @@ static int tc_launch_kind(ss_ctx* ctx, TcParams p, uint32_t slice_begin, uint32_
 // slices [0, nsingle) hold single-segment tiles, [nsingle, nslices) paired ones
 template <int KP>
 static int tc_launch(ss_ctx* ctx, const TcParams& p, uint32_t nsingle, uint32_t nslices, size_t smem, uint32_t nlists, uint32_t nslots, ss_dict* d) {
-    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
+    if (!d->in_fallback) SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     SS_TRY((tc_launch_kind<KP, false>(ctx, p, 0, nsingle, smem, false)));
     SS_TRY((tc_launch_kind<KP, true>(ctx, p, nsingle, nslices - nsingle, smem, nsingle != 0)));
-    SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
-    d->scan_timed = true;
+    if (!d->in_fallback) {  // the fallback stages of a match keep the first stage's scan time
+        SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
+        d->scan_timed = true;
+    }
     k_tc_merge<KP><<<ceil_div(nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, nlists, nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
     return SS_OK;
@@ -816,7 +818,10 @@ static int tc_plan(ss_dict* d, ss_queries* q, int kp, TcPlan* plan) {
     }();
     const uint32_t nslots = q->tc_ngroups * kTcM;
     if (d->slice_for_groups != q->tc_ngroups) {  // the slice table only depends on the dictionary and the number of query groups
-        const uint32_t want = std::max<uint32_t>(1, ((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups);
+        // about `waves` CTAs per SM, but never slices of fewer than ~12 tiles: a small batch (nq = 1: one group) would
+        // otherwise pay a CTA's fixed cost (TMEM allocation, the A-block copy, list merge) two thousand times
+        const uint32_t want = std::max<uint32_t>(1, std::min<uint32_t>(((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups,
+                                                                       std::max<uint32_t>((uint32_t)ctx->sm_count, d->tc_ntiles / 12)));
         std::vector<uint32_t> st;  // (staged by cudaMemcpyAsync before it returns)
         uint64_t total = 0;
         for (uint32_t f : d->h_tc_tile_frames) total += f;

@@ -62,6 +62,7 @@ struct ss_dict {
     ss::DevBuf<uint32_t> d_exh_qid;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;  // around the dominant kernel of the last match
     bool scan_timed = false;
+    bool in_fallback = false;  // set while dtw_match_finish runs later stages
     // tensor-core scan (dtw_tc.cu): fp16 UMMA tiles of 4 segment slots x 32 columns, segments sorted by length
     bool tc_ready = false;
     uint64_t tc_serial = 0;                  // identifies this build of the tiles (query A blocks are keyed on it)

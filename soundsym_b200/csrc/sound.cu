@@ -179,18 +179,23 @@ __device__ __forceinline__ uint32_t seg_of(const uint64_t* __restrict__ off, uin
     return lo;
 }
 
-__global__ void __launch_bounds__(kMfccWarps * 32)
+// (min CTAs per SM: 4 -> 128 registers per thread without spills, 16 warps / SM; left to itself the compiler takes 168
+// registers = 12 warps / SM. 40.5 KB of shared memory per CTA at 44.1 kHz.)
+#ifndef SS_MFCC_MINBLOCKS
+#define SS_MFCC_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kMfccWarps * 32, SS_MFCC_MINBLOCKS)
 k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restrict__ win, const double2* __restrict__ tw,
        const double* __restrict__ dctm, const int* __restrict__ bins, const double* __restrict__ melw, const int4* __restrict__ halfband, int c,
-       double energy_floor, double* __restrict__ out, const uint64_t* __restrict__ frame_off = nullptr,
+       int pw_len, double energy_floor, double* __restrict__ out, const uint64_t* __restrict__ frame_off = nullptr,
        const uint64_t* __restrict__ samp_off = nullptr, uint32_t nsounds = 0) {
     extern __shared__ __align__(16) unsigned char mfcc_smem[];
     double2* s_buf = reinterpret_cast<double2*>(mfcc_smem);                                   // [warps][512]  32 KB
-    double* s_pw = reinterpret_cast<double*>(mfcc_smem + sizeof(double2) * kMfccWarps * kHalf);  // [warps][512]  16 KB
-    double* s_le_all = s_pw + kMfccWarps * kHalf;                                             // [warps][16]
+    double* s_pw = reinterpret_cast<double*>(mfcc_smem + sizeof(double2) * kMfccWarps * kHalf);  // [warps][pw_len]: bins below the bank's top edge
+    double* s_le_all = s_pw + kMfccWarps * pw_len;                                            // [warps][16]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double2* buf = s_buf + warp * kHalf;
-    double* pw = s_pw + warp * kHalf;          // power spectrum of the bins the bank reads
+    double* pw = s_pw + warp * pw_len;         // power spectrum of the bins the bank reads
     double* s_le = s_le_all + warp * 16;
     const int kb0 = bins[0], kb1 = bins[c + 1];
     // lane h < 2 c sums half band h (rising or falling part of band h / 2) sequentially, in the CPU path's element order
@@ -372,11 +377,12 @@ static int mfcc_launch(ss_ctx* ctx, const double* d_samples, size_t n, double sa
     if (!frames) return SS_OK;
     SoundTables* t = nullptr;
     SS_TRY(get_tables(ctx, sample_rate, c, &t));
-    const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 16);
-    const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * 16);
+    const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 4 * SS_MFCC_MINBLOCKS);
+    const int pw_len = (t->bins[c + 1] + 32) & ~31;  // 256 at 44.1 kHz (top edge bin 230)
+    const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * pw_len + sizeof(double) * kMfccWarps * 16);
     SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(d_samples, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, t->d_melw.p,
-                                                         reinterpret_cast<const int4*>(t->d_half.p), c, 1e-10, d_out);
+                                                         reinterpret_cast<const int4*>(t->d_half.p), c, pw_len, 1e-10, d_out);
     SS_LAUNCHED(ctx);
     (void)n;
     return SS_OK;
@@ -594,11 +600,12 @@ int ss_sound_analyze_batch(ss_ctx* ctx, const double* samples, const uint64_t* s
         SS_CUDA(ctx, st->d_mfcc.reserve(frames * (size_t)ncoeffs));
         SoundTables* t = nullptr;
         SS_TRY(get_tables(ctx, sample_rate, ncoeffs, &t));
-        const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 16);
-        const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * 16);
+        const int grid = (int)std::min<size_t>((frames + kMfccWarps - 1) / kMfccWarps, (size_t)ctx->sm_count * 4 * SS_MFCC_MINBLOCKS);
+        const int pw_len = (t->bins[ncoeffs + 1] + 32) & ~31;
+        const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * pw_len + sizeof(double) * kMfccWarps * 16);
         SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(st->d_samples.p, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, t->d_melw.p,
-                                                             reinterpret_cast<const int4*>(t->d_half.p), ncoeffs, 1e-10, st->d_mfcc.p, st->d_off_b.p,
+                                                             reinterpret_cast<const int4*>(t->d_half.p), ncoeffs, pw_len, 1e-10, st->d_mfcc.p, st->d_off_b.p,
                                                              st->d_off_a.p, (uint32_t)nsounds);
         SS_LAUNCHED(ctx);
         if (out_mfcc)
