@@ -60,6 +60,10 @@ struct H2Params {
     unsigned long long* partial;  // [nslices][ngroups * 128][KP]
     uint32_t max_len;
     float inv_s;                  // 1 / S
+    // [ngroups * 128] per query: the smallest "worst kept key" any finished CTA reported. A CTA that kept KP candidates all
+    // below T proves that nothing >= T is in the query's global top-KP, so later CTAs start with that threshold instead of an
+    // empty list's +inf and skip almost every insertion (a CTA's first few hundred pairs are otherwise mostly insertions).
+    unsigned long long* thr;
     float* dbg;                   // DBG instantiation only: [ngroups * 128][dbg_nseg]
     uint32_t dbg_nseg;
 };
@@ -128,7 +132,26 @@ __device__ __forceinline__ __half2 h2_combine(__half2 a, __half2 b) {
     const uint32_t r = __byte_perm(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), 0x7610);
     return *reinterpret_cast<const __half2*>(&r);
 }
-__device__ __forceinline__ __half2 h2_pick4(const __half2* v, int r) { return r == 0 ? v[0] : (r == 1 ? v[1] : (r == 2 ? v[2] : v[3])); }
+// element e (0..7) of a slot descriptor; e is a compile-time constant after unrolling, so these fold to register reads
+// (arrays indexed in unrolled loops ended up in local memory)
+__device__ __forceinline__ int h2_len_of(const int4& sc, int e) { return (int)((((e < 4) ? (uint32_t)sc.x : (uint32_t)sc.y) >> (8 * (e & 3))) & 0xFFu); }
+__device__ __forceinline__ int h2_seg_of(const int4& sa, const int4& sb, int e) {
+    return e == 0 ? sa.x : e == 1 ? sa.y : e == 2 ? sa.z : e == 3 ? sa.w : e == 4 ? sb.x : e == 5 ? sb.y : e == 6 ? sb.z : sb.w;
+}
+// v[r], r in 0..3, as three selects on registers (a plain ternary chain over an array is turned into an indexed load from local
+// memory by the compiler, which put the capture values on the stack)
+__device__ __forceinline__ uint32_t h2_selp(uint32_t a, uint32_t b, int pick_a) {
+    uint32_t r;
+    asm("{\n.reg .pred q;\nsetp.ne.s32 q, %3, 0;\nselp.b32 %0, %1, %2, q;\n}\n" : "=r"(r) : "r"(a), "r"(b), "r"(pick_a));
+    return r;
+}
+__device__ __forceinline__ __half2 h2_pick4(const __half2* v, int r) {
+    const uint32_t v0 = *reinterpret_cast<const uint32_t*>(&v[0]), v1 = *reinterpret_cast<const uint32_t*>(&v[1]);
+    const uint32_t v2 = *reinterpret_cast<const uint32_t*>(&v[2]), v3 = *reinterpret_cast<const uint32_t*>(&v[3]);
+    const uint32_t lo = h2_selp(v1, v0, r & 1), hi = h2_selp(v3, v2, r & 1);
+    const uint32_t o = h2_selp(hi, lo, r & 2);
+    return *reinterpret_cast<const __half2*>(&o);
+}
 
 // TWO rows (i, i + 1) of one band (two interleaved segments), row state in place: per half2 cell VHMNMX + HADD2.
 // c0l receives row i's values of the last 4-column group (row i + 1's stay in d[4 NG - 4 ..]).
@@ -182,8 +205,7 @@ __device__ __forceinline__ void h2_step2(TcCursor& cur, __half2 (&d)[NB][4 * NG]
 // One dictionary tile for one thread (= one query x one slot = 2 NB segments). ra / rb: position of column len - 1 inside the
 // last 4-column group, for the band's first (low halves) and second (high halves) segment. res[b] = D(Lm - 1, len - 1) of both.
 template <int NB, int NG>
-__device__ __forceinline__ void h2_tile(uint32_t L, uint32_t lmin, uint32_t Lm, const int (&ra)[NB], const int (&rb)[NB], TcCursor& cur,
-                                        __half2 (&res)[NB]) {
+__device__ __forceinline__ void h2_tile(uint32_t L, uint32_t lmin, uint32_t Lm, const int4& sc, TcCursor& cur, __half2 (&res)[NB]) {
     __half2 d[NB][4 * NG];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
@@ -231,8 +253,9 @@ __device__ __forceinline__ void h2_tile(uint32_t L, uint32_t lmin, uint32_t Lm, 
         const bool end0 = 2 * st + 1 == Lm, end1 = 2 * st + 2 == Lm;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
-            const __half2 e0 = h2_combine(h2_pick4(c0l[b], ra[b]), h2_pick4(c0l[b], rb[b]));
-            const __half2 e1 = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra[b]), h2_pick4(&d[b][4 * (NG - 1)], rb[b]));
+            const int ra = (h2_len_of(sc, 2 * b) - 1) & 3, rb = (h2_len_of(sc, 2 * b + 1) - 1) & 3;
+            const __half2 e0 = h2_combine(h2_pick4(c0l[b], ra), h2_pick4(c0l[b], rb));
+            const __half2 e1 = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra), h2_pick4(&d[b][4 * (NG - 1)], rb));
             res[b] = end0 ? e0 : (end1 ? e1 : res[b]);
         }
     }
@@ -247,7 +270,8 @@ __device__ __forceinline__ void h2_tile(uint32_t L, uint32_t lmin, uint32_t Lm, 
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             h2_band_row<NG>(tm0[b], d[b], dinit);
-            const __half2 e = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra[b]), h2_pick4(&d[b][4 * (NG - 1)], rb[b]));
+            const int ra = (h2_len_of(sc, 2 * b) - 1) & 3, rb = (h2_len_of(sc, 2 * b + 1) - 1) & 3;
+            const __half2 e = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra), h2_pick4(&d[b][4 * (NG - 1)], rb));
             res[b] = (L == Lm) ? e : res[b];
         }
     }
@@ -342,7 +366,8 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         unsigned long long* list = topk + threadIdx.x;  // [KP][256] keys, this thread's column
 #pragma unroll
         for (int s = 0; s < KP; s++) list[s * kH2DpThreads] = 0xFFFFFFFFFFFFFFFFull;
-        unsigned long long worst = 0xFFFFFFFFFFFFFFFFull;
+        const unsigned long long thr0 = __ldcg(p.thr + g * kTcM + m);  // (L2: other CTAs update it)
+        unsigned long long worst = thr0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * kH2SlotCols;
         const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
         TcCursor cur;
@@ -350,28 +375,22 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         for (uint32_t n = 0; n < ntiles; n++) {
             const int4* dp = p.desc + ((size_t)(t0 + n) * kH2Slots + slot) * kH2DescInt4;
             const int4 sa = __ldg(dp), sb = __ldg(dp + 1), sc = __ldg(dp + 2);
-            const int segs[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
             const int ng = sc.z;
-            int lens[2 * NB], ra[NB], rb[NB];
-#pragma unroll
-            for (int e = 0; e < 2 * NB; e++) lens[e] = (int)((((e < 4) ? (uint32_t)sc.x : (uint32_t)sc.y) >> (8 * (e & 3))) & 0xFFu);
-#pragma unroll
-            for (int b = 0; b < NB; b++) ra[b] = (lens[2 * b] - 1) & 3, rb[b] = (lens[2 * b + 1] - 1) & 3;
             __half2 res[NB];
             // every segment of a tile has the same number of 4-column groups: straight-line code over 4 NG registers per band
             if constexpr (NB == 1) {
                 switch (ng) {
-                    case 5: h2_tile<1, 5>(L, lmin, Lm, ra, rb, cur, res); break;
-                    case 6: h2_tile<1, 6>(L, lmin, Lm, ra, rb, cur, res); break;
-                    case 7: h2_tile<1, 7>(L, lmin, Lm, ra, rb, cur, res); break;
-                    default: h2_tile<1, 8>(L, lmin, Lm, ra, rb, cur, res); break;
+                    case 5: h2_tile<1, 5>(L, lmin, Lm, sc, cur, res); break;
+                    case 6: h2_tile<1, 6>(L, lmin, Lm, sc, cur, res); break;
+                    case 7: h2_tile<1, 7>(L, lmin, Lm, sc, cur, res); break;
+                    default: h2_tile<1, 8>(L, lmin, Lm, sc, cur, res); break;
                 }
             } else if constexpr (NB == 2) {
-                if (ng == 3) h2_tile<2, 3>(L, lmin, Lm, ra, rb, cur, res);
-                else h2_tile<2, 4>(L, lmin, Lm, ra, rb, cur, res);
+                if (ng == 3) h2_tile<2, 3>(L, lmin, Lm, sc, cur, res);
+                else h2_tile<2, 4>(L, lmin, Lm, sc, cur, res);
             } else {
-                if (ng == 1) h2_tile<4, 1>(L, lmin, Lm, ra, rb, cur, res);
-                else h2_tile<4, 2>(L, lmin, Lm, ra, rb, cur, res);
+                if (ng == 1) h2_tile<4, 1>(L, lmin, Lm, sc, cur, res);
+                else h2_tile<4, 2>(L, lmin, Lm, sc, cur, res);
             }
             if (Lm) {
 #pragma unroll
@@ -379,12 +398,15 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
 #pragma unroll
                     for (int hsel = 0; hsel < 2; hsel++) {
                         const int e = 2 * b + hsel;
-                        if (segs[e] < 0) continue;
-                        const float v = hsel ? __high2float(res[b]) : __low2float(res[b]);
-                        // D16 / (S (Lq + Ld)); an overflowed path sum stays +inf and is never inserted
-                        const float dist = __fdividef(v * p.inv_s, (float)(Lm + (uint32_t)lens[e]));
-                        tc_insert<KP, kH2DpThreads>(list, worst, dist, (uint32_t)segs[e]);
-                        if constexpr (DBG) p.dbg[(size_t)(g * kTcM + m) * p.dbg_nseg + segs[e]] = dist;
+                        const int seg = h2_seg_of(sa, sb, e);
+                        if (seg >= 0) {
+                            const float v = hsel ? __high2float(res[b]) : __low2float(res[b]);
+                            // D16 / (S (Lq + Ld)); an overflowed path sum stays +inf and is never inserted
+                            const float dist = __fdividef(v * p.inv_s, (float)(Lm + (uint32_t)h2_len_of(sc, e)));
+                            tc_insert<KP, kH2DpThreads>(list, worst, dist, (uint32_t)seg);
+                            worst = worst < thr0 ? worst : thr0;  // (an insertion reloads `worst` from the list's last place)
+                            if constexpr (DBG) p.dbg[(size_t)(g * kTcM + m) * p.dbg_nseg + seg] = dist;
+                        }
                     }
                 }
             }
@@ -397,7 +419,10 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
                 const unsigned long long key = other[s * kH2DpThreads];
                 if (key >= worst) break;
                 tc_insert_key<KP, kH2DpThreads>(list, worst, key);
+                worst = worst < thr0 ? worst : thr0;
             }
+            const unsigned long long kept_worst = list[(KP - 1) * kH2DpThreads];
+            if (kept_worst != 0xFFFFFFFFFFFFFFFFull && kept_worst < thr0) atomicMin(p.thr + g * kTcM + m, kept_worst);
             unsigned long long* out = p.partial + ((size_t)slice * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
 #pragma unroll
             for (int s = 0; s < KP; s++) out[s] = list[s * kH2DpThreads];
@@ -629,6 +654,9 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     p.partial = d->d_tc_partial.p;
     p.max_len = q->max_len;
     p.inv_s = 1.0f / d->h2_s;
+    SS_CUDA(ctx, d->d_h2_thr.reserve(std::max<uint32_t>(nslots, 1)));
+    SS_CUDA(ctx, cudaMemsetAsync(d->d_h2_thr.p, 0xFF, (size_t)nslots * sizeof(unsigned long long), ctx->stream));
+    p.thr = d->d_h2_thr.p;
     p.dbg = nullptr;
     p.dbg_nseg = 0;
     for (int i = 0; i < 4; i++) plan->kind_begin[i] = d->h2_kind_slice[i];
@@ -667,17 +695,26 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     SS_TRY(h2_queries_build(d, q));
     if (!q->tc_ngroups) return SS_OK;
     // k > 2: the k-th and the kp-th neighbour must be further apart than the filter's ~4 % margin: a longer list
-    const int kp = k <= 2 ? 8 : 32;
+    // SS_DTW_H2_KP=8|16|32: candidates kept per query for k <= 2. Measured at config 4 (profiles/bench/r2_h2_kp_sweep.json): 8 leaves
+    // 47 of the 10 000 queries to the fallback (+1.5 ms for their re-run) but the scan itself is 3 ms faster than with 16.
+    static const int kp_small = [] {
+        const char* e = getenv("SS_DTW_H2_KP");
+        const int v = e ? atoi(e) : 8;
+        return v == 16 || v == 32 ? v : 8;
+    }();
+    const int kp = k <= 2 ? kp_small : 32;
     d->last_work = d->total_frames * q->total_frames;
     d->last_uncertified = 0;
     H2Plan plan;
     SS_TRY(h2_plan(d, q, kp, &plan));
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     if (kp == 8) SS_TRY((h2_launch_all<8, false>(ctx, plan)));
+    else if (kp == 16) SS_TRY((h2_launch_all<16, false>(ctx, plan)));
     else SS_TRY((h2_launch_all<32, false>(ctx, plan)));
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
     d->scan_timed = true;
     if (kp == 8) k_tc_merge<8><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
+    else if (kp == 16) k_tc_merge<16><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     else k_tc_merge<32><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
     // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S
