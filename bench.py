@@ -174,9 +174,16 @@ WORKLOADS = {
     4: "synthetic 100k-segment dictionary x 10k queries, C=13, L~U{4..32}, DTW top-1 (config 4)",
     3: "synthetic 10k-segment dictionary x 1k queries, C=13, L~U{4..32}, DTW top-1 (config 3)",
 }
-# measured on B200 by tools/microbench_band2.cu (profiles/r2_microbench_band2.log): FMNMX3 issues at 16 lanes / clk / SMSP
-ALU_FMNMX3_LANES_PER_CLK_SM = 63.9
-BAND_CEILING_CELLS_PER_CLK_SM = 47.3  # the register-resident band alone (FMNMX3 + FADD per cell), 16 warps / SM
+# measured on B200 by tools/microbench_band2.cu (profiles/r2_microbench_band2.log). Every DP cell needs one three-input min
+# on the ALU pipe, which issues FMNMX3 (fp32: one cell) and VHMNMX (half2: two cells) at 63.9 lanes / clk / SM; the
+# register-resident band alone (min + add per cell, costs already in registers) reaches 47.3 / 83.1 cells / clk / SM.
+SCAN_KERNELS = {
+    1: ("k_dtw_scan_h2 (tcgen05 fp16 cost matrix, F16 accumulator in TMEM + packed-half DP: VHMNMX + HADD2 per two cells)", 2 * 63.9, 83.1,
+        "f16 (packed-half DP scan on f16 tensor-core costs; winners refined in f64)"),
+    2: ("k_dtw_scan_tc (tcgen05 fp16 cost matrix, F32 accumulator in TMEM + fp32 DP: FMNMX3 + FADD per cell)", 63.9, 47.3,
+        "f32 (DP scan; local costs from f16 tensor-core products accumulated in f32; winners refined in f64)"),
+    3: ("k_dtw_scan (fp32 CUDA-core scan)", 63.9, 47.3, "f32 (winners refined in f64)"),
+}
 
 
 def config_dict(args):
@@ -358,12 +365,12 @@ def run_match(args):
         else:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg = algorithmic_bytes(doff, qoff, s0, s1)
-        tc = os.environ.get("SS_DTW_TC", "1") != "0"
-        scan_kernel = "k_dtw_scan_tc (tcgen05 fp16 cost matrix in TMEM + CUDA-core DP)" if tc else "k_dtw_scan (fp32)"
+        kind = shard.last_scan_kind
+        scan_kernel, alu_peak, band_ceiling, dtype = SCAN_KERNELS.get(kind, SCAN_KERNELS[3])
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "dtw_scan_traffic.json")
         if os.path.exists(tp) and world == 1 and args.nd == ND and args.nq == NQ:
-            tj = json.load(open(tp)).get("tc" if tc else "fp32", {})
+            tj = json.load(open(tp)).get({1: "h2", 2: "tc"}.get(kind, "fp32"), {})
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         sm_mhz = ((clocks or {}).get("sm_mhz") or 1965.0)
         sms = 148.0
@@ -380,7 +387,7 @@ def run_match(args):
             "metric": "dtw_cell_updates_per_s", "value": total_cells / (ms_step * 1e-3), "unit": "cells/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (DP scan; local costs from f16 tensor-core products accumulated in f32; winners refined in f64)", "data": "synthetic",
+            "dtype": dtype, "data": "synthetic",
             "config": config_dict(args),
             "parallelism": "dictionary sharded x%d inside the library: queries 1/N per GPU over PCIe + NVLink all-gather, one ncclAllGather of the "
                            "per-shard top-k, merge on every rank" % world,
@@ -391,13 +398,14 @@ def run_match(args):
                     "queries_per_s": nq / (ms_e2e * 1e-3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "issue", "kernel": scan_kernel, "achieved": cells_clk_sm, "peak": ALU_FMNMX3_LANES_PER_CLK_SM,
-                         "unit": "DP cells/clk/SM", "frac": (cells_clk_sm / ALU_FMNMX3_LANES_PER_CLK_SM) if cells_clk_sm else None,
+            "roofline": {"bound": "issue", "kernel": scan_kernel, "achieved": cells_clk_sm, "peak": alu_peak,
+                         "unit": "DP cells/clk/SM", "frac": (cells_clk_sm / alu_peak) if cells_clk_sm else None,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": "measured on B200: the ALU pipe issues FMNMX3 (one per DP cell) at 63.9 lanes/clk/SM (tools/microbench_band2.cu, "
-                                        "profiles/r2_microbench_band2.log); SM clock = median sampled under load",
-                         "band_ceiling": BAND_CEILING_CELLS_PER_CLK_SM,
-                         "frac_of_band_ceiling": (cells_clk_sm / BAND_CEILING_CELLS_PER_CLK_SM) if cells_clk_sm else None,
+                         "peak_source": "measured on B200: every DP cell needs one three-input min on the ALU pipe, which issues FMNMX3 (1 cell) / VHMNMX "
+                                        "(2 cells) at 63.9 lanes/clk/SM (tools/microbench_band2.cu, profiles/r2_microbench_band2.log); SM clock = median "
+                                        "sampled under load",
+                         "band_ceiling": band_ceiling,
+                         "frac_of_band_ceiling": (cells_clk_sm / band_ceiling) if cells_clk_sm else None,
                          "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step if ms_step else None,
                          "cells_per_s_kernel": shard_cells / (scan_ms * 1e-3) if scan_ms > 0 else None,
                          "effective_hbm_gbs": alg / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,

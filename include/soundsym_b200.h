@@ -177,6 +177,9 @@ int ss_queries_invalidate(ss_queries* q);
 /* device time of the dominant kernel (DTW scan / cosine scan) of the last ss_dict_match*(…), measured with CUDA events
  * on the ctx stream; synchronises the stream. Returns a negative value if no match has run. */
 double ss_dict_last_scan_ms(ss_dict* dict);
+/* which kernel scanned the dictionary in the last match (its first stage): 1 = packed-half tensor-core scan (k_dtw_scan_h2), 2 = fp32-DP
+ * tensor-core scan (k_dtw_scan_tc), 3 = fp32 CUDA-core scan (k_dtw_scan: a segment or query longer than 32 frames), 4 = cosine-ref */
+int ss_dict_last_scan_kind(const ss_dict* dict);
 /* DP cells / similarity products the last ss_dict_match*(…) evaluated (sum over pairs of Lq*Ld, resp. of min(Kq,Kd)) */
 uint64_t ss_dict_last_work(const ss_dict* dict);
 /* SS_DTW only: number of queries of the last match whose exact top-k could not be certified from the fp32 scan's

@@ -19,7 +19,7 @@ SYMBOLS = [
     "ss_version", "ss_ctx_create", "ss_ctx_destroy", "ss_last_error", "ss_ctx_stream", "ss_ctx_sync", "ss_ctx_device",
     "ss_ctx_launch_count", "ss_frame_count", "ss_decode_pcm", "ss_sound_analyze", "ss_sound_analyze_pcm", "ss_sound_analyze_batch", "ss_mfcc", "ss_max_power", "ss_mfcc_dev",
     "ss_symbols", "ss_gmm_train", "ss_vote_split", "ss_partition", "ss_dict_create", "ss_dict_destroy", "ss_dict_len", "ss_dict_match",
-    "ss_queries_create", "ss_queries_destroy", "ss_dict_match_dev", "ss_topk_merge_dev", "ss_dict_last_work",
+    "ss_queries_create", "ss_queries_destroy", "ss_dict_match_dev", "ss_topk_merge_dev", "ss_dict_last_work", "ss_dict_last_scan_kind",
     "ss_dict_last_uncertified", "ss_dict_last_tc_fallback", "ss_dict_last_exhaustive", "ss_queries_invalidate", "ss_dict_last_scan_ms", "ss_resynth", "ss_sequence_distances", "ss_dict_debug_tc_scan", "ss_dict_debug_h2_scan", "ss_dict_set_scan", "ss_dict_match_finish",
     "ss_shard_bounds", "ss_comm_unique_id", "ss_comm_create", "ss_comm_create_all", "ss_comm_destroy", "ss_comm_rank", "ss_comm_nranks",
     "ss_queries_create_sharded", "ss_dict_match_sharded_dev", "ss_dict_match_sharded", "ss_dict_create_sharded", "ss_sharded_dict_match",
@@ -81,6 +81,7 @@ def load():
     L.ss_dict_match_dev.argtypes = [vp, vp, i, vp, i, vp, vp]
     L.ss_topk_merge_dev.argtypes = [vp, vp, vp, i, sz, i, vp, vp]
     L.ss_dict_last_work.argtypes = [vp]
+    L.ss_dict_last_scan_kind.argtypes = [vp]
     L.ss_dict_last_work.restype = u64
     L.ss_dict_last_uncertified.argtypes = [vp]
     L.ss_dict_last_uncertified.restype = u64

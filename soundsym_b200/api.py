@@ -276,6 +276,10 @@ class DeviceDictionary:
         self.ctx.check(self.ctx.lib.ss_dict_set_scan(self.h, int(first_stage)))
 
     @property
+    def last_scan_kind(self):
+        return int(self.ctx.lib.ss_dict_last_scan_kind(self.h))
+
+    @property
     def last_work(self):
         return int(self.ctx.lib.ss_dict_last_work(self.h))
 

@@ -184,6 +184,7 @@ void ss_dict_destroy(ss_dict* d) {
 }
 size_t ss_dict_len(const ss_dict* d) { return d ? d->nseg : 0; }
 uint64_t ss_dict_last_work(const ss_dict* d) { return d ? d->last_work : 0; }
+int ss_dict_last_scan_kind(const ss_dict* d) { return d ? d->last_scan_kind : 0; }
 
 int ss_dict_match_finish(ss_dict* d) {
     if (!d) return set_error(nullptr, SS_ERR_INVALID, "dict is NULL");
@@ -257,6 +258,7 @@ int ss_dict_match_dev(ss_dict* d, ss_queries* q, int mode, const double* d_targe
     if (mode == SS_COSINE_REF) {
         if (k != 1) return set_error(ctx, SS_ERR_INVALID, "SS_COSINE_REF returns one match per query (k must be 1, got %d)", k);
         SS_TRY(dtw_match_finish(d));  // a pending SS_DTW match shares the dictionary's workspaces
+        d->last_scan_kind = 4;
         return cosine_match_dev(d, q, d_targets, d_out_idx, d_out_dist);
     }
     if (mode == SS_DTW) return dtw_match_dev(d, q, k, d_out_idx, d_out_dist);

@@ -564,7 +564,11 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
     bool used = false;
     SS_TRY(dtw_h2_match_dev(d, q, k, d_out_idx, d_out_dist, &used));                 // packed-half tensor-core scan
     d->pending.h2 = used;
-    if (!used) SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));      // fp32-DP tensor-core scan
+    d->last_scan_kind = used ? 1 : 0;
+    if (!used) {
+        SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));  // fp32-DP tensor-core scan
+        d->last_scan_kind = used ? 2 : 3;
+    }
     if (!used) SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr));
     SS_TRY(post_counters(d));
     d->pending.active = true;

@@ -63,6 +63,7 @@ struct ss_dict {
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;  // around the dominant kernel of the last match
     bool scan_timed = false;
     bool in_fallback = false;  // set while dtw_match_finish runs later stages
+    int last_scan_kind = 0;    // first-stage scan of the last match: 1 packed-half tensor-core, 2 fp32-DP tensor-core, 3 fp32 CUDA-core, 4 cosine-ref
     // tensor-core scan (dtw_tc.cu): fp16 UMMA tiles of 4 segment slots x 32 columns, segments sorted by length
     bool tc_ready = false;
     uint64_t tc_serial = 0;                  // identifies this build of the tiles (query A blocks are keyed on it)
