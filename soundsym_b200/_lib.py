@@ -42,6 +42,19 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise OSError("libsoundsym_b200.so is not built: run `python -m soundsym_b200.build` (needs nvcc). "
                       "There is no CPU fallback.")
+    if "SS_NCCL_LIB" not in os.environ:
+        # the multi-GPU entry points bind NCCL at run time: point them at the copy PyTorch ships (if there is one), so that
+        # whichever of {this library, torch} touches NCCL first, the process ends up with the same libnccl.so.2
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+                cand = os.path.join(base, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["SS_NCCL_LIB"] = cand
+                    break
+        except Exception:
+            pass
     L = C.CDLL(LIB_PATH)
     vp, sz, u64, u32, dbl, i = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_double, C.c_int
     P = C.POINTER

@@ -8,8 +8,9 @@
 //   ss_comm_create        one rank per process (torchrun / MPI style; the caller ships the 128-byte id to the other ranks)
 //   ss_dict_create_sharded / ss_sharded_dict_match   one process, one worker thread per GPU (ncclCommInitAll) - what a
 //                         Rust SoundDictionary bound to this library calls: same signature as the single-GPU match.
-// NCCL is bound at run time with dlopen("libnccl.so.2") (the copy PyTorch has already mapped, or the system one): the
-// library has no link-time dependency on it and single-GPU users never load it.
+// NCCL is bound at run time with dlopen (the copy already mapped in the process, else $SS_NCCL_LIB - the Python loader points
+// it at the one PyTorch ships - else the system libnccl.so.2): the library has no link-time dependency on it and single-GPU
+// users never load it.
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only; every call goes through the table below
 
@@ -39,10 +40,17 @@ static const NcclApi* nccl_api(std::string* err) {
     std::lock_guard<std::mutex> lock(mu);
     if (!tried) {
         tried = true;
-        void* h = nullptr;
+        // 1. a copy that is already mapped (PyTorch's bundled one, if torch was imported first); 2. $SS_NCCL_LIB (the Python
+        // loader points it at the bundled copy, so that a later `import torch` finds the NCCL it was built against under the
+        // same soname); 3. the system library
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) {
+            const char* env = getenv("SS_NCCL_LIB");
+            if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+        }
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (h) break;
+            h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
         }
         if (!h) {
             why = std::string("cannot load NCCL: ") + (dlerror() ? dlerror() : "libnccl.so.2 not found");

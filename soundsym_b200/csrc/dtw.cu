@@ -384,7 +384,7 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 int dtw_tc_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used);
-int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used);
+int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used, int kp_override = 0);
 int dtw_exhaustive_match(ss_dict* d, ss_queries* q, int k, const std::vector<uint32_t>& subset, uint32_t* d_out_idx, double* d_out_dist);
 }
 
@@ -624,13 +624,28 @@ __global__ void k_scatter_topk(const uint32_t* __restrict__ sub_idx, const doubl
 }
 
 // stages 1b (fp32-DP tensor-core scan, if it applies), 2 and 3 on a whole batch, synchronously; results are exact on return
-static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, uint64_t* n_exhaustive) {
+static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, uint64_t* n_exhaustive,
+                                      bool allow_h2) {
     ss_ctx* ctx = d->ctx;
     SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
     SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
     bool used = false;
     std::vector<uint32_t> subset;
     TraceTimer tt(ctx);
+    // 1a'. the packed-half scan once more with 32 candidates per query: the queries that reach this point had more than 8
+    // segments inside the filter's margin; almost all of them have fewer than 32 (one group of 128 lanes: ~0.1 - 0.5 ms)
+    if (allow_h2) {
+        SS_TRY(dtw_h2_match_dev(d, q, k, d_out_idx, d_out_dist, &used, 32));
+        if (used) {
+            SS_TRY(post_counters(d));
+            SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
+            tt.lap("  packed-half stage, 32 candidates");
+            if (dtw_trace()) fprintf(stderr, "[ss dtw trace]   -> %llu of %zu still uncertified\n", d->h_counters[0], q->nq);
+            if (!d->h_counters[0]) return SS_OK;
+            SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
+            used = false;
+        }
+    }
     SS_TRY(dtw_tc_match_dev(d, q, k, d_out_idx, d_out_dist, &used));
     if (used) {
         SS_TRY(post_counters(d));
@@ -677,7 +692,8 @@ static int dtw_rerun_subset(ss_dict* d, ss_queries* q, int k, const std::vector<
     SS_CUDA(ctx, d->d_sub_idx.reserve(ns * (size_t)k));
     SS_CUDA(ctx, d->d_sub_dist.reserve(ns * (size_t)k));
     const uint64_t work = d->last_work;  // the stages below account their own (partial) work: keep the whole match's figure
-    SS_TRY(dtw_match_remaining_stages(d, sub, k, d->d_sub_idx.p, d->d_sub_dist.p, &d->last_exhaustive));
+    // (with k > 2 the first pass already kept 32 candidates: straight to the fp32-DP tensor-core scan)
+    SS_TRY(dtw_match_remaining_stages(d, sub, k, d->d_sub_idx.p, d->d_sub_dist.p, &d->last_exhaustive, /*allow_h2=*/k <= 2));
     d->last_work = work;
     tt.lap("rerun: remaining stages");
     k_scatter_topk<<<ceil_div((long long)ns * k, 128), 128, 0, ctx->stream>>>(d->d_sub_idx.p, d->d_sub_dist.p, d->d_sub_ids.p, (uint32_t)ns, k, d_out_idx,

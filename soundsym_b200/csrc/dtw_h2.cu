@@ -610,7 +610,13 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
         return e ? std::max(1, atoi(e)) : 16;
     }();
     const uint32_t nslots = q->tc_ngroups * kTcM;
-    if (d->h2_slice_for_groups != q->tc_ngroups) {
+    if (d->h2_slices.size() > 64 && !d->h2_slices.count(q->tc_ngroups)) {  // (many different batch sizes: start over)
+        SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        d->h2_slices.clear();
+    }
+    std::unique_ptr<ss_dict::H2Slices>& sl = d->h2_slices[q->tc_ngroups];
+    if (!sl) {
+        sl.reset(new ss_dict::H2Slices());
         // about `waves` CTAs per SM, but never slices of fewer than ~12 tiles: a small batch (nq = 1: one group) would
         // otherwise pay a CTA's fixed cost (TMEM allocation, the A-block copy, list merge) two thousand times
         const uint32_t want = std::max<uint32_t>(1, std::min<uint32_t>(((uint32_t)ctx->sm_count * waves + q->tc_ngroups - 1) / q->tc_ngroups,
@@ -620,19 +626,18 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
         for (uint32_t f : d->h_h2_tile_cost) total += f;
         const uint64_t per = std::max<uint64_t>(1, (total + want - 1) / want);
         for (int kind = 0; kind < 3; kind++) {
-            d->h2_kind_slice[kind] = (uint32_t)st.size();
+            sl->kind_slice[kind] = (uint32_t)st.size();
             uint64_t acc = per;  // forces a slice start at the first tile of the kind
             for (uint32_t t = d->h2_first_tile[kind]; t < d->h2_first_tile[kind + 1]; t++) {
                 if (acc >= per) st.push_back(t), acc = 0;
                 acc += d->h_h2_tile_cost[t];
             }
         }
-        d->h2_kind_slice[3] = (uint32_t)st.size();
+        sl->kind_slice[3] = (uint32_t)st.size();
         st.push_back(d->h2_ntiles);
-        SS_TRY(upload(ctx, d->d_h2_slice_tile, st.data(), st.size()));
-        d->h2_slice_for_groups = q->tc_ngroups;
+        SS_TRY(upload(ctx, sl->d_slice_tile, st.data(), st.size()));
     }
-    const uint32_t nslices = d->h2_kind_slice[3];
+    const uint32_t nslices = sl->kind_slice[3];
     SS_CUDA(ctx, d->d_tc_partial.reserve((size_t)nslices * nslots * kp));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslots * kp));
     SS_CUDA(ctx, d->d_cand_adist.reserve((size_t)nslots * kp));
@@ -648,7 +653,7 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     p.ngroups = q->tc_ngroups;
     p.tiles = reinterpret_cast<const unsigned char*>(d->d_h2_tiles.p);
     p.desc = d->d_h2_desc.p;
-    p.slice_tile = d->d_h2_slice_tile.p;
+    p.slice_tile = sl->d_slice_tile.p;
     p.nslices = nslices;
     p.slice_begin = 0;
     p.partial = d->d_tc_partial.p;
@@ -659,7 +664,7 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     p.thr = d->d_h2_thr.p;
     p.dbg = nullptr;
     p.dbg_nseg = 0;
-    for (int i = 0; i < 4; i++) plan->kind_begin[i] = d->h2_kind_slice[i];
+    for (int i = 0; i < 4; i++) plan->kind_begin[i] = sl->kind_slice[i];
     plan->nslots = nslots;
     plan->smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kH2DpThreads * 8 + 1024;
     return SS_OK;
@@ -688,7 +693,8 @@ static bool h2_enabled() {
 // eta of the bound (true units, per normalised distance): fp16 subnormal roundings of the S-scaled operands and sums
 static double h2_eta(const ss_dict* d) { return (13.0 * (double)d->h2_bmax + 4.0) * 5.9604644775390625e-08 /* 2^-24 */ / (double)d->h2_s; }
 
-int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used) {
+// kp_override > 0: candidates kept per query (the re-run of the queries a first pass could not certify uses 32)
+int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used, int kp_override) {
     ss_ctx* ctx = d->ctx;
     *used = false;
     if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
@@ -702,17 +708,19 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
         const int v = e ? atoi(e) : 8;
         return v == 16 || v == 32 ? v : 8;
     }();
-    const int kp = k <= 2 ? kp_small : 32;
+    const int kp = kp_override > 0 ? kp_override : (k <= 2 ? kp_small : 32);
     d->last_work = d->total_frames * q->total_frames;
     d->last_uncertified = 0;
     H2Plan plan;
     SS_TRY(h2_plan(d, q, kp, &plan));
-    SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
+    if (!d->in_fallback) SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     if (kp == 8) SS_TRY((h2_launch_all<8, false>(ctx, plan)));
     else if (kp == 16) SS_TRY((h2_launch_all<16, false>(ctx, plan)));
     else SS_TRY((h2_launch_all<32, false>(ctx, plan)));
-    SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
-    d->scan_timed = true;
+    if (!d->in_fallback) {  // a fallback re-run keeps the first pass's scan time
+        SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
+        d->scan_timed = true;
+    }
     if (kp == 8) k_tc_merge<8><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     else if (kp == 16) k_tc_merge<16><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     else k_tc_merge<32><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);

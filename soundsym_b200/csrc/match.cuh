@@ -1,5 +1,8 @@
 // match.cuh — HBM-resident dictionary / query-batch handles shared by the DTW (dtw.cu) and cosine-ref (cosine.cu) matchers.
 #pragma once
+#include <map>
+#include <memory>
+
 #include "common.cuh"
 
 namespace ss {
@@ -80,15 +83,19 @@ struct ss_dict {
     bool h2_ready = false;
     uint32_t h2_ntiles = 0;
     uint32_t h2_first_tile[4] = {0, 0, 0, 0};   // first tile of the kinds NB = 1, 2, 4 (launch order) and the total
-    uint32_t h2_kind_slice[4] = {0, 0, 0, 0};   // the same for the cached slice table
-    uint32_t h2_slice_for_groups = 0xFFFFFFFFu;
+    // slice tables of the packed-half scan, cached per number of query groups (the main batch and the one-group re-run of
+    // its uncertified queries alternate within a match)
+    struct H2Slices {
+        uint32_t kind_slice[4] = {0, 0, 0, 0};  // first slice of the kinds NB = 1, 2, 4 and the total
+        ss::DevBuf<uint32_t> d_slice_tile;
+    };
+    std::map<uint32_t, std::unique_ptr<H2Slices>> h2_slices;
     float h2_s = 1.f;                           // power-of-two cost scale S
     float h2_bmax = 0.f;                        // max |fp16(b - mu)| (bound's eta)
     double h2_bound_inv_s = 1.0;
     std::vector<uint32_t> h_h2_tile_cost;
     ss::DevBuf<uint16_t> d_h2_tiles;
     ss::DevBuf<int4> d_h2_desc;
-    ss::DevBuf<uint32_t> d_h2_slice_tile;
     ss::DevBuf<unsigned long long> d_h2_thr;   // per query slot: running bound on the global KP-th key (dtw_h2.cu)
     int scan_pref = 0;  // test / A-B hook (ss_dict_set_scan): 0 = packed-half scan first, 1 = start at the fp32 tensor-core scan, 2 = fp32 CUDA-core scan
     // the last SS_DTW match is asynchronous up to its fallback decision: ss::dtw_match_finish waits for ev_done, reads the
