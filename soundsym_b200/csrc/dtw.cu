@@ -694,7 +694,10 @@ static int dtw_rerun_subset(ss_dict* d, ss_queries* q, int k, const std::vector<
     const uint64_t work = d->last_work;  // the stages below account their own (partial) work: keep the whole match's figure
     // (a second packed-half pass with 32 candidates certifies all of them too, but measured slower than going straight to the
     // fp32-DP tensor-core scan: 1.95 vs 1.52 ms for the 47 queries of config 4 - one group of 128 lanes padded to 32 rows)
-    SS_TRY(dtw_match_remaining_stages(d, sub, k, d->d_sub_idx.p, d->d_sub_dist.p, &d->last_exhaustive, /*allow_h2=*/false));
+    // Sequences of more than 32 frames have no fp32-DP tensor-core scan: there the second packed-half pass (32 per-pair
+    // lower-bound keys per query) stands between the first pass and the CUDA-core scan.
+    const bool long_seqs = d->max_len > 32 || sub->max_len > 32;
+    SS_TRY(dtw_match_remaining_stages(d, sub, k, d->d_sub_idx.p, d->d_sub_dist.p, &d->last_exhaustive, /*allow_h2=*/long_seqs));
     d->last_work = work;
     tt.lap("rerun: remaining stages");
     k_scatter_topk<<<ceil_div((long long)ns * k, 128), 128, 0, ctx->stream>>>(d->d_sub_idx.p, d->d_sub_dist.p, d->d_sub_ids.p, (uint32_t)ns, k, d_out_idx,

@@ -45,7 +45,10 @@ constexpr int kH2SlotCols = 64;                       // TMEM columns per slot a
 constexpr int kH2DpWarps = 4 * kH2Slots;              // 8
 constexpr int kH2DpThreads = kH2DpWarps * 32;         // 256
 constexpr int kH2Threads = (kH2DpWarps + 1) * 32;     // 288
-constexpr int kH2DescInt4 = 3;                        // per (tile, slot): {seg 0..3}, {seg 4..7}, {len 0..3 bytes, len 4..7 bytes, ng, 0}
+constexpr int kH2DescInt4 = 4;                        // per (tile, slot): {seg 0..3}, {seg 4..7}, {columns 0..3 bytes, 4..7 bytes, ng, flags | strip << 8}, {whole length of seg 0..3}
+constexpr int kH2In = 1, kH2Out = 2;                   // strip flags: boundary column comes in from / goes out to the neighbouring strip
+constexpr int kH2ARing = 32;                          // rows of the A block resident at a time when a query group is longer (4 pieces of 8)
+constexpr int kH2MaxLong = 2048;                      // longest segment / query the strip kernel takes (boundary scratch: %nsmid x rows x 1 KB)
 
 struct H2Params {
     const unsigned char* a_blocks;
@@ -66,6 +69,9 @@ struct H2Params {
     unsigned long long* thr;
     float* dbg;                   // DBG instantiation only: [ngroups * 128][dbg_nseg]
     uint32_t dbg_nseg;
+    __half2* bnd;                 // LONG kernel: [%nsmid][bnd_rows][256] boundary columns between the strips of a long segment
+    uint32_t bnd_rows;
+    float eta;                    // LONG kernel: subtracted from a pair's scan distance before its key is deflated (bound_mode 3)
 };
 
 // ---- packed TMEM loads: N registers <- 2 N adjacent columns ---------------------------------------------------------------
@@ -170,6 +176,38 @@ __device__ __forceinline__ void h2_band(const __half2 (&tm0)[4 * NG], const __ha
         if (j >= 4 * (NG - 1)) c0l[j - 4 * (NG - 1)] = c0;
     }
 }
+// the same band for one 32-column STRIP of a longer segment: the carries start from the previous strip's last column
+// (l0 = D(i, -1), dg0 = D(i-1, -1), l1 = D(i+1, -1)) and the strip's own last column comes back in o0 / o1
+template <int NG>
+__device__ __forceinline__ void h2_band_io(const __half2 (&tm0)[4 * NG], const __half2 (&tm1)[4 * NG], __half2 (&d)[4 * NG], __half2 l0, __half2 dg0,
+                                           __half2 l1, __half2 (&c0l)[4], __half2& o0, __half2& o1) {
+    __half2 left0 = l0, diag0 = dg0, left1 = l1;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const __half2 up0 = d[j];
+        const __half2 c0 = __hadd2(tm0[j], h2_min3(left0, up0, diag0));
+        const __half2 c1 = __hadd2(tm1[j], h2_min3(left1, c0, left0));
+        diag0 = up0;
+        left0 = c0;
+        left1 = c1;
+        d[j] = c1;
+        if (j >= 4 * (NG - 1)) c0l[j - 4 * (NG - 1)] = c0;
+    }
+    o0 = left0, o1 = left1;
+}
+template <int NG>
+__device__ __forceinline__ void h2_band_row_io(const __half2 (&tm)[4 * NG], __half2 (&d)[4 * NG], __half2 l0, __half2 dg0, __half2& o0) {
+    __half2 left = l0, diag = dg0;
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) {
+        const __half2 up = d[j];
+        const __half2 cur = __hadd2(tm[j], h2_min3(left, up, diag));
+        diag = up;
+        left = cur;
+        d[j] = cur;
+    }
+    o0 = left;
+}
 template <int NG>
 __device__ __forceinline__ void h2_band_row(const __half2 (&tm)[4 * NG], __half2 (&d)[4 * NG], __half2 dinit) {
     __half2 left = h2_inf(), diag = dinit;
@@ -273,6 +311,61 @@ __device__ __forceinline__ void h2_tile(uint32_t L, uint32_t lmin, uint32_t Lm, 
             const int ra = (h2_len_of(sc, 2 * b) - 1) & 3, rb = (h2_len_of(sc, 2 * b + 1) - 1) & 3;
             const __half2 e = h2_combine(h2_pick4(&d[b][4 * (NG - 1)], ra), h2_pick4(&d[b][4 * (NG - 1)], rb));
             res[b] = (L == Lm) ? e : res[b];
+        }
+    }
+}
+
+// One 32-column strip of two long segments for one thread. IN: the strip continues a previous one (boundary column read
+// from `bnd`, [row][256 threads]); OUT: another strip follows (this strip's last column written back in place, nothing
+// captured). The LAST strip (IN && !OUT) captures D(Lm - 1, len - 1) like a whole-segment tile.
+template <int NG, bool IN, bool OUT>
+__device__ __forceinline__ void h2_tile_strip(uint32_t L, uint32_t lmin, uint32_t Lm, const int4& sc, TcCursor& cur, __half2* bnd, __half2& res) {
+    constexpr uint32_t kStride = kH2DpThreads;
+    __half2 d[4 * NG];
+#pragma unroll
+    for (int j = 0; j < 4 * NG; j++) d[j] = h2_inf();
+    res = h2_inf();
+    __half2 prev_b = IN ? h2_inf() : h2_zero();  // D(i - 1, -1): +inf above the first row of a later strip, the virtual 0 of D(-1, -1) in the first
+    const uint32_t nfull = L >> 1;
+    const uint32_t ncap = OUT ? nfull : min((lmin - 1) >> 1, nfull);
+    const int ra = (h2_len_of(sc, 0) - 1) & 3, rb = (h2_len_of(sc, 1) - 1) & 3;
+#pragma unroll 1
+    for (uint32_t st = 0; st < nfull; st++) {
+        __half2 b0 = h2_inf(), b1 = h2_inf();
+        if (IN) b0 = bnd[(size_t)(2 * st) * kStride], b1 = bnd[(size_t)(2 * st + 1) * kStride];  // issued ahead of the TMEM wait
+        cur.wait();
+        const uint32_t taddr = cur.taddr;
+        __half2 tm0[4 * NG], tm1[4 * NG], c0l[4], o0, o1;
+        h2_ld_row<NG>(taddr, tm0);
+        h2_ld_row<NG>(taddr + kTcN, tm1);
+        tc_wait_ld();
+        cur.release();
+        h2_band_io<NG>(tm0, tm1, d, b0, prev_b, b1, c0l, o0, o1);
+        prev_b = IN ? b1 : h2_inf();
+        if (OUT) {
+            bnd[(size_t)(2 * st) * kStride] = o0;
+            bnd[(size_t)(2 * st + 1) * kStride] = o1;
+        } else if (st >= ncap) {
+            const bool end0 = 2 * st + 1 == Lm, end1 = 2 * st + 2 == Lm;
+            const __half2 e0 = h2_combine(h2_pick4(c0l, ra), h2_pick4(c0l, rb));
+            const __half2 e1 = h2_combine(h2_pick4(&d[4 * (NG - 1)], ra), h2_pick4(&d[4 * (NG - 1)], rb));
+            res = end0 ? e0 : (end1 ? e1 : res);
+        }
+    }
+    if (L & 1) {
+        __half2 b0 = h2_inf();
+        if (IN) b0 = bnd[(size_t)(L - 1) * kStride];
+        cur.wait();
+        __half2 tm0[4 * NG], o0;
+        h2_ld_row<NG>(cur.taddr, tm0);
+        tc_wait_ld();
+        cur.release();
+        h2_band_row_io<NG>(tm0, d, b0, prev_b, o0);
+        if (OUT) {
+            bnd[(size_t)(L - 1) * kStride] = o0;
+        } else {
+            const __half2 e = h2_combine(h2_pick4(&d[4 * (NG - 1)], ra), h2_pick4(&d[4 * (NG - 1)], rb));
+            res = (L == Lm) ? e : res;
         }
     }
 }
@@ -437,6 +530,224 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
     }
 }
 
+// ---- the same scan for LONG sequences: dictionary segments of more than 32 frames are cut into 32-column strips (tiles of the
+// NB = 1 kind, consecutive in the tile list) whose boundary column travels through a per-SM scratch in global memory, and a
+// query group of more than 32 frames streams its A block through a ring of 4 x 8 rows. Separate kernel: the <= 32 x <= 32 case
+// (the headline) keeps its own, simpler code.
+template <int KP, int NB, bool DBG = false>
+__global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2_long(const H2Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    // [A ring: 32 rows x 4 KB = 4 pieces of 8 rows][B ring: 4 x 4 KB][barriers][candidate lists], 128-byte aligned
+    unsigned char* smem = smem_raw + ((128u - (s32(smem_raw) & 127u)) & 127u);
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + (size_t)kH2ARing * kTcATileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * kTcBTileBytes);
+    uint64_t* a_full = bars;        // [4]
+    uint64_t* a_empty = bars + 4;   // [4]
+    uint64_t* b_full = bars + 8;    // [4]
+    uint64_t* b_empty = bars + 12;  // [4]
+    uint64_t* t_full = bars + 16;
+    uint64_t* t_empty = bars + 18;  // = t_full + 16 bytes (TcCursor::release)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x / p.nslices, slice = p.slice_begin + blockIdx.x % p.nslices;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next tile kind's launch may start filling SMs
+    const uint32_t glen = p.group_len[g];
+    const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;
+    const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
+    const uint32_t ntiles = t1 - t0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; s++) mb_init(&a_full[s], 1), mb_init(&a_empty[s], 1);
+        for (int s = 0; s < kTcStages; s++) mb_init(&b_full[s], 1), mb_init(&b_empty[s], 1);
+        for (int s = 0; s < 2; s++) mb_init(&t_full[s], 1), mb_init(&t_empty[s], kH2DpWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kH2DpWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == kH2DpWarps) {
+        if (lane == 0 && ntiles) {
+            // ---- producer: TMA + MMA issue. The group's A block (L rows) lives in a ring of 4 pieces of 8 rows. Up to 32 rows it
+            // is loaded once and stays; a longer group STREAMS it: every tile consumes pieces 0 .. npieces - 1 in order, the
+            // piece sequence runs on across tiles (n = tile * npieces + piece -> ring slot n % 4), and a slot is refilled one
+            // piece after its MMAs were committed (their completion arrives on a_empty[slot]) -----------------------------------
+            const uint32_t bars_s = s32(bars), sA_s = s32(sA), sB_s = s32(sB);
+            const uint32_t a_full_s = bars_s, a_empty_s = bars_s + 32, b_full_s = bars_s + 64, b_empty_s = bars_s + 96, t_full_s = bars_s + 128,
+                           t_empty_s = bars_s + 144;
+            const uint32_t npieces = (L + 7) >> 3;
+            const bool streaming = npieces > 4;
+            const uint32_t total_pieces = streaming ? ntiles * npieces : npieces;
+            const unsigned char* a_src = p.a_blocks + p.group_off[g];
+            auto load_piece = [&](uint32_t n) {  // sequence number n -> piece n % npieces into ring slot
+                const uint32_t pc = n % npieces, slot = streaming ? (n & 3u) : pc;
+                const uint32_t rows = min(8u, L - 8u * pc);
+                mbs_expect_tx(a_full_s + 8 * slot, rows * kTcATileBytes);
+                tmas_g2s(sA_s + slot * 8 * kTcATileBytes, a_src + (size_t)pc * 8 * kTcATileBytes, rows * kTcATileBytes, a_full_s + 8 * slot);
+            };
+            for (uint32_t n = 0; n < total_pieces && n < 4; n++) load_piece(n);
+            const unsigned char* tile_src = p.tiles + (size_t)t0 * kTcBTileBytes;
+            for (uint32_t n = 0; n < ntiles && n < (uint32_t)kTcStages; n++) {
+                mbs_expect_tx(b_full_s + 8 * n, kTcBTileBytes);
+                tmas_g2s(sB_s + n * kTcBTileBytes, tile_src + (size_t)n * kTcBTileBytes, kTcBTileBytes, b_full_s + 8 * n);
+            }
+            tile_src += (size_t)kTcStages * kTcBTileBytes;
+            // f16 x f16 -> F16 accumulator (c_format = 0), K-major both, N = 128, M = 128
+            const uint32_t idesc = (0u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+            uint32_t cnt = 0, stage = 0, sphase = 0, use_n = 0;
+            for (uint32_t n = 0; n < ntiles; n++) {
+                mbs_wait_sleep(b_full_s + 8 * stage, sphase);
+                const uint64_t bdesc = tc_smem_desc_s<kTcN>(sB_s + stage * kTcBTileBytes);
+                for (uint32_t pc = 0; pc < npieces; pc++, use_n++) {
+                    const uint32_t slot = streaming ? (use_n & 3u) : pc;
+                    if (streaming && use_n >= 1 && use_n + 3 < total_pieces) {  // refill the slot the previous piece sat in
+                        mbs_wait_sleep(a_empty_s + 8 * ((use_n - 1) & 3u), ((use_n - 1) >> 2) & 1);
+                        load_piece(use_n + 3);
+                    }
+                    if (streaming || n == 0) mbs_wait_sleep(a_full_s + 8 * slot, streaming ? ((use_n >> 2) & 1) : 0u);
+                    const uint64_t adesc0 = tc_smem_desc_s<kTcM>(sA_s + slot * 8 * kTcATileBytes);
+                    const uint32_t rows = min(8u, L - 8u * pc);
+                    for (uint32_t r = 0; r < rows; r += 2, cnt++) {
+                        const uint32_t buf = cnt & 1;
+                        if (cnt >= 2) mbs_wait_sleep(t_empty_s + 8 * buf, ((cnt >> 1) - 1) & 1);
+                        tc_fence_after();
+                        const uint32_t tm = tmem_base + buf * kTcBufCols;
+                        const uint64_t adesc = adesc0 + (uint64_t)r * (kTcATileBytes >> 4);
+                        tc_mma_f16(tm, adesc, bdesc, idesc);
+                        if (r + 1 < rows) tc_mma_f16(tm + kTcN, adesc + (kTcATileBytes >> 4), bdesc, idesc);
+                        tcs_commit(t_full_s + 8 * buf);
+                    }
+                    if (streaming) tcs_commit(a_empty_s + 8 * slot);
+                }
+                tcs_commit(b_empty_s + 8 * stage);
+                if (n + kTcStages < ntiles) {
+                    mbs_wait_sleep(b_empty_s + 8 * stage, sphase);
+                    mbs_expect_tx(b_full_s + 8 * stage, kTcBTileBytes);
+                    tmas_g2s(sB_s + stage * kTcBTileBytes, tile_src, kTcBTileBytes, b_full_s + 8 * stage);
+                    tile_src += kTcBTileBytes;
+                }
+                if (++stage == (uint32_t)kTcStages) stage = 0, sphase ^= 1;
+            }
+        }
+    } else {
+        // ---- DP warps ---------------------------------------------------------------------------------------------------
+        const int q = warp & 3, slot = warp >> 2;
+        const int m = q * 32 + lane;
+        unsigned long long* list = topk + threadIdx.x;  // [KP][256] keys, this thread's column
+#pragma unroll
+        for (int s = 0; s < KP; s++) list[s * kH2DpThreads] = 0xFFFFFFFFFFFFFFFFull;
+        const unsigned long long thr0 = __ldcg(p.thr + g * kTcM + m);  // (L2: other CTAs update it)
+        unsigned long long worst = thr0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * kH2SlotCols;
+        const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
+        TcCursor cur;
+        cur.init(s32(t_full), lane_addr);
+        for (uint32_t n = 0; n < ntiles; n++) {
+            const int4* dp = p.desc + ((size_t)(t0 + n) * kH2Slots + slot) * kH2DescInt4;
+            const int4 sa = __ldg(dp), sb = __ldg(dp + 1), sc = __ldg(dp + 2), sd = __ldg(dp + 3);
+            const int ng = sc.z, flags = sc.w & 3;
+            __half2 res[NB];
+            // every segment of a tile has the same number of 4-column groups: straight-line code over 4 NG registers per band
+            if (NB == 1 && flags != 0) {
+                // a 32-column strip of two segments longer than 32 frames
+                unsigned smid;
+                asm("mov.u32 %0, %%smid;" : "=r"(smid));
+                __half2* bnd = p.bnd + ((size_t)smid * p.bnd_rows) * kH2DpThreads + threadIdx.x;
+                if (flags == kH2Out) h2_tile_strip<8, false, true>(L, lmin, Lm, sc, cur, bnd, res[0]);
+                else if (flags == (kH2In | kH2Out)) h2_tile_strip<8, true, true>(L, lmin, Lm, sc, cur, bnd, res[0]);
+                else {
+                    switch (ng) {
+                        case 1: h2_tile_strip<1, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        case 2: h2_tile_strip<2, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        case 3: h2_tile_strip<3, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        case 4: h2_tile_strip<4, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        case 5: h2_tile_strip<5, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        case 6: h2_tile_strip<6, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        case 7: h2_tile_strip<7, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                        default: h2_tile_strip<8, true, false>(L, lmin, Lm, sc, cur, bnd, res[0]); break;
+                    }
+                }
+            } else if constexpr (NB == 1) {
+                switch (ng) {
+                    case 5: h2_tile<1, 5>(L, lmin, Lm, sc, cur, res); break;
+                    case 6: h2_tile<1, 6>(L, lmin, Lm, sc, cur, res); break;
+                    case 7: h2_tile<1, 7>(L, lmin, Lm, sc, cur, res); break;
+                    default: h2_tile<1, 8>(L, lmin, Lm, sc, cur, res); break;
+                }
+            } else if constexpr (NB == 2) {
+                if (ng == 3) h2_tile<2, 3>(L, lmin, Lm, sc, cur, res);
+                else h2_tile<2, 4>(L, lmin, Lm, sc, cur, res);
+            } else {
+                if (ng == 1) h2_tile<4, 1>(L, lmin, Lm, sc, cur, res);
+                else h2_tile<4, 2>(L, lmin, Lm, sc, cur, res);
+            }
+            if (Lm && !(flags & kH2Out)) {  // (a strip with a successor has no result yet)
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+#pragma unroll
+                    for (int hsel = 0; hsel < 2; hsel++) {
+                        const int e = 2 * b + hsel;
+                        const int seg = h2_seg_of(sa, sb, e);
+                        if (seg >= 0) {
+                            const float v = hsel ? __high2float(res[b]) : __low2float(res[b]);
+                            // D16 / (S (Lq + Ld)); an overflowed path sum stays +inf and is never inserted
+                            // whole length of the segment (a last strip's `columns` field is only its own width)
+                            const int whole = NB == 1 ? (e == 0 ? sd.x : sd.y) : h2_len_of(sc, e);
+                            // The KEY is a lower bound of the pair's rounded-frame distance, not the raw scan value: the
+                            // packed-half roundings can only have inflated D16 by (1 + 2^-11) per cell of the path (header), so
+                            // (scan - eta) (1 + 2^-11)^-(Lq + Ld + 2) <= DTW~ / (Lq + Ld) PER PAIR (7.06e-4 > log2(1 + 2^-11), the
+                            // excess covers the fp32 roundings of this line). A list's worst key w then bounds every dropped
+                            // pair whatever its length (bound_mode 3) - a common factor for the longest segment of the
+                            // dictionary would throw away 20 % for 383 frames.
+                            const float npath = (float)(Lm + (uint32_t)whole);
+                            const float dist = fmaxf(__fdividef(v * p.inv_s, npath) - p.eta, 0.f) * exp2f(-7.06e-4f * (npath + 2.f));
+                            tc_insert<KP, kH2DpThreads>(list, worst, dist, (uint32_t)seg);
+                            worst = worst < thr0 ? worst : thr0;  // (an insertion reloads `worst` from the list's last place)
+                            if constexpr (DBG) p.dbg[(size_t)(g * kTcM + m) * p.dbg_nseg + seg] = dist;
+                        }
+                    }
+                }
+            }
+        }
+        // the two slots' lists of query m (threads m, m + 128) are merged by the slot-0 thread
+        asm volatile("bar.sync 1, %0;" ::"n"(kH2DpThreads) : "memory");
+        if (slot == 0) {
+            const unsigned long long* other = list + kTcM;
+            for (int s = 0; s < KP; s++) {  // ascending: stop at the first key that does not make the cut
+                const unsigned long long key = other[s * kH2DpThreads];
+                if (key >= worst) break;
+                tc_insert_key<KP, kH2DpThreads>(list, worst, key);
+                worst = worst < thr0 ? worst : thr0;
+            }
+            const unsigned long long kept_worst = list[(KP - 1) * kH2DpThreads];
+            if (kept_worst != 0xFFFFFFFFFFFFFFFFull && kept_worst < thr0) atomicMin(p.thr + g * kTcM + m, kept_worst);
+            unsigned long long* out = p.partial + ((size_t)slice * p.ngroups * kTcM + (size_t)g * kTcM + m) * KP;
+#pragma unroll
+            for (int s = 0; s < KP; s++) out[s] = list[s * kH2DpThreads];
+        }
+    }
+    if constexpr (NB != 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // see k_dtw_scan_tc: not complete before the launch ahead is
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kH2DpWarps) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__global__ void k_h2_nsmid(uint32_t* out) {
+    uint32_t n;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(n));
+    *out = n;
+}
+
 // one thread per (tile, TMEM column n): writes row n of the tile's B operand. Slot = n / 64; inside the slot band = column /
 // (64 / NB), and inside the band column 2 t + w is frame t of the band's segment w.
 __global__ void k_h2_dict_tiles(const double* __restrict__ mfcc, const uint64_t* __restrict__ off, int c, const double* __restrict__ mu,
@@ -452,12 +763,13 @@ __global__ void k_h2_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
     const int4 sa = dp[0], sb = dp[1], sc = dp[2];
     const int segs[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
     const int seg = segs[e];
-    const int len = (int)((((e < 4) ? (uint32_t)sc.x : (uint32_t)sc.y) >> (8 * (e & 3))) & 0xFFu);
+    const int len = (int)((((e < 4) ? (uint32_t)sc.x : (uint32_t)sc.y) >> (8 * (e & 3))) & 0xFFu);  // columns of this strip
+    const int strip = sc.w >> 8;  // the tile covers frames 32 strip .. of its segments
     __align__(16) __half row[kTcK];
 #pragma unroll
     for (int k = 0; k < kTcK; k++) row[k] = __float2half_rn(0.f);
     if (seg >= 0 && j < len) {
-        const double* src = mfcc + (off[seg] + j) * c;
+        const double* src = mfcc + (off[seg] + 32 * strip + j) * c;
         float nrm = 0.f;
         for (int k = 0; k < c; k++) {
             const __half h = __float2half_rn((float)(src[k] - mu[k]));
@@ -483,23 +795,70 @@ __global__ void k_h2_dict_tiles(const double* __restrict__ mfcc, const uint64_t*
 int dtw_h2_dict_build(ss_dict* d) {
     ss_ctx* ctx = d->ctx;
     d->h2_ready = false;
-    if (!d->tc_ready) return SS_OK;
+    if (!d->tc_stats_ready || d->max_len > (uint32_t)kH2MaxLong) return SS_OK;  // (longer still: dtw.cu's fp32 scan)
     std::vector<uint32_t> order;
     order.reserve(d->nseg);
     for (size_t s = 0; s < d->nseg; s++)
         if (d->h_off[s + 1] > d->h_off[s]) order.push_back((uint32_t)s);
     auto len_of = [&](uint32_t s) { return (int)(d->h_off[s + 1] - d->h_off[s]); };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len_of(a) > len_of(b); });
-    // tiles: all segments of a tile share ng = ceil(len / 4) (and hence the kind NB: ng 5..8 -> 1 band per thread, 3..4 -> 2,
-    // 1..2 -> 4); a tile holds 2 slots x 2 NB segments. Element e of a slot = band e / 2, half e % 2. Consecutive segments in
-    // length order go to the SAME half-pair first, so the two halves of a register carry nearly equal lengths.
+    // Tiles. A segment of <= 32 frames is one column run; all segments of a tile share ng = ceil(len / 4) (and hence the kind
+    // NB: ng 5..8 -> 1 band per thread, 3..4 -> 2, 1..2 -> 4); a tile holds 2 slots x 2 NB segments. Element e of a slot =
+    // band e / 2, half e % 2; consecutive segments in length order go to the SAME half-pair first, so the two halves of a
+    // register carry nearly equal lengths. A LONGER segment is cut into 32-column strips: four segments with the same
+    // number of strips and the same ng of their last strip form nstrips consecutive NB = 1 tiles (flags: boundary column
+    // in / out), which one CTA processes in order.
     std::vector<int4> desc;
     std::vector<uint8_t> tile_nb;
     d->h_h2_tile_cost.clear();
+    d->h_h2_tile_cont.clear();
     d->h2_first_tile[0] = 0;
+    d->h2_has_strips = false;
+    auto push_tile = [&](int nb, int ng, uint32_t cost, bool cont) {
+        tile_nb.push_back((uint8_t)nb);
+        d->h_h2_tile_cost.push_back(cost);
+        d->h_h2_tile_cont.push_back(cont ? 1 : 0);
+        (void)ng;
+    };
     int cur_kind = 1;
     for (size_t o = 0; o < order.size();) {
-        const int ng = (len_of(order[o]) + 3) >> 2;
+        const int len0 = len_of(order[o]);
+        if (len0 > 32) {
+            // ---- a quad of long segments: equal strip count, equal ng of the last strip ------------------------------------
+            const int nstrips = (len0 + 31) / 32, ngl = ((len0 - 32 * (nstrips - 1)) + 3) >> 2;
+            size_t take = 0;
+            while (take < 4 && o + take < order.size()) {
+                const int l = len_of(order[o + take]);
+                if ((l + 31) / 32 != nstrips || (((l - 32 * (nstrips - 1)) + 3) >> 2) != ngl) break;
+                take++;
+            }
+            for (int st = 0; st < nstrips; st++) {
+                const bool last = st == nstrips - 1;
+                const int flags = (st > 0 ? kH2In : 0) | (!last ? kH2Out : 0);
+                for (int slot = 0; slot < kH2Slots; slot++) {
+                    int segs[2] = {-1, -1}, whole[2] = {0, 0};
+                    uint32_t lens = 0;
+                    for (int e = 0; e < 2; e++) {
+                        const size_t pos = (size_t)slot * 2 + e;
+                        if (pos < take) {
+                            const int l = len_of(order[o + pos]);
+                            segs[e] = (int)order[o + pos];
+                            whole[e] = l;
+                            lens |= (uint32_t)(last ? l - 32 * (nstrips - 1) : 32) << (8 * e);
+                        }
+                    }
+                    desc.push_back(make_int4(segs[0], segs[1], -1, -1));
+                    desc.push_back(make_int4(-1, -1, -1, -1));
+                    desc.push_back(make_int4((int)lens, 0, last ? ngl : 8, flags | (st << 8)));
+                    desc.push_back(make_int4(whole[0], whole[1], 0, 0));
+                }
+                push_tile(1, last ? ngl : 8, 24u + 16u * (uint32_t)(last ? ngl : 8), st > 0);
+            }
+            d->h2_has_strips = true;
+            o += take;
+            continue;
+        }
+        const int ng = (len0 + 3) >> 2;
         const int nb = ng >= 5 ? 1 : (ng >= 3 ? 2 : 4);
         while (cur_kind < nb) {  // kinds in launch order 1, 2, 4
             d->h2_first_tile[cur_kind == 1 ? 1 : 2] = (uint32_t)tile_nb.size();
@@ -509,21 +868,22 @@ int dtw_h2_dict_build(ss_dict* d) {
         size_t take = 0;
         while (take < cap && o + take < order.size() && ((len_of(order[o + take]) + 3) >> 2) == ng) take++;
         for (int slot = 0; slot < kH2Slots; slot++) {
-            int segs[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+            int segs[8] = {-1, -1, -1, -1, -1, -1, -1, -1}, whole[4] = {0, 0, 0, 0};
             uint32_t lens[2] = {0, 0};
             for (int e = 0; e < 2 * nb; e++) {
                 const size_t pos = (size_t)slot * 2 * nb + e;
                 if (pos < take) {
                     segs[e] = (int)order[o + pos];
                     lens[e >> 2] |= (uint32_t)len_of(order[o + pos]) << (8 * (e & 3));
+                    if (e < 4) whole[e] = len_of(order[o + pos]);
                 }
             }
             desc.push_back(make_int4(segs[0], segs[1], segs[2], segs[3]));
             desc.push_back(make_int4(segs[4], segs[5], segs[6], segs[7]));
             desc.push_back(make_int4((int)lens[0], (int)lens[1], ng, 0));
+            desc.push_back(make_int4(whole[0], whole[1], whole[2], whole[3]));
         }
-        tile_nb.push_back((uint8_t)nb);
-        d->h_h2_tile_cost.push_back(24u + 16u * (uint32_t)(nb * ng));
+        push_tile(nb, ng, 24u + 16u * (uint32_t)(nb * ng), false);
         o += take;
     }
     while (cur_kind < 4) {
@@ -533,6 +893,7 @@ int dtw_h2_dict_build(ss_dict* d) {
     d->h2_first_tile[3] = (uint32_t)tile_nb.size();
     const uint32_t ntiles = (uint32_t)tile_nb.size();
     d->h2_ntiles = ntiles;
+    d->h2_slices.clear();
     if (!ntiles) return SS_OK;
     SS_TRY(upload(ctx, d->d_h2_desc, desc.data(), desc.size()));
     DevBuf<uint8_t> d_nb;
@@ -543,14 +904,21 @@ int dtw_h2_dict_build(ss_dict* d) {
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // d_nb is released on return
     // cost scale S: S |b|^2_max <= 4096, so that a path of 64 typical cells stays far below 65504 (an overflow is not an error:
-    // the pair reads +inf and the bound is capped, see the header)
-    float mx[2] = {0, 0};
-    SS_CUDA(ctx, cudaMemcpy(mx, d->d_tc_max_norm.p, sizeof(mx), cudaMemcpyDeviceToHost));
+    // the pair reads +inf and the bound is capped, see the header); longer paths scale it down further
     float S = 1.0f;
-    while (S * mx[0] > 4096.f) S *= 0.5f;
-    while (S * mx[0] < 2048.f && S < 64.f) S *= 2.0f;
+    while (S * d->tc_max_nb > 4096.f) S *= 0.5f;
+    while (S * d->tc_max_nb < 2048.f && S < 64.f) S *= 2.0f;
+    for (uint32_t l = 64; l < 2 * d->max_len && S > 1.0f / 65536.f; l *= 2) S *= 0.5f;
     d->h2_s = S;
-    d->h2_bmax = mx[1];
+    d->h2_bmax = d->tc_max_abs;
+    {   // the strip kernel's boundary scratch has one area per SM id
+        DevBuf<uint32_t> d_n;
+        SS_CUDA(ctx, d_n.reserve(1));
+        k_h2_nsmid<<<1, 1, 0, ctx->stream>>>(d_n.p);
+        SS_LAUNCHED(ctx);
+        SS_CUDA(ctx, cudaMemcpyAsync(&d->h2_nsmid, d_n.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     d->h2_ready = true;
     return SS_OK;
 }
@@ -576,12 +944,13 @@ static int h2_queries_build(ss_dict* d, ss_queries* q) {
     return SS_OK;
 }
 
-template <int KP, int NB, bool DBG = false>
+template <int KP, int NB, bool DBG, bool LONG>
 static int h2_launch_kind(ss_ctx* ctx, H2Params p, uint32_t slice_begin, uint32_t nslices, size_t smem, bool dependent) {
     if (!nslices) return SS_OK;
     p.slice_begin = slice_begin;
     p.nslices = nslices;
-    SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_scan_h2<KP, NB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = LONG ? k_dtw_scan_h2_long<KP, NB, DBG> : k_dtw_scan_h2<KP, NB, DBG>;
+    SS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.ngroups * nslices);
     cfg.blockDim = dim3(kH2Threads);
@@ -592,16 +961,20 @@ static int h2_launch_kind(ss_ctx* ctx, H2Params p, uint32_t slice_begin, uint32_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = dependent ? 1 : 0;
-    SS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_dtw_scan_h2<KP, NB, DBG>, p));
+    SS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p));
     SS_LAUNCHED(ctx);
     return SS_OK;
 }
+
+// eta of the bound (true units, per normalised distance): fp16 subnormal roundings of the S-scaled operands and sums
+static double h2_eta(const ss_dict* d) { return (13.0 * (double)d->h2_bmax + 4.0) * 5.9604644775390625e-08 /* 2^-24 */ / (double)d->h2_s; }
 
 struct H2Plan {
     H2Params p;
     uint32_t kind_begin[4];  // first slice of each kind (1, 2, 4) and the total
     uint32_t nslots;
     size_t smem;
+    bool use_long;  // segments or queries of more than 32 frames: k_dtw_scan_h2_long (strips, streamed A block, deflated keys)
 };
 static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     ss_ctx* ctx = d->ctx;
@@ -629,7 +1002,7 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
             sl->kind_slice[kind] = (uint32_t)st.size();
             uint64_t acc = per;  // forces a slice start at the first tile of the kind
             for (uint32_t t = d->h2_first_tile[kind]; t < d->h2_first_tile[kind + 1]; t++) {
-                if (acc >= per) st.push_back(t), acc = 0;
+                if (acc >= per && !d->h_h2_tile_cont[t]) st.push_back(t), acc = 0;  // (the strips of a long segment stay in one slice)
                 acc += d->h_h2_tile_cost[t];
             }
         }
@@ -666,20 +1039,38 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     p.dbg_nseg = 0;
     for (int i = 0; i < 4; i++) plan->kind_begin[i] = sl->kind_slice[i];
     plan->nslots = nslots;
-    plan->smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kH2DpThreads * 8 + 1024;
+    plan->use_long = d->h2_has_strips || q->max_len > (uint32_t)kTcMaxLen;
+    p.bnd = nullptr;
+    p.bnd_rows = 0;
+    p.eta = 0.f;
+    if (plan->use_long) {
+        if (d->h2_has_strips) {
+            p.bnd_rows = (q->max_len + 1) & ~1u;
+            SS_CUDA(ctx, d->d_h2_bnd.reserve((size_t)d->h2_nsmid * p.bnd_rows * kH2DpThreads));
+            p.bnd = d->d_h2_bnd.p;
+        }
+        p.eta = (float)h2_eta(d) * 1.0001f;
+        plan->smem = (size_t)kH2ARing * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kH2DpThreads * 8 + 1024;
+    } else {
+        plan->smem = (size_t)q->max_len * kTcATileBytes + kTcStages * kTcBTileBytes + 32 * 8 + (size_t)kp * kH2DpThreads * 8 + 1024;
+    }
     return SS_OK;
 }
 
-template <int KP, bool DBG>
-static int h2_launch_all(ss_ctx* ctx, const H2Plan& plan) {
+template <int KP, bool DBG, bool LONG>
+static int h2_launch_kinds(ss_ctx* ctx, const H2Plan& plan) {
     bool dep = false;
     const uint32_t* kb = plan.kind_begin;
-    SS_TRY((h2_launch_kind<KP, 1, DBG>(ctx, plan.p, kb[0], kb[1] - kb[0], plan.smem, dep)));
+    SS_TRY((h2_launch_kind<KP, 1, DBG, LONG>(ctx, plan.p, kb[0], kb[1] - kb[0], plan.smem, dep)));
     dep = dep || kb[1] > kb[0];
-    SS_TRY((h2_launch_kind<KP, 2, DBG>(ctx, plan.p, kb[1], kb[2] - kb[1], plan.smem, dep)));
+    SS_TRY((h2_launch_kind<KP, 2, DBG, LONG>(ctx, plan.p, kb[1], kb[2] - kb[1], plan.smem, dep)));
     dep = dep || kb[2] > kb[1];
-    SS_TRY((h2_launch_kind<KP, 4, DBG>(ctx, plan.p, kb[2], kb[3] - kb[2], plan.smem, dep)));
+    SS_TRY((h2_launch_kind<KP, 4, DBG, LONG>(ctx, plan.p, kb[2], kb[3] - kb[2], plan.smem, dep)));
     return SS_OK;
+}
+template <int KP, bool DBG>
+static int h2_launch_all(ss_ctx* ctx, const H2Plan& plan) {
+    return plan.use_long ? h2_launch_kinds<KP, DBG, true>(ctx, plan) : h2_launch_kinds<KP, DBG, false>(ctx, plan);
 }
 
 static bool h2_enabled() {
@@ -690,14 +1081,12 @@ static bool h2_enabled() {
     return enabled != 0;
 }
 
-// eta of the bound (true units, per normalised distance): fp16 subnormal roundings of the S-scaled operands and sums
-static double h2_eta(const ss_dict* d) { return (13.0 * (double)d->h2_bmax + 4.0) * 5.9604644775390625e-08 /* 2^-24 */ / (double)d->h2_s; }
 
 // kp_override > 0: candidates kept per query (the re-run of the queries a first pass could not certify uses 32)
 int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used, int kp_override) {
     ss_ctx* ctx = d->ctx;
     *used = false;
-    if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
+    if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kH2MaxLong || q->total_frames == 0) return SS_OK;
     SS_TRY(h2_queries_build(d, q));
     if (!q->tc_ngroups) return SS_OK;
     // k > 2: the k-th and the kp-th neighbour must be further apart than the filter's ~4 % margin: a longer list
@@ -725,10 +1114,11 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     else if (kp == 16) k_tc_merge<16><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     else k_tc_merge<32><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
-    // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S
+    // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S.
+    // bound_mode 3 (strip kernel): the keys are per-pair lower bounds already; eta and the longest segment go into the cap.
     d->h2_bound_inv_s = 1.0 / (double)d->h2_s;
-    SS_TRY(dtw_rescore_finalize(d, q, k, kp, plan.nslots, q->d_tc_qid.p, h2_eta(d), q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 2,
-                                q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
+    SS_TRY(dtw_rescore_finalize(d, q, k, kp, plan.nslots, q->d_tc_qid.p, h2_eta(d), q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p,
+                                plan.use_long ? 3 : 2, q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
     *used = true;
     return SS_OK;
 }
@@ -736,8 +1126,8 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
 // ss_dict_debug_tc_scan's half-precision counterpart: the raw scan distance of every pair (see dtw_tc_debug_scan)
 int dtw_h2_debug_scan(ss_dict* d, ss_queries* q, float* d_out, std::vector<uint32_t>* slot_qid, double* mu16, float* scale, float* s_out) {
     ss_ctx* ctx = d->ctx;
-    if (!h2_enabled() || !d->h2_ready || q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0)
-        return set_error(ctx, SS_ERR_INVALID, "debug_h2_scan: the packed-half scan does not apply (segments / queries > %d frames, or disabled)", kTcMaxLen);
+    if (!h2_enabled() || !d->h2_ready || q->max_len > (uint32_t)kH2MaxLong || q->total_frames == 0)
+        return set_error(ctx, SS_ERR_INVALID, "debug_h2_scan: the packed-half scan does not apply (segments / queries > %d frames, or disabled)", kH2MaxLong);
     SS_TRY(h2_queries_build(d, q));
     if (!q->tc_ngroups) return set_error(ctx, SS_ERR_INVALID, "debug_h2_scan: no non-empty query");
     H2Plan plan;

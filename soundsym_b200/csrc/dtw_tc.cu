@@ -604,10 +604,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dtw_scan_tc(const TcParams p)
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+// Statistics both tensor-core scans centre and scale their fp16 operands with (any segment length): the dictionary's mean
+// frame, max |fp16(b - mu)|^2 and max |fp16(b - mu)|, the power-of-two norm scale s; tc_serial identifies this build.
+static int tc_dict_stats(ss_dict* d) {
+    ss_ctx* ctx = d->ctx;
+    d->tc_stats_ready = false;
+    if (d->total_frames == 0) return SS_OK;
+    SS_CUDA(ctx, d->d_mu.reserve(16));
+    SS_CUDA(ctx, cudaMemsetAsync(d->d_mu.p, 0, 16 * sizeof(double), ctx->stream));
+    {
+        const int nb = (int)std::min<size_t>(std::max<size_t>(d->total_frames / 256, 1), 512);
+        SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)nb * 16));  // scratch
+        k_tc_mean_partial<<<nb, 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_rescore_rows.p);
+        SS_LAUNCHED(ctx);
+        k_tc_mean_final<<<1, 32, 0, ctx->stream>>>(d->d_rescore_rows.p, nb, d->total_frames, d->c, d->d_mu.p);
+        SS_LAUNCHED(ctx);
+    }
+    DevBuf<float>& d_mx = d->d_tc_max_norm;
+    SS_CUDA(ctx, d_mx.reserve(2));
+    SS_CUDA(ctx, cudaMemsetAsync(d_mx.p, 0, 2 * sizeof(float), ctx->stream));
+    k_tc_dict_maxnorm<<<ceil_div((long long)d->total_frames, 256), 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_mu.p, d_mx.p);
+    SS_LAUNCHED(ctx);
+    float mx[2] = {0, 0};
+    SS_CUDA(ctx, cudaMemcpyAsync(mx, d_mx.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));
+    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!(mx[1] < 3.0e4f) || !(mx[0] < 1.0e9f)) return SS_OK;  // values outside a safe fp16 range: keep the fp32 scan
+    float scale = 1.f;
+    while (mx[0] / scale > 16384.f) scale *= 2.f;  // |b|^2 / s must fit fp16 comfortably; s <= 2^16 is exact in fp16
+    if (scale > 32768.f) return SS_OK;
+    d->tc_nb_scale = scale;
+    d->tc_max_nb = mx[0];
+    d->tc_max_abs = mx[1];
+    static std::atomic<uint64_t> serial{0};  // process-wide: dictionaries of different contexts / host threads never share one
+    d->tc_serial = ++serial;
+    d->tc_stats_ready = true;
+    return SS_OK;
+}
+
 int dtw_tc_dict_build(ss_dict* d) {
     ss_ctx* ctx = d->ctx;
     d->tc_ready = false;
-    if (d->max_len > (uint32_t)kTcMaxLen || d->total_frames == 0) return SS_OK;  // dtw.cu's fp32 scan handles these
+    SS_TRY(tc_dict_stats(d));
+    if (!d->tc_stats_ready || d->max_len > (uint32_t)kTcMaxLen) return SS_OK;  // longer segments: dtw_h2.cu's strips, or dtw.cu's fp32 scan
     // segments sorted by length (longest first) so that the 4 slots of a tile, and hence both column halves, carry equal work
     std::vector<uint32_t> order;
     order.reserve(d->nseg);
@@ -644,41 +682,17 @@ int dtw_tc_dict_build(ss_dict* d) {
     const uint32_t ntiles = (uint32_t)(desc.size() / 4);
     d->tc_ntiles = ntiles;
     SS_TRY(upload(ctx, d->d_tc_desc, desc.data(), desc.size()));
-    SS_CUDA(ctx, d->d_mu.reserve(16));
-    SS_CUDA(ctx, cudaMemsetAsync(d->d_mu.p, 0, 16 * sizeof(double), ctx->stream));
-    {
-        const int nb = (int)std::min<size_t>(std::max<size_t>(d->total_frames / 256, 1), 512);
-        SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)nb * 16));  // scratch
-        k_tc_mean_partial<<<nb, 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_rescore_rows.p);
-        SS_LAUNCHED(ctx);
-        k_tc_mean_final<<<1, 32, 0, ctx->stream>>>(d->d_rescore_rows.p, nb, d->total_frames, d->c, d->d_mu.p);
-        SS_LAUNCHED(ctx);
-    }
-    DevBuf<float>& d_mx = d->d_tc_max_norm;
-    SS_CUDA(ctx, d_mx.reserve(2));
-    SS_CUDA(ctx, cudaMemsetAsync(d_mx.p, 0, 2 * sizeof(float), ctx->stream));
-    k_tc_dict_maxnorm<<<ceil_div((long long)d->total_frames, 256), 256, 0, ctx->stream>>>(d->d_mfcc.p, d->total_frames, d->c, d->d_mu.p, d_mx.p);
-    SS_LAUNCHED(ctx);
-    float mx[2] = {0, 0};
-    SS_CUDA(ctx, cudaMemcpyAsync(mx, d_mx.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));
-    SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!(mx[1] < 3.0e4f) || !(mx[0] < 1.0e9f)) return SS_OK;  // values outside a safe fp16 range: keep the fp32 scan
-    float scale = 1.f;
-    while (mx[0] / scale > 16384.f) scale *= 2.f;  // |b|^2 / s must fit fp16 comfortably; s <= 2^16 is exact in fp16
-    if (scale > 32768.f) return SS_OK;
-    d->tc_nb_scale = scale;
     SS_CUDA(ctx, d->d_tc_tiles.reserve((size_t)ntiles * kTcBTileBytes / 2));
-    k_tc_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_tc_desc.p, ntiles, scale,
+    k_tc_dict_tiles<<<ntiles, kTcN, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->c, d->d_mu.p, d->d_tc_desc.p, ntiles, d->tc_nb_scale,
                                                      reinterpret_cast<unsigned char*>(d->d_tc_tiles.p));
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    static std::atomic<uint64_t> serial{0};  // process-wide: dictionaries of different contexts / host threads never share one
-    d->tc_serial = ++serial;
     d->tc_ready = true;
     return SS_OK;
 }
 
-// Length-sorted groups of 128 queries (a counting sort on the host: lengths <= 32 here). Depends on the lengths only, so it
+// Length-sorted groups of 128 queries (a counting sort on the host: lengths <= 32 for the scans of <= 32 x <= 32 frames, up
+// to kTcGroupMaxLen for dtw_h2.cu's strip kernel). Depends on the lengths only, so it
 // runs once per batch, when the batch is filled (ss_queries_create / the fill inside ss_dict_match, where it overlaps the
 // host-to-device copy of the frames), not inside the match.
 int dtw_tc_queries_group(ss_queries* q) {
@@ -686,7 +700,7 @@ int dtw_tc_queries_group(ss_queries* q) {
     q->tc_grouped = false;
     q->tc_built = false;
     q->tc_ngroups = 0;
-    if (q->max_len > (uint32_t)kTcMaxLen || q->total_frames == 0) return SS_OK;
+    if (q->max_len > (uint32_t)kTcGroupMaxLen || q->total_frames == 0) return SS_OK;
     auto len_of = [&](uint32_t i) { return (uint32_t)(q->h_off[i + 1] - q->h_off[i]); };
     std::vector<uint32_t> order;
     {

@@ -215,13 +215,17 @@ int cosine_queries_build(ss_queries* q) {
 int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
     SS_TRY(cosine_queries_build(q));
-    // work = sum over pairs of min(Kq, Kd) products
+    // work = sum over pairs of min(Kq, Kd) products (the sorted segment lengths and their prefix sums are built once per
+    // dictionary: sorting 100 000 lengths on every call was 4 ms of a 4.05 ms nq = 1 match)
     {
-        std::vector<uint64_t> dl(d->nseg);
-        for (size_t s = 0; s < d->nseg; s++) dl[s] = d->h_off[s + 1] - d->h_off[s];
-        std::sort(dl.begin(), dl.end());
-        std::vector<uint64_t> pre(dl.size() + 1, 0);
-        for (size_t s = 0; s < dl.size(); s++) pre[s + 1] = pre[s] + dl[s];
+        if (d->h_len_sorted.size() != d->nseg) {
+            d->h_len_sorted.resize(d->nseg);
+            for (size_t s = 0; s < d->nseg; s++) d->h_len_sorted[s] = d->h_off[s + 1] - d->h_off[s];
+            std::sort(d->h_len_sorted.begin(), d->h_len_sorted.end());
+            d->h_len_prefix.assign(d->nseg + 1, 0);
+            for (size_t s = 0; s < d->nseg; s++) d->h_len_prefix[s + 1] = d->h_len_prefix[s] + d->h_len_sorted[s];
+        }
+        const std::vector<uint64_t>&dl = d->h_len_sorted, &pre = d->h_len_prefix;
         uint64_t work = 0;
         for (size_t i = 0; i < q->nq; i++) {
             const uint64_t lq = q->h_off[i + 1] - q->h_off[i];
@@ -238,8 +242,8 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     if (!nqb || !d->nseg) return SS_OK;
     const uint32_t nslots = q->ngroups * 32;
     uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)d->nseg, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
-    std::vector<uint32_t> ss(1, 0);
-    {
+    if (d->cos_slices_for != nslices) {  // slice table (contiguous segment ranges balanced by frames), cached per slice count
+        std::vector<uint32_t> ss(1, 0);
         const uint64_t total = d->total_frames + d->nseg;  // +1 per segment so empty segments still spread
         uint64_t acc = 0;
         for (size_t s = 0; s < d->nseg; s++) {
@@ -247,9 +251,11 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
             acc += d->h_off[s + 1] - d->h_off[s] + 1;
         }
         ss.push_back((uint32_t)d->nseg);
-        nslices = (uint32_t)ss.size() - 1;
+        SS_TRY(upload(ctx, d->d_cos_slice_seg, ss.data(), ss.size()));
+        d->cos_slices_for = nslices;
+        d->cos_nslices = (uint32_t)ss.size() - 1;
     }
-    SS_TRY(upload(ctx, d->d_slice_tile, ss.data(), ss.size()));
+    nslices = d->cos_nslices;
     SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
     if (!d->ev_scan0) {
@@ -257,7 +263,7 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
     }
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
-    k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->d_norm.p, d->c, d->d_slice_tile.p, nslices,
+    k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->d_norm.p, d->c, d->d_cos_slice_seg.p, nslices,
                                                          q->d_lane64.p, q->d_group_len.p, q->d_group_rowbase.p, q->d_group_qid.p,
                                                          q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p);
     SS_LAUNCHED(ctx);
@@ -281,9 +287,21 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
 //     rounding on the path (cost + running sum per cell, <= Lq + Ld cells, Ld <= 32) plus eta (fp16 subnormals; `eps` carries
 //     it), and a path sum beyond the fp16 range reads +inf: w is capped at 60000 / (S (Lq + 32)). Then the same input-rounding
 //     step as mode 1:  exact >= t - 2 delta sqrt(t),  t = (min(w, cap) - eta) (1 + 2^-11)^-(Lq + 34)
-__device__ __forceinline__ double scan_lower_bound(float scan, double na, double nb, double eps, int bound_mode, int la = 0, double inv_s = 0.0) {
+//   bound_mode 3 (dtw_h2.cu's strip kernel, sequences of any length): the candidate KEYS are per-pair lower bounds of the
+//     rounded-frame distance already - (scan - eta)(1 + 2^-11)^-(Lq + Ld + 2), computed by the scan - so w needs no common
+//     factor; only the cap remains (a path sum beyond the fp16 range reads +inf whatever the pair: its rounded-frame
+//     distance is at least the bound of a pair of the longest segment, ld_max, at 60000 / S):  t = min(w, cap)
+__device__ __forceinline__ double scan_lower_bound(float scan, double na, double nb, double eps, int bound_mode, int la = 0, double inv_s = 0.0,
+                                                   int ld_max = 32) {
     if (bound_mode == 0) return (double)scan - eps * (na + nb);
     const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
+    if (bound_mode == 3) {
+        const double n = (double)(la + ld_max);
+        const double cap = fmax(60000.0 * inv_s / n - 1.001 * eps, 0.0) * exp(-(n + 2.0) * 4.8937e-4 /* = 7.06e-4 ln 2, as the scan */);
+        const double w = scan > 0.f ? (double)scan : 0.0;
+        const double t = fmin(w, cap);
+        return t - 2.0 * delta * sqrt(t);
+    }
     if (bound_mode == 2) {
         const double cap = 60000.0 * inv_s / (double)(la + 32);
         double w = scan > 0.f ? (double)scan : 0.0;  // (+inf stays +inf)
@@ -311,6 +329,8 @@ struct RescoreBound {
     const float* slot_max_na;  // per slot max |a|^2 (nullable)
     double eps;
     int bound_mode, k;
+    double inv_s;  // bound_mode 2 / 3: 1 / S
+    int ld_max;    // bound_mode 3: the dictionary's longest segment
 };
 template <bool SMEM_ROWS>
 __global__ void __launch_bounds__(128)
@@ -339,7 +359,8 @@ k_dtw_rescore(const double* __restrict__ dmfcc, const uint64_t* __restrict__ dof
             kth = fmax(kth, e);
         }
         const double na = rb.slot_max_na ? (double)rb.slot_max_na[slot] : (double)rb.max_na[0];
-        if (scan_lower_bound(rb.cand_adist[pair], na, (double)rb.max_nb[0], rb.eps, rb.bound_mode) > kth) {
+        const int lq = (int)(qoff[qid + 1] - qoff[qid]);
+        if (scan_lower_bound(rb.cand_adist[pair], na, (double)rb.max_nb[0], rb.eps, rb.bound_mode, lq, rb.inv_s, rb.ld_max) > kth) {
             exact[pair] = kInf;  // provably outside the top-k
             return;
         }
@@ -506,7 +527,8 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
 __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
                                const double* __restrict__ exact, const uint32_t* __restrict__ group_qid, uint32_t nslots, int kp,
                                int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb, double eps,
-                               const float* __restrict__ slot_max_na, int bound_mode, uint8_t* __restrict__ uncert_flag,
+                               const float* __restrict__ slot_max_na, int bound_mode, double inv_s, int ld_max,
+                               const uint64_t* __restrict__ qoff, uint8_t* __restrict__ uncert_flag,
                                uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, unsigned long long* __restrict__ counters) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= nslots) return;
@@ -542,12 +564,13 @@ __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const floa
     // If that lower bound exceeds the exact k-th distance found among the candidates, the reported top-k is THE f64 top-k.
     const float worst = cand_adist[(size_t)slot * kp + kp - 1];
     bool uncertified = false;
-    if (worst < __int_as_float(0x7f800000)) {
+    // (bound_mode 2 / 3: a list that is not full does NOT mean every pair is in it - an overflowed pair reads +inf)
+    if (bound_mode >= 2 || worst < __int_as_float(0x7f800000)) {
         const double kth = n >= k ? dv[k - 1] : kInf;
         const double na = slot_max_na ? (double)slot_max_na[slot] : (double)max_na[0];
         const double nb = (double)max_nb[0];
         double lower;
-        lower = scan_lower_bound(worst, na, nb, eps, bound_mode);
+        lower = scan_lower_bound(worst, na, nb, eps, bound_mode, (int)(qoff[qid + 1] - qoff[qid]), inv_s, ld_max);
         uncertified = !(lower > kth);
         if (uncertified) atomicAdd(&counters[0], 1ull);
     }
@@ -587,7 +610,8 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     for (int phase = 0; phase < 2; phase++) {
         const int s_begin = phase ? std::min(k, kp) : 0, s_count = phase ? kp - std::min(k, kp) : std::min(k, kp);
         if (s_count <= 0) continue;
-        RescoreBound rb = {phase ? d->d_cand_adist.p : nullptr, d_max_na, d_max_nb, d_slot_max_na, eps, bound_mode, std::min(k, kp)};
+        RescoreBound rb = {phase ? d->d_cand_adist.p : nullptr, d_max_na, d_max_nb, d_slot_max_na, eps, bound_mode, std::min(k, kp), d->h2_bound_inv_s,
+                           (int)d->max_len};
         const uint32_t nt = nslots * (uint32_t)s_count;
         for (uint32_t tb = 0; tb < nt; tb += batch) {
             const uint32_t te = std::min<uint32_t>(nt, tb + batch);
@@ -599,8 +623,8 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     }
     k_dtw_finalize<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_idx.p, d->d_cand_adist.p, d->d_cand_exact.p,
                                                                   d_slot_qid, nslots, kp, k, d->index_base, d_max_na, d_max_nb, eps,
-                                                                  d_slot_max_na, bound_mode, d_uncert_flag, d_out_idx, d_out_dist,
-                                                                  d->d_counters.p);
+                                                                  d_slot_max_na, bound_mode, d->h2_bound_inv_s, (int)d->max_len, q->d_off.p,
+                                                                  d_uncert_flag, d_out_idx, d_out_dist, d->d_counters.p);
     SS_LAUNCHED(ctx);
     return SS_OK;
 }

@@ -1,5 +1,7 @@
 // match.cuh — HBM-resident dictionary / query-batch handles shared by the DTW (dtw.cu) and cosine-ref (cosine.cu) matchers.
 #pragma once
+#include <cuda_fp16.h>
+
 #include <map>
 #include <memory>
 
@@ -41,6 +43,9 @@ struct ss_dict {
     ss::DevBuf<uint64_t> d_off;   // nseg+1
     // cosine-ref
     ss::DevBuf<double> d_norm;  // per segment: norm(mfccs) (src/sound.rs:36-38)
+    std::vector<uint64_t> h_len_sorted, h_len_prefix;  // work accounting (sum of min(Kq, Kd)), built on first use
+    ss::DevBuf<uint32_t> d_cos_slice_seg;              // cached slice table of the cosine scan
+    uint32_t cos_slices_for = 0xFFFFFFFFu, cos_nslices = 0;
     // DTW scan
     ss::DevBuf<float> d_stream;  // frames x kSlots
     ss::DevBuf<int4> d_strips, d_tiles;
@@ -69,6 +74,8 @@ struct ss_dict {
     int last_scan_kind = 0;    // first-stage scan of the last match: 1 packed-half tensor-core, 2 fp32-DP tensor-core, 3 fp32 CUDA-core, 4 cosine-ref
     // tensor-core scan (dtw_tc.cu): fp16 UMMA tiles of 4 segment slots x 32 columns, segments sorted by length
     bool tc_ready = false;
+    bool tc_stats_ready = false;             // mean frame, norm scale, max norms (both tensor-core scans)
+    float tc_max_nb = 0.f, tc_max_abs = 0.f;  // max |fp16(b - mu)|^2, max |fp16(b - mu)|
     uint64_t tc_serial = 0;                  // identifies this build of the tiles (query A blocks are keyed on it)
     uint32_t tc_ntiles = 0;
     uint32_t tc_first_pair_tile = 0;         // tiles [0, first_pair) hold one segment per slot, the rest two short ones
@@ -94,6 +101,10 @@ struct ss_dict {
     float h2_bmax = 0.f;                        // max |fp16(b - mu)| (bound's eta)
     double h2_bound_inv_s = 1.0;
     std::vector<uint32_t> h_h2_tile_cost;
+    std::vector<uint8_t> h_h2_tile_cont;        // 1 if the tile continues the previous one (a later strip of the same long segments)
+    bool h2_has_strips = false;
+    ss::DevBuf<__half2> d_h2_bnd;               // boundary-column scratch of the long kernel, [192 SM ids][rows][256]
+    uint32_t h2_nsmid = 0;                      // %nsmid of the device
     ss::DevBuf<uint16_t> d_h2_tiles;
     ss::DevBuf<int4> d_h2_desc;
     ss::DevBuf<unsigned long long> d_h2_thr;   // per query slot: running bound on the global KP-th key (dtw_h2.cu)

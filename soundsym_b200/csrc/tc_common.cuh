@@ -17,6 +17,7 @@ constexpr int kTcBTileBytes = kTcN * kTcK * 2;  // 4096: one dictionary tile
 constexpr int kTcStages = 4;       // B-tile ring
 constexpr int kTcBufCols = 2 * kTcN;  // one pipeline step = two rows of the tile = 256 TMEM columns; two buffers = all 512
 constexpr int kTcMaxLen = 32;
+constexpr int kTcGroupMaxLen = 2048;  // longest query the length-sorted groups of 128 are built for (dtw_h2.cu's strip kernel)
 constexpr int kTcPairCol = 16;     // segments of <= 16 frames share a slot two by two: the second one's columns start here
 constexpr int kTcDpWarps = 4 * kTcSlots;             // 16; warp w: TMEM lane quadrant w % 4, slot w / 4
 // The producer warp sits in a warpgroup of its own (three idle warps) that hands its registers to the DP warpgroups

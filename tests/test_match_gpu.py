@@ -54,6 +54,15 @@ def test_dtw_config1_real_segments_long_strips(ctx, section71, sample_excerpt):
     dev = api.DeviceDictionary(ctx, d, doff)
     idx, dist = dev.match(q, qoff, SS_DTW, 4)
     check_dtw(idx, dist, sample_excerpt["dtw_idx"], sample_excerpt["dtw_dist"], 4)
+    # real segments take the tensor-core path too: 32-column strips + streamed query rows (dtw_h2.cu, k_dtw_scan_h2_long)
+    assert dev.last_scan_kind == 1, "config 1 did not run the packed-half tensor-core scan (kind %d)" % dev.last_scan_kind
+    assert dev.last_uncertified == 0
+    print("\nconfig 1: %d of %d queries left the first tensor-core pass, %d reached the exhaustive stage"
+          % (dev.last_tc_fallback, len(qoff) - 1, dev.last_exhaustive))
+    dev.set_scan(2)  # and the fp32 CUDA-core scan (the path these fixtures took before) still agrees
+    idx2, dist2 = dev.match(q, qoff, SS_DTW, 4)
+    assert dev.last_scan_kind == 3
+    check_dtw(idx2, dist2, sample_excerpt["dtw_idx"], sample_excerpt["dtw_dist"], 4)
 
 
 def test_cosine_ref_config1_bit_exact(ctx, section71, sample_excerpt):
