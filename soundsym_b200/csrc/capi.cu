@@ -115,6 +115,7 @@ void ss_ctx_destroy(ss_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->sound_state && ctx->sound_state_free) ctx->sound_state_free(ctx->sound_state);
     if (ctx->seg_state && ctx->seg_state_free) ctx->seg_state_free(ctx->seg_state);
+    for (void* b : ctx->pinned_free) cudaFreeHost(b);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -180,6 +181,7 @@ void ss_dict_destroy(ss_dict* d) {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
+    CacheFrees cache;  // nothing can still touch the buffers: they go to the device cache, not back to the driver
     delete d;
 }
 size_t ss_dict_len(const ss_dict* d) { return d ? d->nseg : 0; }
@@ -244,6 +246,7 @@ void ss_queries_destroy(ss_queries* q) {
     if (!q) return;
     cudaSetDevice(q->ctx->device);
     cudaStreamSynchronize(q->ctx->stream);
+    CacheFrees cache;
     delete q;
 }
 
@@ -283,12 +286,15 @@ int ss_dict_match(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offs
     ss_queries* q = d->scratch_q;
     auto body = [&]() -> int {
         SS_TRY(dtw_match_finish(d));  // a pending asynchronous match still owns the workspaces
+        TraceTimer tt(ctx);
         SS_TRY(queries_fill(q, q_mfcc, q_frame_offsets, nq));
+        tt.lap("ss_dict_match: queries_fill");
         SS_CUDA(ctx, d->d_res_idx.reserve(nq * (size_t)k));
         SS_CUDA(ctx, d->d_res_dist.reserve(nq * (size_t)k));
         const bool use_targets = targets && mode == SS_COSINE_REF;
         if (use_targets) SS_TRY(upload(ctx, d->d_res_targets, targets, nq));
         SS_TRY(ss_dict_match_dev(d, q, mode, use_targets ? d->d_res_targets.p : nullptr, k, d->d_res_idx.p, d->d_res_dist.p));
+        tt.lap("ss_dict_match: first stage");
         // ONE blocking point per call: the result copies (into the caller's pageable or pinned buffers) queue behind the
         // match; the uncertified count reaches pinned memory ahead of them, so the fallback decision costs no extra round
         // trip. Only if a fallback stage had to run are the results copied again.

@@ -4,7 +4,10 @@
 
 #include <cstdarg>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,6 +25,7 @@ struct ss_ctx {
     void (*sound_state_free)(void*) = nullptr;
     void* seg_state = nullptr;
     void (*seg_state_free)(void*) = nullptr;
+    std::vector<void*> pinned_free;  // 32-byte pinned blocks handed to dictionaries (the match's counters) and taken back
 };
 
 namespace ss {
@@ -49,17 +53,92 @@ int set_error(ss_ctx* ctx, int code, const char* fmt, ...);
         SS_CUDA((ctx), cudaGetLastError()); \
     } while (0)
 
-// RAII device buffer bound to a ctx's device (allocation is synchronous; used at create time and for workspaces)
+// Device-memory cache. A dictionary or query batch owns dozens of buffers; cudaMalloc / cudaFree cost 0.1 - 1 ms each (and
+// cudaFree synchronises the device), so a flow that builds a fresh dictionary per match (examples/reconstruction.rs) paid
+// 10 - 50 ms of allocator time per match. Blocks released by a handle's destructor AFTER its stream was synchronised
+// (ss_dict_destroy, ss_queries_destroy: CacheFrees scope) go to a per-device free list instead of back to the driver: no work
+// can still touch them, so any stream may take them. Blocks released while work may be pending (a workspace growing in the
+// middle of a match) still go through cudaFree, which waits.
+struct DevCache {
+    static constexpr int kMaxDev = 16;
+    static constexpr size_t kMaxBytes = 16ull << 30;  // cached per device; beyond that blocks go back to the driver
+    std::mutex m;
+    std::multimap<size_t, void*> blocks[kMaxDev];
+    size_t bytes[kMaxDev] = {};
+};
+inline DevCache& dev_cache() {
+    static DevCache* c = new DevCache();  // (never destroyed: handles may be released during process teardown)
+    return *c;
+}
+inline thread_local bool tl_cache_frees = false;
+struct CacheFrees {
+    bool prev;
+    CacheFrees() : prev(tl_cache_frees) { tl_cache_frees = true; }
+    ~CacheFrees() { tl_cache_frees = prev; }
+};
+inline size_t dev_round(size_t bytes) {
+    const size_t g = bytes < (1u << 20) ? 4096 : (1u << 20);
+    return (bytes + g - 1) / g * g;
+}
+inline cudaError_t dev_alloc(void** p, size_t bytes, size_t* cap, int* dev) {
+    *p = nullptr;
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return e;
+    const size_t want = dev_round(bytes);
+    DevCache& c = dev_cache();
+    if (*dev >= 0 && *dev < DevCache::kMaxDev) {
+        std::lock_guard<std::mutex> lock(c.m);
+        auto it = c.blocks[*dev].lower_bound(want);
+        if (it != c.blocks[*dev].end() && it->first <= want + std::max<size_t>(want / 4, 1u << 20)) {
+            *p = it->second;
+            *cap = it->first;
+            c.bytes[*dev] -= it->first;
+            c.blocks[*dev].erase(it);
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(p, want);
+    if (e == cudaErrorMemoryAllocation && *dev >= 0 && *dev < DevCache::kMaxDev) {  // give the cached blocks back and try again
+        cudaGetLastError();
+        std::multimap<size_t, void*> drop;
+        {
+            std::lock_guard<std::mutex> lock(c.m);
+            drop.swap(c.blocks[*dev]);
+            c.bytes[*dev] = 0;
+        }
+        for (auto& b : drop) cudaFree(b.second);
+        e = cudaMalloc(p, want);
+    }
+    *cap = want;
+    return e;
+}
+inline void dev_free(void* p, size_t cap, int dev) {
+    if (!p) return;
+    if (tl_cache_frees && dev >= 0 && dev < DevCache::kMaxDev) {
+        DevCache& c = dev_cache();
+        std::lock_guard<std::mutex> lock(c.m);
+        if (c.bytes[dev] + cap <= DevCache::kMaxBytes) {
+            c.blocks[dev].emplace(cap, p);
+            c.bytes[dev] += cap;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
+// RAII device buffer (allocation is synchronous; used at create time and for grow-only workspaces)
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    size_t cap_bytes = 0;
+    int dev = -1;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p, cap_bytes, dev);
         p = nullptr;
         n = 0;
     }
@@ -68,8 +147,9 @@ struct DevBuf {
         if (count <= n && p) return cudaSuccess;
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        void* q = nullptr;
+        cudaError_t e = dev_alloc(&q, count * sizeof(T), &cap_bytes, &dev);
+        if (e == cudaSuccess) p = static_cast<T*>(q), n = count;
         else p = nullptr;
         return e;
     }

@@ -515,6 +515,16 @@ static int g_scan_rb = 0;  // 0 = default; tools/tests may override through SS_D
 
 static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset);
 
+// Sequences of more than 32 frames have no cheap second filter (the fp32-DP tensor-core scan stops at 32 frames, the CUDA-core
+// scan of ONE long query is a single warp's serial walk: 16 ms at config 5): below 2e8 cells the exhaustive stage is the
+// fastest way to finish (f64, measured 9e10 cells / s: 2 ms); a dozen such queries first take the second packed-half pass.
+static bool exhaustive_is_cheaper(const ss_dict* d, const ss_queries* q, const std::vector<uint32_t>& subset) {
+    if (d->max_len <= 32 && q->max_len <= 32) return false;
+    uint64_t rows = 0;
+    for (uint32_t i : subset) rows += q->h_off[i + 1] - q->h_off[i];
+    return rows * d->total_frames <= 200000000ull;
+}
+
 // which queries the last stage could not certify (synchronous; only called once the counter said there are some)
 static int uncertified_subset(ss_dict* d, ss_queries* q, std::vector<uint32_t>* subset) {
     ss_ctx* ctx = d->ctx;
@@ -531,7 +541,12 @@ static int uncertified_subset(ss_dict* d, ss_queries* q, std::vector<uint32_t>* 
 static int post_counters(ss_dict* d) {
     ss_ctx* ctx = d->ctx;
     if (!d->h_counters) {
-        SS_CUDA(ctx, cudaHostAlloc((void**)&d->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+        if (!ctx->pinned_free.empty()) {  // (a block a destroyed dictionary of this ctx handed back)
+            d->h_counters = static_cast<unsigned long long*>(ctx->pinned_free.back());
+            ctx->pinned_free.pop_back();
+        } else {
+            SS_CUDA(ctx, cudaHostAlloc((void**)&d->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+        }
         SS_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
     }
     SS_CUDA(ctx, d->d_counters.reserve(4));
@@ -580,27 +595,6 @@ int dtw_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double*
     return SS_OK;
 }
 
-// SS_DTW_TRACE=1: wall-clock of the fallback path's steps on stderr (each step is followed by a stream synchronisation)
-static bool dtw_trace() {
-    static const bool on = [] {
-        const char* e = getenv("SS_DTW_TRACE");
-        return e && atoi(e) != 0;
-    }();
-    return on;
-}
-struct TraceTimer {
-    ss_ctx* ctx;
-    std::chrono::steady_clock::time_point t0;
-    explicit TraceTimer(ss_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) {}
-    void lap(const char* what) {
-        if (!dtw_trace()) return;
-        cudaStreamSynchronize(ctx->stream);
-        const auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[ss dtw trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
-
 // ---- re-running a few queries through the slower stages -------------------------------------------------------------------
 // The queries a first stage could not certify are gathered (on the device) into a small batch of their own, which then runs
 // the remaining stages - fp32-DP tensor-core scan, fp32 CUDA-core scan, exhaustive f64 - synchronously; their rows are
@@ -629,7 +623,7 @@ static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t
     ss_ctx* ctx = d->ctx;
     SS_CUDA(ctx, q->d_uncert_flag.reserve(std::max<size_t>(q->nq, 1)));
     SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
-    bool used = false;
+    bool used = false, h2_ran = false;
     std::vector<uint32_t> subset;
     TraceTimer tt(ctx);
     // 1a'. the packed-half scan once more with 32 candidates per query: the queries that reach this point had more than 8
@@ -642,7 +636,7 @@ static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t
             tt.lap("  packed-half stage, 32 candidates");
             if (dtw_trace()) fprintf(stderr, "[ss dtw trace]   -> %llu of %zu still uncertified\n", d->h_counters[0], q->nq);
             if (!d->h_counters[0]) return SS_OK;
-            SS_CUDA(ctx, cudaMemsetAsync(q->d_uncert_flag.p, 0, std::max<size_t>(q->nq, 1), ctx->stream));
+            h2_ran = true;
             used = false;
         }
     }
@@ -656,7 +650,14 @@ static int dtw_match_remaining_stages(ss_dict* d, ss_queries* q, int k, uint32_t
         SS_TRY(uncertified_subset(d, q, &subset));
         SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, &subset));
     } else {
-        SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, nullptr));
+        if (h2_ran) {  // what the second packed-half pass left
+            SS_TRY(uncertified_subset(d, q, &subset));
+            if (exhaustive_is_cheaper(d, q, subset)) {
+                *n_exhaustive += subset.size();
+                return dtw_exhaustive_match(d, q, k, subset, d_out_idx, d_out_dist);
+            }
+        }
+        SS_TRY(dtw_fp32_match(d, q, k, d_out_idx, d_out_dist, h2_ran ? &subset : nullptr));
     }
     SS_TRY(post_counters(d));
     SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
@@ -713,7 +714,9 @@ int dtw_match_finish(ss_dict* d) {
     d->pending.active = false;
     ss_queries* q = d->pending.q;
     const int k = d->pending.k;
+    TraceTimer tt(ctx);
     SS_CUDA(ctx, cudaEventSynchronize(d->ev_done));
+    tt.lap("first stage (wait)");
     unsigned long long n_unc = d->h_counters[0];
     std::vector<uint32_t> subset;
     struct Guard {  // the stages below are fallbacks: they do not touch the first stage's scan-time events
@@ -724,7 +727,14 @@ int dtw_match_finish(ss_dict* d) {
     if (d->pending.stage == 1 && n_unc) {
         SS_TRY(uncertified_subset(d, q, &subset));
         d->last_tc_fallback = subset.size();
-        if (d->pending.h2) {
+        if (exhaustive_is_cheaper(d, q, subset)) {
+            // a handful of long queries: the f64 DTW against every segment, one warp per pair, costs less than any further filter
+            // pass (a scan's CTA walks all rows of a group of 128 lanes whatever the number of live queries)
+            d->last_exhaustive += subset.size();
+            SS_TRY(dtw_exhaustive_match(d, q, k, subset, d->pending.d_out_idx, d->pending.d_out_dist));
+            tt.lap("exhaustive f64 (few long queries)");
+            n_unc = 0;
+        } else if (d->pending.h2) {
             // the packed-half filter leaves a fraction of a percent of the queries: a small batch of their own
             SS_TRY(dtw_rerun_subset(d, q, k, subset, d->pending.d_out_idx, d->pending.d_out_dist));
             n_unc = 0;

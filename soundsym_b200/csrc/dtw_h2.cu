@@ -1087,7 +1087,9 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     ss_ctx* ctx = d->ctx;
     *used = false;
     if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kH2MaxLong || q->total_frames == 0) return SS_OK;
+    TraceTimer tt(ctx);
     SS_TRY(h2_queries_build(d, q));
+    tt.lap("  h2: query A blocks");
     if (!q->tc_ngroups) return SS_OK;
     // k > 2: the k-th and the kp-th neighbour must be further apart than the filter's ~4 % margin: a longer list
     // SS_DTW_H2_KP=8|16|32: candidates kept per query for k <= 2. Measured at config 4 (profiles/bench/r2_h2_kp_sweep.json): 8 leaves
@@ -1102,6 +1104,7 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     d->last_uncertified = 0;
     H2Plan plan;
     SS_TRY(h2_plan(d, q, kp, &plan));
+    tt.lap("  h2: plan (slices, workspaces)");
     if (!d->in_fallback) SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     if (kp == 8) SS_TRY((h2_launch_all<8, false>(ctx, plan)));
     else if (kp == 16) SS_TRY((h2_launch_all<16, false>(ctx, plan)));
@@ -1114,11 +1117,13 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     else if (kp == 16) k_tc_merge<16><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     else k_tc_merge<32><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
+    tt.lap("  h2: scan + merge");
     // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S.
     // bound_mode 3 (strip kernel): the keys are per-pair lower bounds already; eta and the longest segment go into the cap.
     d->h2_bound_inv_s = 1.0 / (double)d->h2_s;
     SS_TRY(dtw_rescore_finalize(d, q, k, kp, plan.nslots, q->d_tc_qid.p, h2_eta(d), q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p,
                                 plan.use_long ? 3 : 2, q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
+    tt.lap("  h2: f64 refine + certification");
     *used = true;
     return SS_OK;
 }

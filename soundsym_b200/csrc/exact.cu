@@ -524,6 +524,131 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same exact recurrence for sequences of ANY length, one warp per pair (k_dtw_rescore's interface; a single thread needs
+// ~80 ms for a pair of 383 x 383 frames, which was most of config 5's match). The dictionary segment is cut into strips of 32
+// columns, lane j owning column 32 s + j of strip s with its frame in registers. Per strip the warp alternates
+//   A. local costs of the next 32 query rows against the strip's 32 columns -> a shared-memory ring of 64 rows (the row's
+//      frame is a broadcast load; all lanes busy; 39 f64 operations per cell, the oracle's order), and
+//   B. 32 steps of the anti-diagonal wavefront (lane j computes cell (t - j, column j) at step t: up = its own previous
+//      value, left / diag = its left neighbour's values one / two steps earlier, by shuffle),
+// and the strip's last column travels to the next strip through `bnd` (global, one row of max query length per warp), IN
+// PLACE: lane 31 writes row t - 31 at the step lane 0 reads row t.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_dtw_exact_long(const double* __restrict__ a, int la, const double* __restrict__ b, int lb, int c,
+                                                      double* __restrict__ ring, double* bnd, int lane) {
+    if (!la || !lb) return kInf;
+    double result = kInf;
+    const int nstrips = (lb + 31) >> 5;
+    const int nsteps = la + 31;
+    for (int s = 0; s < nstrips; s++) {
+        const int col = 32 * s + lane;
+        const bool colv = col < lb, first = s == 0, last = s == nstrips - 1;
+        double br[SS_MAX_NCOEFFS];
+#pragma unroll
+        for (int k = 0; k < SS_MAX_NCOEFFS; k++) br[k] = (k < c && colv) ? b[(size_t)col * c + k] : 0.0;
+        double cur = kInf, recv_prev = kInf, bl_prev = kInf;
+        __syncwarp();  // the previous strip's boundary writes and ring reads are complete
+        for (int t0 = 0; t0 < nsteps; t0 += 32) {
+            // A: rows t0 .. t0 + 31 (ring slots of rows t0 - 64 .. t0 - 33, last read at step t0 - 2)
+            const int rows = min(32, la - t0);
+            int r = 0;
+            for (; r + 4 <= rows; r += 4) {  // four rows at a time: four independent accumulation chains
+                const double* ar = a + (size_t)(t0 + r) * c;
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < SS_MAX_NCOEFFS; k++)
+                    if (k < c) {
+                        const double d0 = ar[k] - br[k], d1 = ar[c + k] - br[k], d2 = ar[2 * c + k] - br[k], d3 = ar[3 * c + k] - br[k];
+                        c0 = c0 + d0 * d0;
+                        c1 = c1 + d1 * d1;
+                        c2 = c2 + d2 * d2;
+                        c3 = c3 + d3 * d3;
+                    }
+                double* dst = ring + ((t0 + r) & 63) * 32 + lane;  // (t0 + r is a multiple of 4: the four slots do not wrap)
+                dst[0] = c0, dst[32] = c1, dst[64] = c2, dst[96] = c3;
+            }
+            for (; r < rows; r++) {
+                const double* ar = a + (size_t)(t0 + r) * c;
+                double cost = 0.0;
+#pragma unroll
+                for (int k = 0; k < SS_MAX_NCOEFFS; k++)
+                    if (k < c) {
+                        const double dlt = ar[k] - br[k];
+                        cost = cost + dlt * dlt;
+                    }
+                ring[((t0 + r) & 63) * 32 + lane] = cost;
+            }
+            __syncwarp();
+            // B: steps t0 .. t0 + 31
+            const int steps = min(32, nsteps - t0);
+            double left_in = (lane == 0 && !first && t0 < la) ? bnd[t0] : kInf;  // D(t, col0 - 1), fetched one step ahead
+            for (int r = 0; r < steps; r++) {
+                const int t = t0 + r;
+                const double recv = __shfl_up_sync(0xffffffffu, cur, 1);  // left neighbour's last cell = D(i, col - 1)
+                const double left_now = left_in;
+                if (r + 1 < steps) left_in = (lane == 0 && !first && t + 1 < la) ? bnd[t + 1] : kInf;
+                const int i = t - lane;
+                const bool active = colv && i >= 0 && i < la;
+                if (active) {
+                    const double up = cur;
+                    const double left = lane ? recv : left_now;
+                    const double diag = lane ? recv_prev : bl_prev;
+                    double m;
+                    if (first && i == 0 && lane == 0) m = 0.0;
+                    else m = fmin(fmin(up, left), diag);
+                    cur = ring[(i & 63) * 32 + lane] + m;
+                    if (last && i == la - 1 && col == lb - 1) result = cur;
+                    if (!last && lane == 31) bnd[i] = cur;  // i = t - 31: behind every row lane 0 still has to read
+                }
+                bl_prev = left_now;
+                recv_prev = recv;
+            }
+            __syncwarp();
+        }
+    }
+    result = __shfl_sync(0xffffffffu, result, (lb - 1) & 31);
+    return result / (double)(la + lb);
+}
+
+// k_dtw_rescore with one WARP per (slot, candidate) pair (grid-stride over the pairs; bnd: one row of bnd_stride doubles per warp)
+__global__ void __launch_bounds__(64)
+k_dtw_rescore_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                   const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
+                   uint32_t nt, int kp, int s_begin, int s_count, RescoreBound rb, double* __restrict__ bnd, uint32_t bnd_stride,
+                   double* __restrict__ exact, unsigned long long* __restrict__ counters) {
+    __shared__ double ring[2][64 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * 2 + warp, nw = gridDim.x * 2;
+    for (uint32_t t = gw; t < nt; t += nw) {  // warp-uniform
+        const uint32_t slot = t / (uint32_t)s_count;
+        const uint32_t pair = slot * (uint32_t)kp + (uint32_t)s_begin + t % (uint32_t)s_count;
+        const uint32_t qid = group_qid[slot];
+        const uint32_t idx = cand_idx[pair];
+        if (qid == 0xFFFFFFFFu || idx == 0xFFFFFFFFu) {
+            if (lane == 0) exact[pair] = kInf;
+            continue;
+        }
+        const int la = (int)(qoff[qid + 1] - qoff[qid]), lb = (int)(doff[idx + 1] - doff[idx]);
+        if (rb.cand_adist) {
+            double kth = 0.0;  // k-th smallest exact distance among the slot's first k candidates
+            for (int s = 0; s < rb.k; s++) {
+                double e = exact[(size_t)slot * kp + s];
+                if (!(e < kInf)) e = kInf;  // empty slot / NaN: nothing can be ruled out
+                kth = fmax(kth, e);
+            }
+            const double na = rb.slot_max_na ? (double)rb.slot_max_na[slot] : (double)rb.max_na[0];
+            if (scan_lower_bound(rb.cand_adist[pair], na, (double)rb.max_nb[0], rb.eps, rb.bound_mode, la, rb.inv_s, rb.ld_max) > kth) {
+                if (lane == 0) exact[pair] = kInf;  // provably outside the top-k
+                continue;
+            }
+            if (lane == 0) atomicAdd(&counters[1], 1ull);
+        }
+        const double e = warp_dtw_exact_long(qmfcc + qoff[qid] * c, la, dmfcc + doff[idx] * c, lb, c, ring[warp], bnd + (size_t)gw * bnd_stride, lane);
+        if (lane == 0) exact[pair] = e;
+    }
+}
+
 __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
                                const double* __restrict__ exact, const uint32_t* __restrict__ group_qid, uint32_t nslots, int kp,
                                int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb, double eps,
@@ -601,6 +726,33 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
     }
     const uint32_t npairs = nslots * (uint32_t)kp;
     SS_CUDA(ctx, d->d_cand_exact.reserve(npairs));
+    static const bool thread_rescore = [] {  // SS_DTW_THREAD_RESCORE=1: the thread-per-pair kernels (A/B measurements)
+        const char* e = getenv("SS_DTW_THREAD_RESCORE");
+        return e && atoi(e) != 0;
+    }();
+    if (!thread_rescore) {
+        // one warp per pair: the k best of every slot, then the others unless the scan's bound rules them out, then the sort
+        const uint32_t stride = (std::max<uint32_t>(q->max_len, 1) + 15) & ~15u;
+        const uint32_t max_ctas = (uint32_t)ctx->sm_count * 6;  // 33 KB of shared memory each
+        SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)max_ctas * 2 * stride));
+        for (int phase = 0; phase < 2; phase++) {
+            const int s_begin = phase ? std::min(k, kp) : 0, s_count = phase ? kp - std::min(k, kp) : std::min(k, kp);
+            if (s_count <= 0) continue;
+            RescoreBound rb = {phase ? d->d_cand_adist.p : nullptr, d_max_na, d_max_nb, d_slot_max_na, eps, bound_mode, std::min(k, kp), d->h2_bound_inv_s,
+                               (int)d->max_len};
+            const uint32_t nt = nslots * (uint32_t)s_count;
+            k_dtw_rescore_warp<<<std::min<uint32_t>(max_ctas, ceil_div(nt, 2)), 64, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
+                                                                                                  d_slot_qid, d->d_cand_idx.p, nt, kp, s_begin, s_count, rb,
+                                                                                                  d->d_rescore_rows.p, stride, d->d_cand_exact.p,
+                                                                                                  d->d_counters.p);
+            SS_LAUNCHED(ctx);
+        }
+        k_dtw_finalize<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_idx.p, d->d_cand_adist.p, d->d_cand_exact.p, d_slot_qid, nslots, kp, k,
+                                                                      d->index_base, d_max_na, d_max_nb, eps, d_slot_max_na, bound_mode, d->h2_bound_inv_s,
+                                                                      (int)d->max_len, q->d_off.p, d_uncert_flag, d_out_idx, d_out_dist, d->d_counters.p);
+        SS_LAUNCHED(ctx);
+        return SS_OK;
+    }
     const uint64_t budget = 32ull << 20;  // doubles of DP-row scratch (256 MB)
     const uint32_t batch = (uint32_t)std::min<uint64_t>(npairs, std::max<uint64_t>(1024, budget / max_ld));
     SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)batch * max_ld));
@@ -630,44 +782,24 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// exhaustive f64 DTW: (uncertified query u, every dictionary segment). One thread per pair, DP row in a [column][pair]
-// global scratch; then one block per query selects its top-k by (distance, index).
+// exhaustive f64 DTW: (uncertified query u, every dictionary segment). One warp per pair (warp_dtw_exact_long); then one block
+// per query selects its top-k by (distance, index).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_dtw_pairs_exact(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
-                                  const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ qids, uint32_t nu, uint32_t seg_begin,
-                                  uint32_t seg_count, double* __restrict__ rows, uint32_t row_pairs, double* __restrict__ exact, uint32_t nseg) {
-    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
-    if (local >= nu * seg_count) return;
-    const uint32_t u = local / seg_count, sidx = seg_begin + local % seg_count;
-    const uint32_t qid = qids[u];
-    const double* a = qmfcc + qoff[qid] * c;
-    const double* b = dmfcc + doff[sidx] * c;
-    const uint32_t la = (uint32_t)(qoff[qid + 1] - qoff[qid]), lb = (uint32_t)(doff[sidx + 1] - doff[sidx]);
-    double* row = rows + local;
-    double last = kInf;
-    for (uint32_t i = 0; i < la; i++) {
-        double ar[SS_MAX_NCOEFFS];
-#pragma unroll
-        for (int k = 0; k < SS_MAX_NCOEFFS; k++) ar[k] = k < c ? a[(size_t)i * c + k] : 0.0;
-        double left = kInf, diag = kInf;
-        for (uint32_t j = 0; j < lb; j++) {
-            double cost = 0.0;
-#pragma unroll
-            for (int k = 0; k < SS_MAX_NCOEFFS; k++)
-                if (k < c) {
-                    const double dlt = ar[k] - b[(size_t)j * c + k];
-                    cost = cost + dlt * dlt;
-                }
-            const double up = i ? row[(size_t)j * row_pairs] : kInf;
-            const double m = (i == 0 && j == 0) ? 0.0 : fmin(fmin(up, left), diag);
-            const double cur = cost + m;
-            row[(size_t)j * row_pairs] = cur;
-            diag = up;
-            left = cur;
-        }
-        last = left;
+__global__ void __launch_bounds__(64)
+k_dtw_pairs_exact_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                       const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ qids, uint32_t nu, uint32_t nseg,
+                       double* __restrict__ bnd, uint32_t bnd_stride, double* __restrict__ exact) {
+    __shared__ double ring[2][64 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * 2 + warp, nw = gridDim.x * 2;
+    const uint64_t npairs = (uint64_t)nu * nseg;
+    for (uint64_t t = gw; t < npairs; t += nw) {  // warp-uniform; consecutive warps take consecutive segments of one query
+        const uint32_t u = (uint32_t)(t / nseg), sidx = (uint32_t)(t % nseg);
+        const uint32_t qid = qids[u];
+        const int la = (int)(qoff[qid + 1] - qoff[qid]), lb = (int)(doff[sidx + 1] - doff[sidx]);
+        const double e = warp_dtw_exact_long(qmfcc + qoff[qid] * c, la, dmfcc + doff[sidx] * c, lb, c, ring[warp], bnd + (size_t)gw * bnd_stride, lane);
+        if (lane == 0) exact[(size_t)u * nseg + sidx] = e;
     }
-    exact[(size_t)u * nseg + sidx] = (la && lb) ? last / (double)(la + lb) : kInf;
 }
 
 __global__ void __launch_bounds__(256)
@@ -713,21 +845,21 @@ k_dtw_select_exact(const double* __restrict__ exact, uint32_t nseg, int k, const
 
 int dtw_exhaustive_match(ss_dict* d, ss_queries* q, int k, const std::vector<uint32_t>& subset, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
-    const uint32_t nseg = (uint32_t)d->nseg, max_ld = std::max<uint32_t>(d->max_len, 1);
-    const uint64_t budget = 32ull << 20;  // doubles of DP-row scratch and of the distance table (256 MB each)
+    const uint32_t nseg = (uint32_t)d->nseg;
+    const uint64_t budget = 32ull << 20;  // doubles of the distance table (256 MB)
     const uint32_t ubatch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(subset.size(), budget / std::max<uint32_t>(nseg, 1)));
     SS_CUDA(ctx, d->d_exh_qid.reserve(subset.size()));
     SS_CUDA(ctx, cudaMemcpyAsync(d->d_exh_qid.p, subset.data(), subset.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     SS_CUDA(ctx, d->d_exh_dist.reserve((size_t)ubatch * nseg));
+    const uint32_t stride = (std::max<uint32_t>(q->max_len, 1) + 15) & ~15u;
+    const uint32_t max_ctas = (uint32_t)ctx->sm_count * 6;
+    SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)max_ctas * 2 * stride));
     for (size_t u0 = 0; u0 < subset.size(); u0 += ubatch) {
         const uint32_t nu = (uint32_t)std::min<size_t>(ubatch, subset.size() - u0);
-        const uint32_t seg_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nseg, budget / ((uint64_t)max_ld * nu)));
-        SS_CUDA(ctx, d->d_rescore_rows.reserve((size_t)seg_batch * nu * max_ld));
-        for (uint32_t s0 = 0; s0 < nseg; s0 += seg_batch) {
-            const uint32_t sc = std::min<uint32_t>(seg_batch, nseg - s0);
-            k_dtw_pairs_exact<<<ceil_div((long long)nu * sc, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c,
-                                                                                         d->d_exh_qid.p + u0, nu, s0, sc, d->d_rescore_rows.p,
-                                                                                         nu * sc, d->d_exh_dist.p, nseg);
+        const uint64_t npairs = (uint64_t)nu * nseg;
+        if (npairs) {
+            k_dtw_pairs_exact_warp<<<(unsigned)std::min<uint64_t>(max_ctas, (npairs + 1) / 2), 64, 0, ctx->stream>>>(
+                d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d->d_exh_qid.p + u0, nu, nseg, d->d_rescore_rows.p, stride, d->d_exh_dist.p);
             SS_LAUNCHED(ctx);
         }
         k_dtw_select_exact<<<nu, 256, 0, ctx->stream>>>(d->d_exh_dist.p, nseg, k, d->d_exh_qid.p + u0, d->index_base, d_out_idx, d_out_dist);

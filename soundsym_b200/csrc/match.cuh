@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <chrono>
 #include <map>
 #include <memory>
 
@@ -181,12 +182,36 @@ inline ss_dict::~ss_dict() {
     if (ev_scan0) cudaEventDestroy(ev_scan0);
     if (ev_scan1) cudaEventDestroy(ev_scan1);
     if (ev_done) cudaEventDestroy(ev_done);
-    if (h_counters) cudaFreeHost(h_counters);
+    if (h_counters) {
+        if (ctx) ctx->pinned_free.push_back(h_counters);
+        else cudaFreeHost(h_counters);
+    }
     delete scratch_q;
     delete sub_q;
 }
 
 namespace ss {
+// SS_DTW_TRACE=1: wall-clock of the fallback path's steps on stderr (each step is followed by a stream synchronisation)
+inline bool dtw_trace() {
+    static const bool on = [] {
+        const char* e = getenv("SS_DTW_TRACE");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+struct TraceTimer {
+    ss_ctx* ctx;
+    std::chrono::steady_clock::time_point t0;
+    explicit TraceTimer(ss_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!dtw_trace()) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ss dtw trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int dtw_dict_build(ss_dict* d);       // builds the fp32 stream + strip / tile tables (dtw.cu)
 int dtw_tc_dict_build(ss_dict* d);    // builds the fp16 UMMA tiles (dtw_tc.cu)
 int dtw_queries_build(ss_queries* q, const std::vector<uint32_t>* subset = nullptr); // builds the lane layout (dtw.cu)
