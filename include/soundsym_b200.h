@@ -253,8 +253,9 @@ int ss_dict_debug_tc_scan(ss_dict* dict, const double* q_mfcc, const uint64_t* q
 int ss_dict_debug_h2_scan(ss_dict* dict, const double* q_mfcc, const uint64_t* q_frame_offsets, size_t nq, float* out_scan,
                           double* out_mu, float* out_scale, float* out_s);
 /* test / A-B hook: which filter stage an SS_DTW match STARTS with when all of them apply. 0 (default) = packed-half tensor-core
- * scan, 1 = fp32-DP tensor-core scan, 2 = fp32 CUDA-core scan. The results are identical by construction (every stage is
- * followed by the f64 refine + certification); only the speed differs. */
+ * scan, 1 = fp32-DP tensor-core scan, 2 = fp32 CUDA-core scan, 3 = packed-half scan WITHOUT its second chance (the pass over the
+ * per-slice candidate lists that certifies most of what the merged list could not), so that tests can drive the later stages.
+ * The results are identical by construction (every stage is followed by the f64 refine + certification); only the speed differs. */
 int ss_dict_set_scan(ss_dict* dict, int first_stage);
 
 /* ss_resynth   SoundSequence::clone_from_dictionary sample assembly (src/sound.rs:451-472) + to_sound (:475-483):

@@ -317,7 +317,7 @@ int ss_dict_match(ss_dict* d, const double* q_mfcc, const uint64_t* q_frame_offs
 
 int ss_dict_set_scan(ss_dict* d, int first_stage) {
     if (!d) return set_error(nullptr, SS_ERR_INVALID, "dict is NULL");
-    if (first_stage < 0 || first_stage > 2) return set_error(d->ctx, SS_ERR_INVALID, "first_stage must be 0, 1 or 2");
+    if (first_stage < 0 || first_stage > 3) return set_error(d->ctx, SS_ERR_INVALID, "first_stage must be 0, 1, 2 or 3");
     SS_CUDA(d->ctx, cudaSetDevice(d->ctx->device));
     SS_TRY(dtw_match_finish(d));
     d->scan_pref = first_stage;

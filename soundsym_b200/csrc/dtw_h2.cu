@@ -40,6 +40,10 @@ int dtw_rescore_finalize(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslo
                          const float* d_max_na, const float* d_max_nb, const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag,
                          bool fill, uint32_t* d_out_idx, double* d_out_dist);
 
+int dtw_second_chance(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, const unsigned long long* d_partial,
+                      uint32_t nlists, const unsigned long long* d_thr, double eps, const float* d_max_na, const float* d_max_nb,
+                      const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag, uint32_t* d_out_idx, double* d_out_dist);
+
 constexpr int kH2Slots = 2;
 constexpr int kH2SlotCols = 64;                       // TMEM columns per slot and row
 constexpr int kH2DpWarps = 4 * kH2Slots;              // 8
@@ -1086,7 +1090,7 @@ static bool h2_enabled() {
 int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, bool* used, int kp_override) {
     ss_ctx* ctx = d->ctx;
     *used = false;
-    if (!h2_enabled() || d->scan_pref != 0 || !d->h2_ready || q->max_len > (uint32_t)kH2MaxLong || q->total_frames == 0) return SS_OK;
+    if (!h2_enabled() || (d->scan_pref != 0 && d->scan_pref != 3) || !d->h2_ready || q->max_len > (uint32_t)kH2MaxLong || q->total_frames == 0) return SS_OK;
     TraceTimer tt(ctx);
     SS_TRY(h2_queries_build(d, q));
     tt.lap("  h2: query A blocks");
@@ -1124,6 +1128,17 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     SS_TRY(dtw_rescore_finalize(d, q, k, kp, plan.nslots, q->d_tc_qid.p, h2_eta(d), q->d_tc_max_norm.p, d->d_tc_max_norm.p, q->d_tc_slot_max_na.p,
                                 plan.use_long ? 3 : 2, q->d_uncert_flag.p, /*fill=*/true, d_out_idx, d_out_dist));
     tt.lap("  h2: f64 refine + certification");
+    // the queries the merged list could not certify: refine what the union of the per-slice lists still holds below the scan's
+    // own insertion threshold, and certify against that threshold (exact.cu, k_dtw_second_chance)
+    static const bool second = [] {
+        const char* e = getenv("SS_DTW_SECOND_CHANCE");
+        return e ? atoi(e) != 0 : true;
+    }();
+    if (second && !plan.use_long && d->scan_pref != 3) {
+        SS_TRY(dtw_second_chance(d, q, k, kp, plan.nslots, q->d_tc_qid.p, d->d_tc_partial.p, plan.p.nslices, d->d_h2_thr.p, h2_eta(d), q->d_tc_max_norm.p,
+                                 d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 2, q->d_uncert_flag.p, d_out_idx, d_out_dist));
+        tt.lap("  h2: second chance (union of the slice lists)");
+    }
     *used = true;
     return SS_OK;
 }

@@ -649,6 +649,129 @@ k_dtw_rescore_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second chance for the queries the packed-half scan's merged candidate list could not certify (dtw_h2.cu, <= 32 x <= 32
+// frames). The scan leaves one ascending list of kp keys per (slice, query), and a per-query threshold `thr` = the smallest
+// "worst kept key" any CTA with a full list reported (later CTAs start from it). Every pair that is in NO slice list was
+// dropped against a threshold >= thr, so its scan distance is >= W = dist(thr) - usually far above the merged list's kp-th
+// entry, because one slice holds ~1/2000 of the dictionary. The union of the slice lists therefore contains every pair below
+// W: one warp per uncertified query walks it, refines in f64 every entry the bound cannot rule out against the current k-th
+// exact distance, and certifies against W. No host round trip, no second scan (the re-run of ~47 queries through the fp32-DP
+// tensor-core scan was 1.5 of config 4's 39 ms, and a fixed ~0.5 ms of every shard's step at 8 GPUs).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSecondQueue = 192;  // entries a warp can queue for refinement; a query with more stays uncertified
+__global__ void __launch_bounds__(64)
+k_dtw_second_chance(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                    const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
+                    const unsigned long long* __restrict__ partial, uint32_t nlists, const unsigned long long* __restrict__ thr, uint32_t nslots,
+                    int kp, int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb, double eps,
+                    const float* __restrict__ slot_max_na, int bound_mode, double inv_s, uint8_t* __restrict__ uncert_flag,
+                    uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, unsigned long long* __restrict__ counters) {
+    __shared__ double scost[2][32 * 32];
+    __shared__ double squery[2][32 * SS_MAX_NCOEFFS];
+    __shared__ uint32_t squeue[2][kSecondQueue];
+    __shared__ uint32_t scount[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * 2 + warp;
+    if (slot >= nslots) return;  // warp-uniform from here on
+    const uint32_t qid = group_qid[slot];
+    if (qid == 0xFFFFFFFFu || !uncert_flag[qid]) return;
+    const double na = slot_max_na ? (double)slot_max_na[slot] : (double)max_na[0];
+    const double nb = (double)max_nb[0];
+    const double* a = qmfcc + qoff[qid] * c;
+    const int la = (int)(qoff[qid + 1] - qoff[qid]);
+    // current top-k (the k best of the merged list's kp candidates, exact)
+    double dv[SS_MAX_TOPK];
+    uint32_t iv[SS_MAX_TOPK];
+    int n = 0;
+    for (int s = 0; s < k; s++) {
+        const uint32_t ii = out_idx[(size_t)qid * k + s];
+        if (ii == 0xFFFFFFFFu) break;
+        iv[n] = ii - index_base;
+        dv[n] = out_dist[(size_t)qid * k + s];
+        n++;
+    }
+    double kth = n >= k ? dv[k - 1] : kInf;
+    const uint32_t my_cand = lane < kp ? cand_idx[(size_t)slot * kp + lane] : 0xFFFFFFFFu;  // already refined
+    if (lane == 0) scount[warp] = 0;
+    for (int e = lane; e < la * c; e += 32) squery[warp][e] = a[e];
+    __syncwarp();
+    // ---- walk the slice lists: queue every entry the bound cannot rule out and the first pass did not refine ----------------
+    for (uint32_t l = lane; l < ((nlists + 31) & ~31u); l += 32) {
+        for (int s = 0; s < kp; s++) {
+            unsigned long long key = 0xFFFFFFFFFFFFFFFFull;
+            if (l < nlists) key = __ldg(partial + ((size_t)l * nslots + slot) * kp + s);
+            bool want = false;
+            if (key != 0xFFFFFFFFFFFFFFFFull) {
+                const uint32_t o = (uint32_t)(key >> 32);
+                const float dist = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+                want = !(scan_lower_bound(dist, na, nb, eps, bound_mode, la, inv_s) > kth);
+            }
+            if (!__any_sync(0xffffffffu, want)) break;  // lists ascend: nothing further down any of these 32 lists qualifies
+            const uint32_t idx = (uint32_t)key;
+            bool seen = false;
+            for (int j = 0; j < kp; j++) seen |= __shfl_sync(0xffffffffu, my_cand, j) == idx;  // (all lanes take part)
+            want = want && !seen;
+            if (want) {
+                const uint32_t pos = atomicAdd(&scount[warp], 1u);
+                if (pos < (uint32_t)kSecondQueue) squeue[warp][pos] = idx;
+            }
+        }
+    }
+    __syncwarp();
+    const uint32_t nqueued = scount[warp];
+    if (nqueued > (uint32_t)kSecondQueue) return;  // stays uncertified: the host re-runs it
+    // ---- refine the queue (exact f64, the oracle's arithmetic), keeping the (distance, index) top-k --------------------------
+    for (uint32_t e = 0; e < nqueued; e++) {
+        const uint32_t idx = squeue[warp][e];
+        const double ex = warp_dtw_exact(squery[warp], la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, scost[warp], lane);
+        if (!(ex < kInf)) continue;
+        if (n == k && !(ex < dv[k - 1] || (ex == dv[k - 1] && idx < iv[k - 1]))) continue;
+        int pos = n < k ? n : k - 1;
+        while (pos > 0 && (ex < dv[pos - 1] || (ex == dv[pos - 1] && idx < iv[pos - 1]))) {
+            dv[pos] = dv[pos - 1];
+            iv[pos] = iv[pos - 1];
+            pos--;
+        }
+        dv[pos] = ex;
+        iv[pos] = idx;
+        if (n < k) n++;
+    }
+    kth = n >= k ? dv[k - 1] : kInf;
+    // ---- certify against W: every pair outside the union of the slice lists has scan distance >= W -------------------------
+    const unsigned long long t = thr[slot];
+    float w = __int_as_float(0x7f800000);  // no CTA kept a full list: every (finite) pair is in the union
+    if (t != 0xFFFFFFFFFFFFFFFFull) {
+        const uint32_t o = (uint32_t)(t >> 32);
+        w = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+    }
+    const bool certified = scan_lower_bound(w, na, nb, eps, bound_mode, la, inv_s) > kth;
+    if (lane == 0) {
+        for (int s = 0; s < k; s++) {
+            out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
+            out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
+        }
+        if (certified) {
+            uncert_flag[qid] = 0;
+            atomicAdd(&counters[0], ~0ull);  // -1
+            atomicAdd(&counters[2], 1ull);
+        }
+    }
+}
+
+int dtw_second_chance(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, const unsigned long long* d_partial,
+                      uint32_t nlists, const unsigned long long* d_thr, double eps, const float* d_max_na, const float* d_max_nb,
+                      const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag, uint32_t* d_out_idx, double* d_out_dist) {
+    ss_ctx* ctx = d->ctx;
+    if (!nslots || d->max_len > 32 || q->max_len > 32) return SS_OK;
+    k_dtw_second_chance<<<ceil_div(nslots, 2), 64, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid, d->d_cand_idx.p,
+                                                                      d_partial, nlists, d_thr, nslots, kp, std::min(k, kp), d->index_base, d_max_na, d_max_nb,
+                                                                      eps, d_slot_max_na, bound_mode, d->h2_bound_inv_s, d_uncert_flag, d_out_idx, d_out_dist,
+                                                                      d->d_counters.p);
+    SS_LAUNCHED(ctx);
+    return SS_OK;
+}
+
 __global__ void k_dtw_finalize(const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_adist,
                                const double* __restrict__ exact, const uint32_t* __restrict__ group_qid, uint32_t nslots, int kp,
                                int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb, double eps,

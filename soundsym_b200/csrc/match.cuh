@@ -109,7 +109,7 @@ struct ss_dict {
     ss::DevBuf<uint16_t> d_h2_tiles;
     ss::DevBuf<int4> d_h2_desc;
     ss::DevBuf<unsigned long long> d_h2_thr;   // per query slot: running bound on the global KP-th key (dtw_h2.cu)
-    int scan_pref = 0;  // test / A-B hook (ss_dict_set_scan): 0 = packed-half scan first, 1 = start at the fp32 tensor-core scan, 2 = fp32 CUDA-core scan
+    int scan_pref = 0;  // test / A-B hook (ss_dict_set_scan): 0 = packed-half scan first, 1 = start at the fp32 tensor-core scan, 2 = fp32 CUDA-core scan, 3 = packed-half scan without its second chance
     // the last SS_DTW match is asynchronous up to its fallback decision: ss::dtw_match_finish waits for ev_done, reads the
     // uncertified count from pinned memory and runs the fallback stages for the queries that need them
     struct Pending {

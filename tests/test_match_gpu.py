@@ -183,11 +183,19 @@ def test_tensor_core_scan_fallback_on_near_duplicates(ctx):
     q = np.concatenate([seg, base[int(boff[10]):int(boff[11])]])
     qoff = np.array([0, L, L + int(boff[11] - boff[10])], dtype=np.uint64)
     dev = api.DeviceDictionary(ctx, d, doff)
-    idx, dist = dev.match(q, qoff, SS_DTW, 4)
     oidx, odist = O.dtw_topk(d, doff, q, qoff, 13, 4)
+    # default flow: the packed-half scan's second chance walks the per-slice candidate lists (here: the whole dictionary, no
+    # slice list is full), refines all 43 near-identical segments in f64 and certifies - no later stage runs
+    idx, dist = dev.match(q, qoff, SS_DTW, 4)
     check_dtw(idx, dist, oidx, odist, 4)
     assert list(idx[0, :3]) == [3, 104, 105] and dist[0, 0] == 0.0  # the original and its two exact copies, lowest index first
-    # 43 segments within 1e-7 of each other: neither scan can certify query 0 -> exhaustive f64 stage; nothing stays uncertified
+    assert dev.last_tc_fallback == 0 and dev.last_exhaustive == 0 and dev.last_uncertified == 0
+    # without the second chance (ss_dict_set_scan 3) the later stages are driven: 43 segments within 1e-7 of each other, neither
+    # scan can certify query 0 -> exhaustive f64 stage; nothing stays uncertified
+    dev.set_scan(3)
+    idx, dist = dev.match(q, qoff, SS_DTW, 4)
+    check_dtw(idx, dist, oidx, odist, 4)
+    assert list(idx[0, :3]) == [3, 104, 105] and dist[0, 0] == 0.0
     assert dev.last_tc_fallback >= 1 and dev.last_exhaustive >= 1 and dev.last_uncertified == 0
 
 
