@@ -908,11 +908,12 @@ int dtw_h2_dict_build(ss_dict* d) {
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // d_nb is released on return
     // cost scale S: S |b|^2_max <= 4096, so that a path of 64 typical cells stays far below 65504 (an overflow is not an error:
-    // the pair reads +inf and the bound is capped, see the header); longer paths scale it down further
+    // the pair reads +inf and the bound is capped, see the header); longer paths scale it down further, per query batch
+    // (h2_cost_scale: S only enters the query side's A blocks)
     float S = 1.0f;
     while (S * d->tc_max_nb > 4096.f) S *= 0.5f;
     while (S * d->tc_max_nb < 2048.f && S < 64.f) S *= 2.0f;
-    for (uint32_t l = 64; l < 2 * d->max_len && S > 1.0f / 65536.f; l *= 2) S *= 0.5f;
+    d->h2_s0 = S;
     d->h2_s = S;
     d->h2_bmax = d->tc_max_abs;
     {   // the strip kernel's boundary scratch has one area per SM id
@@ -927,9 +928,18 @@ int dtw_h2_dict_build(ss_dict* d) {
     return SS_OK;
 }
 
+// S for one (dictionary, query batch): halved for every doubling of the longest possible path (Lq + Ld cells) beyond 64, so that
+// path sums of the longest sequences still fit the fp16 range. Sets d->h2_s (what the launch, eta and the bound read).
+static void h2_cost_scale(ss_dict* d, const ss_queries* q) {
+    float S = d->h2_s0;
+    for (uint64_t l = 64; l < (uint64_t)d->max_len + q->max_len && S > 1.0f / 65536.f; l *= 2) S *= 0.5f;
+    d->h2_s = S;
+}
+
 static int h2_queries_build(ss_dict* d, ss_queries* q) {
     ss_ctx* ctx = q->ctx;
-    if (q->h2_built && q->h2_dict_serial == d->tc_serial) return SS_OK;
+    h2_cost_scale(d, q);
+    if (q->h2_built && q->h2_dict_serial == d->tc_serial && q->h2_s_built == d->h2_s) return SS_OK;
     if (!q->tc_grouped) SS_TRY(dtw_tc_queries_group(q));
     SS_CUDA(ctx, q->d_h2_a.reserve(std::max<uint64_t>(q->tc_a_bytes, 16)));
     SS_CUDA(ctx, q->d_tc_slot_max_na.reserve(std::max<size_t>((size_t)q->tc_ngroups * kTcM, 1)));
@@ -945,6 +955,7 @@ static int h2_queries_build(ss_dict* d, ss_queries* q) {
     }
     q->h2_built = true;
     q->h2_dict_serial = d->tc_serial;
+    q->h2_s_built = d->h2_s;
     return SS_OK;
 }
 
@@ -1134,9 +1145,9 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
         const char* e = getenv("SS_DTW_SECOND_CHANCE");
         return e ? atoi(e) != 0 : true;
     }();
-    if (second && !plan.use_long && d->scan_pref != 3) {
+    if (second && d->scan_pref != 3) {
         SS_TRY(dtw_second_chance(d, q, k, kp, plan.nslots, q->d_tc_qid.p, d->d_tc_partial.p, plan.p.nslices, d->d_h2_thr.p, h2_eta(d), q->d_tc_max_norm.p,
-                                 d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, 2, q->d_uncert_flag.p, d_out_idx, d_out_dist));
+                                 d->d_tc_max_norm.p, q->d_tc_slot_max_na.p, plan.use_long ? 3 : 2, q->d_uncert_flag.p, d_out_idx, d_out_dist));
         tt.lap("  h2: second chance (union of the slice lists)");
     }
     *used = true;

@@ -759,15 +759,138 @@ k_dtw_second_chance(const double* __restrict__ dmfcc, const uint64_t* __restrict
     }
 }
 
+// The same for sequences of more than 32 frames (bound_mode 3), one CTA of 8 warps per uncertified query: a long pair takes a warp
+// 0.1 - 0.5 ms, so the queue is refined by the CTA's warps in parallel (each with its own cost ring and boundary row), then
+// thread 0 folds the results into the top-k and certifies.
+constexpr int kSecondWarps = 8;
+__global__ void __launch_bounds__(kSecondWarps * 32)
+k_dtw_second_chance_long(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff, const double* __restrict__ qmfcc,
+                         const uint64_t* __restrict__ qoff, int c, const uint32_t* __restrict__ group_qid, const uint32_t* __restrict__ cand_idx,
+                         const unsigned long long* __restrict__ partial, uint32_t nlists, const unsigned long long* __restrict__ thr,
+                         uint32_t nslots, int kp, int k, uint32_t index_base, const float* __restrict__ max_na, const float* __restrict__ max_nb,
+                         double eps, const float* __restrict__ slot_max_na, int bound_mode, double inv_s, int ld_max, double* __restrict__ bnd,
+                         uint32_t bnd_stride, uint32_t bnd_rows_cap, uint8_t* __restrict__ uncert_flag, uint32_t* __restrict__ out_idx,
+                         double* __restrict__ out_dist, unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char second_smem[];
+    double* rings = reinterpret_cast<double*>(second_smem);                 // [warps][64 * 32]
+    double* sexact = rings + kSecondWarps * 64 * 32;                         // [kSecondQueue]
+    uint32_t* squeue = reinterpret_cast<uint32_t*>(sexact + kSecondQueue);   // [kSecondQueue]
+    __shared__ uint32_t scount;
+    __shared__ unsigned long long srow;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x;
+    const uint32_t qid = group_qid[slot];
+    if (qid == 0xFFFFFFFFu || !uncert_flag[qid]) return;  // CTA-uniform
+    if (threadIdx.x == 0) {
+        scount = 0;
+        srow = atomicAdd(&counters[3], (unsigned long long)kSecondWarps);
+    }
+    __syncthreads();
+    if (srow + kSecondWarps > bnd_rows_cap) return;  // no boundary rows left: stays uncertified
+    double* my_bnd = bnd + (size_t)(srow + warp) * bnd_stride;
+    const double na = slot_max_na ? (double)slot_max_na[slot] : (double)max_na[0];
+    const double nb = (double)max_nb[0];
+    const double* a = qmfcc + qoff[qid] * c;
+    const int la = (int)(qoff[qid + 1] - qoff[qid]);
+    double kth = out_idx[(size_t)qid * k + k - 1] != 0xFFFFFFFFu ? out_dist[(size_t)qid * k + k - 1] : kInf;
+    const uint32_t my_cand = lane < kp ? cand_idx[(size_t)slot * kp + lane] : 0xFFFFFFFFu;  // already refined
+    // ---- walk the slice lists (32 lists per warp and round) ------------------------------------------------------------------
+    const uint32_t lround = kSecondWarps * 32;
+    for (uint32_t l0 = 0; l0 < nlists; l0 += lround) {
+        const uint32_t l = l0 + warp * 32 + lane;
+        for (int s = 0; s < kp; s++) {
+            unsigned long long key = 0xFFFFFFFFFFFFFFFFull;
+            if (l < nlists) key = __ldg(partial + ((size_t)l * nslots + slot) * kp + s);
+            bool want = false;
+            if (key != 0xFFFFFFFFFFFFFFFFull) {
+                const uint32_t o = (uint32_t)(key >> 32);
+                const float dist = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+                want = !(scan_lower_bound(dist, na, nb, eps, bound_mode, la, inv_s, ld_max) > kth);
+            }
+            if (!__any_sync(0xffffffffu, want)) break;  // lists ascend
+            const uint32_t idx = (uint32_t)key;
+            bool seen = false;
+            for (int j = 0; j < kp; j++) seen |= __shfl_sync(0xffffffffu, my_cand, j) == idx;
+            want = want && !seen;
+            if (want) {
+                const uint32_t pos = atomicAdd(&scount, 1u);
+                if (pos < (uint32_t)kSecondQueue) squeue[pos] = idx;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t nqueued = scount;
+    if (nqueued > (uint32_t)kSecondQueue) return;  // stays uncertified: the host re-runs it
+    for (uint32_t e = warp; e < nqueued; e += kSecondWarps) {
+        const uint32_t idx = squeue[e];
+        const double ex = warp_dtw_exact_long(a, la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, rings + warp * 64 * 32, my_bnd, lane);
+        if (lane == 0) sexact[e] = ex;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double dv[SS_MAX_TOPK];
+    uint32_t iv[SS_MAX_TOPK];
+    int n = 0;
+    for (int s = 0; s < k; s++) {
+        const uint32_t ii = out_idx[(size_t)qid * k + s];
+        if (ii == 0xFFFFFFFFu) break;
+        iv[n] = ii - index_base;
+        dv[n] = out_dist[(size_t)qid * k + s];
+        n++;
+    }
+    for (uint32_t e = 0; e < nqueued; e++) {
+        const uint32_t idx = squeue[e];
+        const double ex = sexact[e];
+        if (!(ex < kInf)) continue;
+        if (n == k && !(ex < dv[k - 1] || (ex == dv[k - 1] && idx < iv[k - 1]))) continue;
+        int pos = n < k ? n : k - 1;
+        while (pos > 0 && (ex < dv[pos - 1] || (ex == dv[pos - 1] && idx < iv[pos - 1]))) {
+            dv[pos] = dv[pos - 1];
+            iv[pos] = iv[pos - 1];
+            pos--;
+        }
+        dv[pos] = ex;
+        iv[pos] = idx;
+        if (n < k) n++;
+    }
+    kth = n >= k ? dv[k - 1] : kInf;
+    const unsigned long long t = thr[slot];
+    float w = __int_as_float(0x7f800000);
+    if (t != 0xFFFFFFFFFFFFFFFFull) {
+        const uint32_t o = (uint32_t)(t >> 32);
+        w = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+    }
+    for (int s = 0; s < k; s++) {
+        out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
+        out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
+    }
+    if (scan_lower_bound(w, na, nb, eps, bound_mode, la, inv_s, ld_max) > kth) {
+        uncert_flag[qid] = 0;
+        atomicAdd(&counters[0], ~0ull);  // -1
+        atomicAdd(&counters[2], 1ull);
+    }
+}
+
 int dtw_second_chance(ss_dict* d, ss_queries* q, int k, int kp, uint32_t nslots, const uint32_t* d_slot_qid, const unsigned long long* d_partial,
                       uint32_t nlists, const unsigned long long* d_thr, double eps, const float* d_max_na, const float* d_max_nb,
                       const float* d_slot_max_na, int bound_mode, uint8_t* d_uncert_flag, uint32_t* d_out_idx, double* d_out_dist) {
     ss_ctx* ctx = d->ctx;
-    if (!nslots || d->max_len > 32 || q->max_len > 32) return SS_OK;
-    k_dtw_second_chance<<<ceil_div(nslots, 2), 64, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid, d->d_cand_idx.p,
-                                                                      d_partial, nlists, d_thr, nslots, kp, std::min(k, kp), d->index_base, d_max_na, d_max_nb,
-                                                                      eps, d_slot_max_na, bound_mode, d->h2_bound_inv_s, d_uncert_flag, d_out_idx, d_out_dist,
-                                                                      d->d_counters.p);
+    if (!nslots) return SS_OK;
+    if (d->max_len > 32 || q->max_len > 32) {
+        const uint32_t stride = (std::max<uint32_t>(q->max_len, 1) + 15) & ~15u;
+        const uint32_t rows_cap = (uint32_t)std::max<uint64_t>(kSecondWarps, std::min<uint64_t>((uint64_t)nslots * kSecondWarps, (4ull << 20) / stride));
+        SS_CUDA(ctx, d->d_second_bnd.reserve((size_t)rows_cap * stride));  // <= 32 MB of boundary rows
+        const size_t smem = (size_t)kSecondWarps * 64 * 32 * sizeof(double) + kSecondQueue * (sizeof(double) + sizeof(uint32_t));
+        SS_CUDA(ctx, cudaFuncSetAttribute(k_dtw_second_chance_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dtw_second_chance_long<<<nslots, kSecondWarps * 32, smem, ctx->stream>>>(
+            d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid, d->d_cand_idx.p, d_partial, nlists, d_thr, nslots, kp, std::min(k, kp),
+            d->index_base, d_max_na, d_max_nb, eps, d_slot_max_na, bound_mode, d->h2_bound_inv_s, (int)d->max_len, d->d_second_bnd.p, stride, rows_cap,
+            d_uncert_flag, d_out_idx, d_out_dist, d->d_counters.p);
+    } else {
+        k_dtw_second_chance<<<ceil_div(nslots, 2), 64, 0, ctx->stream>>>(
+            d->d_mfcc.p, d->d_off.p, q->d_mfcc.p, q->d_off.p, d->c, d_slot_qid, d->d_cand_idx.p, d_partial, nlists, d_thr, nslots, kp, std::min(k, kp),
+            d->index_base, d_max_na, d_max_nb, eps, d_slot_max_na, bound_mode, d->h2_bound_inv_s, d_uncert_flag, d_out_idx, d_out_dist, d->d_counters.p);
+    }
     SS_LAUNCHED(ctx);
     return SS_OK;
 }

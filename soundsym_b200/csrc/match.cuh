@@ -62,6 +62,7 @@ struct ss_dict {
     ss::DevBuf<float> d_cand_adist;
     ss::DevBuf<double> d_cand_exact;
     ss::DevBuf<double> d_rescore_rows;
+    ss::DevBuf<double> d_second_bnd;  // boundary rows of the long second-chance kernel (exact.cu)
     ss::DevBuf<unsigned long long> d_counters;  // [0] uncertified
     std::vector<uint32_t> h_slice_tile;
     uint64_t last_work = 0, last_uncertified = 0;
@@ -98,7 +99,8 @@ struct ss_dict {
         ss::DevBuf<uint32_t> d_slice_tile;
     };
     std::map<uint32_t, std::unique_ptr<H2Slices>> h2_slices;
-    float h2_s = 1.f;                           // power-of-two cost scale S
+    float h2_s = 1.f;                           // power-of-two cost scale S of the current match (h2_cost_scale)
+    float h2_s0 = 1.f;                          // S for paths of <= 64 cells (from the dictionary's largest frame norm)
     float h2_bmax = 0.f;                        // max |fp16(b - mu)| (bound's eta)
     double h2_bound_inv_s = 1.0;
     std::vector<uint32_t> h_h2_tile_cost;
@@ -167,6 +169,7 @@ struct ss_queries {
     uint64_t tc_a_bytes = 0;
     bool h2_built = false;                   // the packed-half scan's A blocks (the same rows scaled by S)
     uint64_t h2_dict_serial = 0;
+    float h2_s_built = 0.f;                  // the cost scale S those A blocks carry
     ss::DevBuf<unsigned char> d_h2_a;
     uint32_t tc_ngroups = 0;
     std::vector<uint32_t> h_tc_group_len;

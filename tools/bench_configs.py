@@ -195,7 +195,7 @@ def run_config5(args):
         r = flow(t)
         t["total_ms"] = (time.perf_counter() - t0) * 1e3
         runs.append(t)
-    warm = {k: float(np.mean([t.get(k, 0.0) for t in runs])) for k in keys + ["total_ms"]}
+    warm = {k: float(np.median([t.get(k, 0.0) for t in runs])) for k in keys + ["total_ms"]}  # (median: a host hiccup in one run is not the flow)
     vals = [warm[k] for k in keys + ["total_ms"]]
     if world > 1:
         tt = torch.tensor(vals, dtype=torch.float64, device="cuda")
@@ -211,7 +211,7 @@ def run_config5(args):
                            "seconds": args.seconds, "mode": args.mode},
                 "e2e": {"value": nq / (tm["total_ms"] * 1e-3), "unit": "segments/s", "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": int(len(audio) * 8),
                         "note": "the flow is host-buffer to host-buffer throughout (integer PCM in, resynthesised f64 samples out): value is the e2e number"},
-                "stage_ms_warm": tm, "stage_ms_cold_rank0": cold, "source_frames": r["src_frames"], "target_frames": r["tgt_frames"],
+                "stage_ms_warm": tm, "stage_ms_cold_rank0": cold, "match_ms_runs_rank0": [t.get("match_ms") for t in runs], "source_frames": r["src_frames"], "target_frames": r["tgt_frames"],
                 "dictionary_segments": r["nd"], "target_segments": nq, "max_segment_frames": r["maxlen"],
                 "match_pairs_per_s": r["nd"] * nq / (tm["match_ms"] * 1e-3), "match_info": r["info"],
                 "idx_sha1": hashlib.sha1(r["idx"].tobytes()).hexdigest()[:16], "dist_sha1": hashlib.sha1(r["dst"].tobytes()).hexdigest()[:16],
