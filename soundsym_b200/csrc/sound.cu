@@ -167,6 +167,12 @@ __device__ __forceinline__ void dft8(cplx* u) {
 
 constexpr int kMfccWarps = 4;
 constexpr int kHalf = SS_BIN / 2;  // 512
+// Where element `idx` of the warp's 512 x double2 exchange buffer lives: the low three index bits are XOR-ed with the next
+// three. A quarter-warp's 16-byte accesses are conflict-free when its 8 addresses cover 8 different 16-byte bank groups; the
+// Stockham stores of passes 0 and 1 go to idx = 8 i + t and (i & ~7) 8 + (i & 7) + 8 t (lane i, fixed t) - stride 8 in the low
+// bits, an 8-way conflict in the natural layout (pass 0 alone was half of the kernel's shared-memory wavefronts) - and the
+// loads to idx = i + 64 t; with the swizzle every one of them touches 8 distinct groups.
+__device__ __forceinline__ int mfcc_sw(int idx) { return idx ^ ((idx >> 3) & 7); }
 
 // largest s in [0, n) with off[s] <= x (off ascending, off[0] = 0 <= x < off[n])
 __device__ __forceinline__ uint32_t seg_of(const uint64_t* __restrict__ off, uint32_t n, uint64_t x) {
@@ -227,7 +233,7 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
             }
             dft8(u[h]);
 #pragma unroll
-            for (int t = 0; t < 8; t++) buf[8 * i + t] = make_double2(u[h][t].x, u[h][t].y);
+            for (int t = 0; t < 8; t++) buf[mfcc_sw(8 * i + t)] = make_double2(u[h][t].x, u[h][t].y);
         }
         __syncwarp();
         // ---- passes 1, 2 (Ns = 8, 64) -------------------------------------------------------------------------------
@@ -241,7 +247,7 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
                 const int k = i & (p - 1);
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    const double2 v = buf[i + 64 * t];
+                    const double2 v = buf[mfcc_sw(i + 64 * t)];
                     const double2 w = __ldg(&tw[(t * k * tstep) & (SS_BIN - 1)]);
                     u[h][t] = cmul(cplx{v.x, v.y}, cplx{w.x, w.y});
                 }
@@ -254,14 +260,14 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
                 const int k = i & (p - 1);
                 const int jo = ((i - k) << 3) + k;
 #pragma unroll
-                for (int t = 0; t < 8; t++) buf[jo + t * p] = make_double2(u[h][t].x, u[h][t].y);
+                for (int t = 0; t < 8; t++) buf[mfcc_sw(jo + t * p)] = make_double2(u[h][t].x, u[h][t].y);
             }
             __syncwarp();
         }
         // ---- even/odd split: X[k] = E[k] + W_1024^k O[k] for the bins of the mel bank; power |X|^2 (A3) -------------
         for (int k = kb0 + lane; k < kb1; k += 32) {
-            const double2 zk = buf[k & (kHalf - 1)];
-            const double2 zm = buf[(kHalf - k) & (kHalf - 1)];
+            const double2 zk = buf[mfcc_sw(k & (kHalf - 1))];
+            const double2 zm = buf[mfcc_sw((kHalf - k) & (kHalf - 1))];
             const cplx e = {0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y)};
             const cplx o = {0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x)};  // (Zk - conj(Zm)) / (2i)
             const double2 w = __ldg(&tw[k]);

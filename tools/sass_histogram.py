@@ -16,4 +16,7 @@ for obj in sys.argv[1:]:
             if m:
                 ops[m.group(1).split(".")[0] + ("." + m.group(1).split(".")[1] if m.group(1).startswith(("LDTM", "UTC", "UBLKCP")) and "." in m.group(1) else "")] += 1
         demangled = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
-        print("%s\n   %d instructions: %s" % (demangled[:140], sum(ops.values()), ", ".join("%s %d" % kv for kv in ops.most_common(48))))
+        top = ops.most_common(48)
+        proof = [(k, v) for k, v in ops.items() if k.startswith(("UTC", "LDTM", "STTM", "UBLKCP", "UTMA", "USETMAXREG", "VHMNMX", "FMNMX3", "HMMA")) and (k, v) not in top]
+        print("%s\n   %d instructions: %s%s" % (demangled[:140], sum(ops.values()), ", ".join("%s %d" % kv for kv in top),
+                                               ("; [tensor / TMEM / TMA] " + ", ".join("%s %d" % kv for kv in sorted(proof))) if proof else ""))
