@@ -511,7 +511,6 @@ static int launch_scan(ss_ctx* ctx, const ScanParams& p, uint32_t grid) {
     return SS_OK;
 }
 
-static int g_scan_rb = 0;  // 0 = default; tools/tests may override through SS_DTW_RB
 
 static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, double* d_out_dist, const std::vector<uint32_t>* subset);
 
@@ -767,11 +766,10 @@ static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx,
     const uint32_t nqb = (q->ngroups + kWarpsPerCta - 1) / kWarpsPerCta;
     uint32_t nslices = 1;
     if (nqb && d->ntiles) {
-        static int waves = 0;
-        if (!waves) {
+        static const int waves = [] {  // (initialised once, thread-safe)
             const char* e = getenv("SS_DTW_WAVES");
-            waves = e ? std::max(1, atoi(e)) : 8;
-        }
+            return e ? std::max(1, atoi(e)) : 8;
+        }();
         const uint32_t target_ctas = (uint32_t)ctx->sm_count * 4 * waves;  // ~`waves` waves at 4 CTAs / SM
         nslices = std::max<uint32_t>(1, std::min<uint32_t>(d->ntiles, (target_ctas + nqb - 1) / nqb));
     }
@@ -795,11 +793,11 @@ static int dtw_fp32_match(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx,
     SS_CUDA(ctx, d->d_cand_adist.reserve(std::max<size_t>((size_t)nslots * kp, 1)));
 
     if (nqb) {
-        if (!g_scan_rb) {
+        static const int g_scan_rb = [] {  // rows per pass; tools may override through SS_DTW_RB (read once, thread-safe)
             const char* e = getenv("SS_DTW_RB");
-            g_scan_rb = e ? atoi(e) : 4;
-            if (g_scan_rb != 1 && g_scan_rb != 2 && g_scan_rb != 4) g_scan_rb = 4;
-        }
+            const int v = e ? atoi(e) : 4;
+            return (v == 1 || v == 2) ? v : 4;
+        }();
         const uint32_t grid = nqb * nslices;
         ScanParams p;
         p.qlane = q->d_lane.p;

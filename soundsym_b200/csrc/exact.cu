@@ -86,24 +86,37 @@ __global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ 
         if (!active) continue;
         // ---- chunks of 8 ---------------------------------------------------------------------------------------------
         double p[kCosG][8];
-        size_t nchunk[kCosG], len[kCosG];
-        size_t maxchunk = 0;
+        uint32_t nchunk[kCosG], len[kCosG];
+        uint32_t maxchunk = 0;
+        bool all_staged = true;
 #pragma unroll
         for (int u = 0; u < kCosG; u++) {
-            len[u] = kd[u] < kq ? kd[u] : kq;
+            len[u] = (uint32_t)(kd[u] < kq ? kd[u] : kq);
             nchunk[u] = len[u] / 8;
             maxchunk = nchunk[u] > maxchunk ? nchunk[u] : maxchunk;
+            all_staged = all_staged && kd[u] <= (size_t)kCosSegCap;
 #pragma unroll
             for (int v = 0; v < 8; v++) p[u][v] = 0.0;
         }
-        for (size_t ch = 0; ch < maxchunk; ch++) {
+        if (all_staged) {
+            // every segment of the group sits in shared memory (always, for segments of <= 39 frames): 32-bit indices, and the
+            // query's next chunk is fetched while the current one is consumed
+            const double* yp = y;
             double yv[8];
+            if (maxchunk) {
 #pragma unroll
-            for (int v = 0; v < 8; v++) yv[v] = y[(ch * 8 + v) * 32];
+                for (int v = 0; v < 8; v++) yv[v] = yp[v * 32];
+            }
+            for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                double yn[8];
+                yp += 8 * 32;
+                if (ch + 1 < maxchunk) {
 #pragma unroll
-            for (int u = 0; u < kCosG; u++) {
-                if (ch < nchunk[u]) {  // warp-uniform
-                    if (kd[u] <= (size_t)kCosSegCap) {
+                    for (int v = 0; v < 8; v++) yn[v] = yp[v * 32];
+                }
+#pragma unroll
+                for (int u = 0; u < kCosG; u++) {
+                    if (ch < nchunk[u]) {  // warp-uniform
                         const double2* xs = reinterpret_cast<const double2*>(&sseg[u][ch * 8]);
 #pragma unroll
                         for (int v = 0; v < 4; v++) {
@@ -111,9 +124,31 @@ __global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ 
                             p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
                             p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
                         }
-                    } else {
+                    }
+                }
 #pragma unroll
-                        for (int v = 0; v < 8; v++) p[u][v] = p[u][v] + __ldg(xg[u] + ch * 8 + v) * yv[v];
+                for (int v = 0; v < 8; v++) yv[v] = yn[v];
+            }
+        } else {
+            for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                double yv[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++) yv[v] = y[((size_t)ch * 8 + v) * 32];
+#pragma unroll
+                for (int u = 0; u < kCosG; u++) {
+                    if (ch < nchunk[u]) {  // warp-uniform
+                        if (kd[u] <= (size_t)kCosSegCap) {
+                            const double2* xs = reinterpret_cast<const double2*>(&sseg[u][ch * 8]);
+#pragma unroll
+                            for (int v = 0; v < 4; v++) {
+                                const double2 xx = xs[v];
+                                p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
+                                p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+                            }
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < 8; v++) p[u][v] = p[u][v] + __ldg(xg[u] + (size_t)ch * 8 + v) * yv[v];
+                        }
                     }
                 }
             }
@@ -127,9 +162,9 @@ __global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ 
                 sum = sum + (p[u][1] + p[u][5]);
                 sum = sum + (p[u][2] + p[u][6]);
                 sum = sum + (p[u][3] + p[u][7]);
-                for (size_t e = nchunk[u] * 8; e < len[u]; e++) {
+                for (uint32_t e = nchunk[u] * 8; e < len[u]; e++) {
                     const double xv = kd[u] <= (size_t)kCosSegCap ? sseg[u][e] : __ldg(xg[u] + e);
-                    sum = sum + xv * y[e * 32];
+                    sum = sum + xv * y[(size_t)e * 32];
                 }
                 const double nrm = dnorm[s0 + u] * nq;   // norm(me) * norm(you), src/sound.rs:30
                 const double sim = sum / nrm;            // src/sound.rs:32
@@ -291,28 +326,50 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
 //     rounded-frame distance already - (scan - eta)(1 + 2^-11)^-(Lq + Ld + 2), computed by the scan - so w needs no common
 //     factor; only the cap remains (a path sum beyond the fp16 range reads +inf whatever the pair: its rounded-frame
 //     distance is at least the bound of a pair of the longest segment, ld_max, at 60000 / S):  t = min(w, cap)
+// The per-query part (two square roots, one exponential) is computed once (make_scan_bound); lower() is what runs per candidate.
+struct ScanBound {
+    int mode;
+    double a, delta, cap, defl;  // a: the additive term of modes 0 / 1 (eps (na + nb) / E32), eta of mode 2
+    __device__ __forceinline__ double lower(float scan) const {
+        if (mode == 0) return (double)scan - a;
+        const double w = scan > 0.f ? (double)scan : 0.0;  // (+inf stays +inf)
+        if (mode == 3) {
+            const double t = fmin(w, cap);
+            return t - 2.0 * delta * sqrt(t);
+        }
+        if (mode == 2) {
+            const double v = fmin(w, cap) - a;
+            const double t = v > 0.0 ? v * defl : 0.0;
+            return t - 2.0 * delta * sqrt(t);
+        }
+        return w - 2.0 * delta * sqrt(w) - a;
+    }
+};
+__device__ __forceinline__ ScanBound make_scan_bound(double na, double nb, double eps, int bound_mode, int la = 0, double inv_s = 0.0, int ld_max = 32) {
+    ScanBound b;
+    b.mode = bound_mode;
+    b.delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
+    b.cap = 0.0, b.defl = 1.0;
+    if (bound_mode == 0) {
+        b.a = eps * (na + nb);
+    } else if (bound_mode == 3) {
+        const double n = (double)(la + ld_max);
+        b.a = 0.0;
+        b.cap = fmax(60000.0 * inv_s / n - 1.001 * eps, 0.0) * exp(-(n + 2.0) * 4.8937e-4 /* = 7.06e-4 ln 2, as the scan */);
+    } else if (bound_mode == 2) {
+        b.a = eps;
+        b.cap = 60000.0 * inv_s / (double)(la + 32);
+        b.defl = exp(-(double)(la + 34) * 4.8816207e-4 /* > ln(1 + 2^-11) */);
+    } else {
+        // E32: fp32 accumulation of the 16 products in the tensor core (<= 16 ulp of na + nb + 2 sqrt(na nb), truncating)
+        // plus <= Lq + Ld <= 64 roundings of the running sum along the path
+        b.a = 2e-5 * (na + nb);
+    }
+    return b;
+}
 __device__ __forceinline__ double scan_lower_bound(float scan, double na, double nb, double eps, int bound_mode, int la = 0, double inv_s = 0.0,
                                                    int ld_max = 32) {
-    if (bound_mode == 0) return (double)scan - eps * (na + nb);
-    const double delta = 1.001 * (sqrt(na) + sqrt(nb)) / 2048.0 + 1e-6;
-    if (bound_mode == 3) {
-        const double n = (double)(la + ld_max);
-        const double cap = fmax(60000.0 * inv_s / n - 1.001 * eps, 0.0) * exp(-(n + 2.0) * 4.8937e-4 /* = 7.06e-4 ln 2, as the scan */);
-        const double w = scan > 0.f ? (double)scan : 0.0;
-        const double t = fmin(w, cap);
-        return t - 2.0 * delta * sqrt(t);
-    }
-    if (bound_mode == 2) {
-        const double cap = 60000.0 * inv_s / (double)(la + 32);
-        double w = scan > 0.f ? (double)scan : 0.0;  // (+inf stays +inf)
-        w = fmin(w, cap) - eps;
-        const double t = w > 0.0 ? w * exp(-(double)(la + 34) * 4.8816207e-4 /* > ln(1 + 2^-11) */) : 0.0;
-        return t - 2.0 * delta * sqrt(t);
-    }
-    const double w = scan > 0.f ? (double)scan : 0.0;
-    // E32: fp32 accumulation of the 16 products in the tensor core (<= 16 ulp of na + nb + 2 sqrt(na nb), truncating)
-    // plus <= Lq + Ld <= 64 roundings of the running sum along the path
-    return w - 2.0 * delta * sqrt(w) - 2e-5 * (na + nb);
+    return make_scan_bound(na, nb, eps, bound_mode, la, inv_s, ld_max).lower(scan);
 }
 
 // Thread t of the launch handles candidate s_begin + t % s_count of slot t / s_count. Two launches per match:
@@ -472,6 +529,7 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
     __syncwarp();
     double my_exact = kInf, kth = 0.0;
     unsigned extra = 0;
+    const ScanBound bound = make_scan_bound(na, nb, eps, bound_mode, la, inv_s);
     for (int s = 0; s < kp; s++) {
         const uint32_t idx = __shfl_sync(0xffffffffu, my_idx, s);
         if (idx == 0xFFFFFFFFu) {
@@ -480,7 +538,7 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
         }
         if (s >= k) {
             const float adist = __shfl_sync(0xffffffffu, my_adist, s);
-            if (scan_lower_bound(adist, na, nb, eps, bound_mode, la, inv_s) > kth) continue;  // provably outside the top-k
+            if (bound.lower(adist) > kth) continue;  // provably outside the top-k
             extra++;
         }
         const double e = warp_dtw_exact(squery[warp], la, dmfcc + doff[idx] * c, (int)(doff[idx + 1] - doff[idx]), c, scost[warp], lane);
@@ -516,7 +574,7 @@ k_dtw_refine_warp(const double* __restrict__ dmfcc, const uint64_t* __restrict__
         // inserted - so the bound is evaluated anyway, at its cap)
         if (bound_mode == 2 || worst < __int_as_float(0x7f800000)) {
             const double kth_exact = n >= k ? dv[k - 1] : kInf;
-            uncertified = !(scan_lower_bound(worst, na, nb, eps, bound_mode, la, inv_s) > kth_exact);
+            uncertified = !(bound.lower(worst) > kth_exact);
             if (uncertified) atomicAdd(&counters[0], 1ull);
         }
         if (uncert_flag) uncert_flag[qid] = uncertified ? 1 : 0;
@@ -680,6 +738,7 @@ k_dtw_second_chance(const double* __restrict__ dmfcc, const uint64_t* __restrict
     const double nb = (double)max_nb[0];
     const double* a = qmfcc + qoff[qid] * c;
     const int la = (int)(qoff[qid + 1] - qoff[qid]);
+    const ScanBound bound = make_scan_bound(na, nb, eps, bound_mode, la, inv_s);
     // current top-k (the k best of the merged list's kp candidates, exact)
     double dv[SS_MAX_TOPK];
     uint32_t iv[SS_MAX_TOPK];
@@ -705,7 +764,7 @@ k_dtw_second_chance(const double* __restrict__ dmfcc, const uint64_t* __restrict
             if (key != 0xFFFFFFFFFFFFFFFFull) {
                 const uint32_t o = (uint32_t)(key >> 32);
                 const float dist = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
-                want = !(scan_lower_bound(dist, na, nb, eps, bound_mode, la, inv_s) > kth);
+                want = !(bound.lower(dist) > kth);
             }
             if (!__any_sync(0xffffffffu, want)) break;  // lists ascend: nothing further down any of these 32 lists qualifies
             const uint32_t idx = (uint32_t)key;
@@ -745,7 +804,7 @@ k_dtw_second_chance(const double* __restrict__ dmfcc, const uint64_t* __restrict
         const uint32_t o = (uint32_t)(t >> 32);
         w = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
     }
-    const bool certified = scan_lower_bound(w, na, nb, eps, bound_mode, la, inv_s) > kth;
+    const bool certified = bound.lower(w) > kth;
     if (lane == 0) {
         for (int s = 0; s < k; s++) {
             out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
@@ -792,6 +851,7 @@ k_dtw_second_chance_long(const double* __restrict__ dmfcc, const uint64_t* __res
     const double nb = (double)max_nb[0];
     const double* a = qmfcc + qoff[qid] * c;
     const int la = (int)(qoff[qid + 1] - qoff[qid]);
+    const ScanBound bound = make_scan_bound(na, nb, eps, bound_mode, la, inv_s, ld_max);
     double kth = out_idx[(size_t)qid * k + k - 1] != 0xFFFFFFFFu ? out_dist[(size_t)qid * k + k - 1] : kInf;
     const uint32_t my_cand = lane < kp ? cand_idx[(size_t)slot * kp + lane] : 0xFFFFFFFFu;  // already refined
     // ---- walk the slice lists (32 lists per warp and round) ------------------------------------------------------------------
@@ -805,7 +865,7 @@ k_dtw_second_chance_long(const double* __restrict__ dmfcc, const uint64_t* __res
             if (key != 0xFFFFFFFFFFFFFFFFull) {
                 const uint32_t o = (uint32_t)(key >> 32);
                 const float dist = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
-                want = !(scan_lower_bound(dist, na, nb, eps, bound_mode, la, inv_s, ld_max) > kth);
+                want = !(bound.lower(dist) > kth);
             }
             if (!__any_sync(0xffffffffu, want)) break;  // lists ascend
             const uint32_t idx = (uint32_t)key;
@@ -864,7 +924,7 @@ k_dtw_second_chance_long(const double* __restrict__ dmfcc, const uint64_t* __res
         out_idx[(size_t)qid * k + s] = s < n ? iv[s] + index_base : 0xFFFFFFFFu;
         out_dist[(size_t)qid * k + s] = s < n ? dv[s] : kInf;
     }
-    if (scan_lower_bound(w, na, nb, eps, bound_mode, la, inv_s, ld_max) > kth) {
+    if (bound.lower(w) > kth) {
         uncert_flag[qid] = 0;
         atomicAdd(&counters[0], ~0ull);  // -1
         atomicAdd(&counters[2], 1ull);
