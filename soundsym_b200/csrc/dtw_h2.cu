@@ -76,7 +76,15 @@ struct H2Params {
     __half2* bnd;                 // LONG kernel: [%nsmid][bnd_rows][256] boundary columns between the strips of a long segment
     uint32_t bnd_rows;
     float eta;                    // LONG kernel: subtracted from a pair's scan distance before its key is deflated (bound_mode 3)
+    // measurement hook (SS_DTW_H2_TIMELINE=<file>, nullptr otherwise): per CTA {start, setup done, DP done, end} in %globaltimer ns,
+    // then {smid, kind, group, slice} - [grid][8] u64, written by thread 0
+    unsigned long long* timeline;
 };
+__device__ __forceinline__ unsigned long long h2_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- packed TMEM loads: N registers <- 2 N adjacent columns ---------------------------------------------------------------
 template <int N>
@@ -398,6 +406,12 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
     const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;
     const uint32_t t0 = p.slice_tile[slice], t1 = p.slice_tile[slice + 1];
     const uint32_t ntiles = t1 - t0;
+    unsigned long long* tl = p.timeline ? p.timeline + ((size_t)(p.slice_begin * p.ngroups) + blockIdx.x) * 8 : nullptr;
+    if (tl && threadIdx.x == 0) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        tl[0] = h2_now(), tl[4] = smid, tl[5] = NB, tl[6] = g, tl[7] = ((unsigned long long)L << 32) | ntiles;
+    }
 
     if (threadIdx.x == 0) {
         mb_init(a_full, 1);
@@ -413,6 +427,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tl && threadIdx.x == 0) tl[1] = h2_now();
     if (warp == kH2DpWarps) {
         if (lane == 0 && ntiles) {
             // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------------
@@ -510,6 +525,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         }
         // the two slots' lists of query m (threads m, m + 128) are merged by the slot-0 thread
         asm volatile("bar.sync 1, %0;" ::"n"(kH2DpThreads) : "memory");
+        if (tl && threadIdx.x == 0) tl[2] = h2_now();
         if (slot == 0) {
             const unsigned long long* other = list + kTcM;
             for (int s = 0; s < KP; s++) {  // ascending: stop at the first key that does not make the cut
@@ -532,6 +548,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+    if (tl && threadIdx.x == 0) tl[3] = h2_now();
 }
 
 // ---- the same scan for LONG sequences: dictionary segments of more than 32 frames are cut into 32-column strips (tiles of the
@@ -887,7 +904,9 @@ int dtw_h2_dict_build(ss_dict* d) {
             desc.push_back(make_int4((int)lens[0], (int)lens[1], ng, 0));
             desc.push_back(make_int4(whole[0], whole[1], whole[2], whole[3]));
         }
-        push_tile(nb, ng, 24u + 16u * (uint32_t)(nb * ng), false);
+        // cost of one two-row step of the tile, relative: measured per kind with the per-CTA timeline (SS_DTW_H2_TIMELINE,
+        // tools/h2_timeline.py): 0.385 / 0.399 / 0.575 us for NB = 1 / 2 / 4 - four short bands cost 1.5 x what the column count says
+        push_tile(nb, ng, (24u + 16u * (uint32_t)(nb * ng)) * (nb == 4 ? 3u : 2u) / 2u, false);
         o += take;
     }
     while (cur_kind < 4) {
@@ -1012,9 +1031,16 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
         std::vector<uint32_t> st;
         uint64_t total = 0;
         for (uint32_t f : d->h_h2_tile_cost) total += f;
-        const uint64_t per = std::max<uint64_t>(1, (total + want - 1) / want);
+        const uint64_t per0 = std::max<uint64_t>(1, (total + want - 1) / want);
+        // the kind that is launched LAST gets slices of half the cost: the step ends when its slowest CTA does, and the timeline
+        // showed 2.7 % of the step's SM-time idle behind the last CTAs (one wave of 158 CTAs of 1.0 - 4.4 ms each at config 4)
+        int last_kind = -1, nkinds = 0;
+        for (int kind = 0; kind < 3; kind++)
+            if (d->h2_first_tile[kind + 1] > d->h2_first_tile[kind]) last_kind = kind, nkinds++;
+        if (nkinds < 2) last_kind = -1;  // (a single kind keeps its wave count)
         for (int kind = 0; kind < 3; kind++) {
             sl->kind_slice[kind] = (uint32_t)st.size();
+            const uint64_t per = kind == last_kind ? std::max<uint64_t>(1, per0 / 2) : per0;
             uint64_t acc = per;  // forces a slice start at the first tile of the kind
             for (uint32_t t = d->h2_first_tile[kind]; t < d->h2_first_tile[kind + 1]; t++) {
                 if (acc >= per && !d->h_h2_tile_cont[t]) st.push_back(t), acc = 0;  // (the strips of a long segment stay in one slice)
@@ -1058,6 +1084,7 @@ static int h2_plan(ss_dict* d, ss_queries* q, int kp, H2Plan* plan) {
     p.bnd = nullptr;
     p.bnd_rows = 0;
     p.eta = 0.f;
+    p.timeline = nullptr;
     if (plan->use_long) {
         if (d->h2_has_strips) {
             p.bnd_rows = (q->max_len + 1) & ~1u;
@@ -1120,6 +1147,12 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     H2Plan plan;
     SS_TRY(h2_plan(d, q, kp, &plan));
     tt.lap("  h2: plan (slices, workspaces)");
+    if (getenv("SS_DTW_H2_TIMELINE") && !plan.use_long) {
+        const size_t n = (size_t)plan.p.ngroups * plan.p.nslices * 8;
+        SS_CUDA(ctx, d->d_h2_timeline.reserve(n));
+        SS_CUDA(ctx, cudaMemsetAsync(d->d_h2_timeline.p, 0, n * sizeof(unsigned long long), ctx->stream));
+        plan.p.timeline = d->d_h2_timeline.p;
+    }
     if (!d->in_fallback) SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     if (kp == 8) SS_TRY((h2_launch_all<8, false>(ctx, plan)));
     else if (kp == 16) SS_TRY((h2_launch_all<16, false>(ctx, plan)));
@@ -1133,6 +1166,19 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
     else k_tc_merge<32><<<ceil_div(plan.nslots, 8), 256, 0, ctx->stream>>>(d->d_tc_partial.p, plan.p.nslices, plan.nslots, d->d_cand_idx.p, d->d_cand_adist.p);
     SS_LAUNCHED(ctx);
     tt.lap("  h2: scan + merge");
+    if (plan.p.timeline) {  // SS_DTW_H2_TIMELINE: one line per CTA (measurement only; synchronises)
+        const size_t n = (size_t)plan.p.ngroups * plan.p.nslices;
+        std::vector<unsigned long long> h(n * 8);
+        SS_CUDA(ctx, cudaMemcpyAsync(h.data(), plan.p.timeline, n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (FILE* f = fopen(getenv("SS_DTW_H2_TIMELINE"), "w")) {
+            fprintf(f, "# cta start_ns setup_ns dp_done_ns end_ns smid kind group L ntiles\n");
+            for (size_t i = 0; i < n; i++)
+                fprintf(f, "%zu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i, h[i * 8], h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3], h[i * 8 + 4], h[i * 8 + 5],
+                        h[i * 8 + 6], h[i * 8 + 7] >> 32, h[i * 8 + 7] & 0xFFFFFFFFull);
+            fclose(f);
+        }
+    }
     // bound_mode 2: eps carries eta; the cap (an overflowed path reads +inf) is 60000 / (S (Lq + 32)), passed as the scale 1 / S.
     // bound_mode 3 (strip kernel): the keys are per-pair lower bounds already; eta and the longest segment go into the cap.
     d->h2_bound_inv_s = 1.0 / (double)d->h2_s;

@@ -110,6 +110,7 @@ struct ss_dict {
     uint32_t h2_nsmid = 0;                      // %nsmid of the device
     ss::DevBuf<uint16_t> d_h2_tiles;
     ss::DevBuf<int4> d_h2_desc;
+    ss::DevBuf<unsigned long long> d_h2_timeline;  // SS_DTW_H2_TIMELINE measurement hook
     ss::DevBuf<unsigned long long> d_h2_thr;   // per query slot: running bound on the global KP-th key (dtw_h2.cu)
     int scan_pref = 0;  // test / A-B hook (ss_dict_set_scan): 0 = packed-half scan first, 1 = start at the fp32 tensor-core scan, 2 = fp32 CUDA-core scan, 3 = packed-half scan without its second chance
     // the last SS_DTW match is asynchronous up to its fallback decision: ss::dtw_match_finish waits for ev_done, reads the
