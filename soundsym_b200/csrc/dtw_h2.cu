@@ -484,9 +484,15 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
         TcCursor cur;
         cur.init(s32(t_full), lane_addr);
+        // the NEXT tile's descriptors are fetched while the current tile is processed: a tile of a short query group is only 2 - 4
+        // steps long, and an L2 round trip at its start stalled the warp - and within two steps the whole pipeline
+        const int4* dp = p.desc + ((size_t)t0 * kH2Slots + slot) * kH2DescInt4;
+        int4 na = make_int4(0, 0, 0, 0), nb = na, nc = na;
+        if (ntiles) na = __ldg(dp), nb = __ldg(dp + 1), nc = __ldg(dp + 2);
         for (uint32_t n = 0; n < ntiles; n++) {
-            const int4* dp = p.desc + ((size_t)(t0 + n) * kH2Slots + slot) * kH2DescInt4;
-            const int4 sa = __ldg(dp), sb = __ldg(dp + 1), sc = __ldg(dp + 2);
+            const int4 sa = na, sb = nb, sc = nc;
+            dp += kH2Slots * kH2DescInt4;
+            if (n + 1 < ntiles) na = __ldg(dp), nb = __ldg(dp + 1), nc = __ldg(dp + 2);
             const int ng = sc.z;
             __half2 res[NB];
             // every segment of a tile has the same number of 4-column groups: straight-line code over 4 NG registers per band
@@ -670,9 +676,13 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2_long(const H2Para
         const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
         TcCursor cur;
         cur.init(s32(t_full), lane_addr);
+        const int4* dp = p.desc + ((size_t)t0 * kH2Slots + slot) * kH2DescInt4;  // (next tile's descriptors prefetched, as above)
+        int4 na = make_int4(0, 0, 0, 0), nb = na, nc = na, nd = na;
+        if (ntiles) na = __ldg(dp), nb = __ldg(dp + 1), nc = __ldg(dp + 2), nd = __ldg(dp + 3);
         for (uint32_t n = 0; n < ntiles; n++) {
-            const int4* dp = p.desc + ((size_t)(t0 + n) * kH2Slots + slot) * kH2DescInt4;
-            const int4 sa = __ldg(dp), sb = __ldg(dp + 1), sc = __ldg(dp + 2), sd = __ldg(dp + 3);
+            const int4 sa = na, sb = nb, sc = nc, sd = nd;
+            dp += kH2Slots * kH2DescInt4;
+            if (n + 1 < ntiles) na = __ldg(dp), nb = __ldg(dp + 1), nc = __ldg(dp + 2), nd = __ldg(dp + 3);
             const int ng = sc.z, flags = sc.w & 3;
             __half2 res[NB];
             // every segment of a tile has the same number of 4-column groups: straight-line code over 4 NG registers per band
