@@ -40,142 +40,232 @@ __global__ void k_query_lanes64(const double* __restrict__ mfcc, const uint64_t*
 }
 
 // one thread per (query, dictionary segment) pair: lanes are 32 equal-length queries, the dictionary segments are
-// warp-uniform. A CTA stages G = 4 consecutive segments in shared memory (cooperative coalesced load), and every thread
-// walks its query in chunks of 8 values held in registers, feeding the 8 interleaved partial sums of all 4 pairs from one
-// set of query loads and broadcast LDS.128 reads of the segments: ~0.4 load-store operations per product instead of 2,
-// so the FP64 pipe (one DMUL + one DADD per product — products and sums are rounded separately, --fmad=false) bounds the
-// kernel. Accumulation order is rulinalg's dot (A9): p_u += x[8c+u] * y[8c+u] chunk by chunk, then
-// (p0+p4) + (p1+p5) + (p2+p6) + (p3+p7), then the scalar tail — per pair exactly as the CPU path.
+// warp-uniform. Accumulation order is rulinalg's dot (A9): p_u += x[8c+u] * y[8c+u] chunk by chunk, then
+// (p0+p4) + (p1+p5) + (p2+p6) + (p3+p7), then the scalar tail — per pair exactly as the CPU path; products and sums are
+// rounded separately (--fmad=false), so one DMUL + one DADD per product on the FP64 pipe is the floor.
+//
+// The kernel walks the dictionary in (length, index) order (CosSeg table, built once per dictionary): a CTA stages G = 4
+// consecutive segments of that order in shared memory — almost always four segments of the SAME length, so that all four
+// pairs of a thread run the same number of chunks and the chunk loop is branch-free straight-line code: 8 coalesced query
+// loads + 16 broadcast LDS.128 feed 64 FP64 instructions, the query's chunks double-buffered in registers two chunks per
+// iteration (no register copies). Staging is asynchronous (cp.async into the other half of a double buffer while the
+// current group is consumed, descriptors two groups ahead): one barrier per group and no exposed global latency. Slice
+// `sl` takes groups sl, sl + nslices, ... — every slice sees the same mix of lengths. Because the walk is no longer in
+// index order, the reference's "first minimum wins" (strict '<' in index order, src/sound.rs:361-366) is carried by an
+// explicit (distance, index) comparison.
 constexpr int kCosG = 4;        // segments in flight per thread
-constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments fall back to global reads)
-__global__ void __launch_bounds__(128) k_cosine_scan(const double* __restrict__ dmfcc, const uint64_t* __restrict__ doff,
-                                                     const double* __restrict__ dnorm, int c, const uint32_t* __restrict__ slice_seg,
-                                                     uint32_t nslices, const double* __restrict__ qlanes,
-                                                     const uint32_t* __restrict__ group_len,
-                                                     const uint32_t* __restrict__ group_rowbase,
-                                                     const uint32_t* __restrict__ group_qid, uint32_t ngroups,
-                                                     const double* __restrict__ qnorm, const double* __restrict__ targets,
-                                                     double* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
-    __shared__ __align__(16) double sseg[kCosG][kCosSegCap];
+constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments are read from global memory)
+constexpr uint32_t kCosNone = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void cos_cp_async8(double* smem_dst, const double* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cos_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// the 8 partial sums of all G pairs advance by one chunk: yv = the query's 8 values, xs = chunk of segment 0 in shared memory
+__device__ __forceinline__ void cos_chunk(double (&p)[kCosG][8], const double (&yv)[8], const double2* xs) {
+#pragma unroll
+    for (int u = 0; u < kCosG; u++) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const double2 xx = xs[u * (kCosSegCap / 2) + v];
+            p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
+            p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 3)
+k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, const double* __restrict__ cnorm, uint32_t nseg, int c,
+              uint32_t nslices, const double* __restrict__ qlanes, const uint32_t* __restrict__ group_len,
+              const uint32_t* __restrict__ group_rowbase, const uint32_t* __restrict__ group_qid, uint32_t ngroups,
+              const double* __restrict__ qnorm, const double* __restrict__ targets, double* __restrict__ part_dist,
+              uint32_t* __restrict__ part_idx) {
+    __shared__ __align__(16) double sseg[2][kCosG][kCosSegCap];  // 32 KB
+    __shared__ uint4 sdesc[3][kCosG];                            // {first frame lo, hi, frames, local segment index}
+    __shared__ double snorm[3][kCosG];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qb = blockIdx.x / nslices, slice = blockIdx.x % nslices;
     const uint32_t g = qb * 4 + warp;
     const bool active = g < ngroups;
-    const uint32_t qid = active ? group_qid[g * 32 + lane] : 0xFFFFFFFFu;
-    const size_t kq = active ? (size_t)group_len[g] * c : 0;
+    const uint32_t qid = active ? group_qid[g * 32 + lane] : kCosNone;
+    const uint32_t kq = active ? group_len[g] * (uint32_t)c : 0;
     const double* y = active ? qlanes + (size_t)group_rowbase[g] * c * 32 + lane : qlanes;
-    const double nq = qid != 0xFFFFFFFFu ? qnorm[qid] : 1.0;
-    const double target = (qid != 0xFFFFFFFFu && targets) ? targets[qid] : 1.0;
+    const double nq = qid != kCosNone ? qnorm[qid] : 1.0;
+    const double target = (qid != kCosNone && targets) ? targets[qid] : 1.0;
     double best = 2.0;  // fold((0, 2.0)), src/sound.rs:361
-    uint32_t best_idx = 0xFFFFFFFFu;
-    const uint32_t s_begin = slice_seg[slice], s_end = slice_seg[slice + 1];
-    for (uint32_t s0 = s_begin; s0 < s_end; s0 += kCosG) {
-        const int ng = (int)min((uint32_t)kCosG, s_end - s0);
-        // ---- stage the segments (all 128 threads; segments are contiguous in dmfcc) ---------------------------------
-        __syncthreads();
-        size_t kd[kCosG];
-        const double* xg[kCosG];
+    uint32_t best_idx = kCosNone;
+    const uint32_t ngrp = (nseg + kCosG - 1) / kCosG;
+
+    // descriptor of sorted position grp * G + t (thread t < G), absent beyond the table
+    auto fetch = [&](uint32_t grp, uint4& dsc, double& nrm) {
+        const uint64_t s = (uint64_t)grp * kCosG + threadIdx.x;
+        dsc = make_uint4(0, 0, 0, kCosNone);
+        nrm = 1.0;
+        if (threadIdx.x < kCosG && s < nseg) {
+            dsc = __ldg(&cseg[s]);
+            nrm = __ldg(&cnorm[s]);
+        }
+    };
+    auto stage = [&](int slot, int b) {
 #pragma unroll
         for (int u = 0; u < kCosG; u++) {
-            kd[u] = u < ng ? (size_t)(doff[s0 + u + 1] - doff[s0 + u]) * c : 0;
-            xg[u] = dmfcc + doff[s0 + min(u, ng - 1)] * c;
-            if (kd[u] <= (size_t)kCosSegCap)
-                for (size_t e = threadIdx.x; e < kd[u]; e += 128) sseg[u][e] = xg[u][e];
+            const uint4 dsc = sdesc[slot][u];
+            const uint32_t kd = dsc.z * (uint32_t)c;
+            if (dsc.w != kCosNone && kd <= (uint32_t)kCosSegCap) {
+                const double* src = dmfcc + (((uint64_t)dsc.y << 32) | dsc.x) * c;
+                for (uint32_t e = threadIdx.x; e < kd; e += 128) cos_cp_async8(&sseg[b][u][e], src + e);
+            }
+        }
+    };
+    {
+        uint4 d0, d1;
+        double n0, n1;
+        fetch(slice, d0, n0);
+        fetch(slice + nslices, d1, n1);
+        if (threadIdx.x < kCosG) {
+            sdesc[0][threadIdx.x] = d0, snorm[0][threadIdx.x] = n0;
+            sdesc[1][threadIdx.x] = d1, snorm[1][threadIdx.x] = n1;
         }
         __syncthreads();
-        if (!active) continue;
-        // ---- chunks of 8 ---------------------------------------------------------------------------------------------
-        double p[kCosG][8];
-        uint32_t nchunk[kCosG], len[kCosG];
-        uint32_t maxchunk = 0;
-        bool all_staged = true;
+        stage(0, 0);
+    }
+    int cur = 0, b = 0;  // descriptor slot and staging buffer of the current group
+    for (uint32_t grp = slice; grp < ngrp; grp += nslices) {
+        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
+        cos_cp_async_wait_all();
+        __syncthreads();  // buffer b and descriptor slot nxt are complete; everyone is done with buffer b ^ 1 and slot nxt2
+        stage(nxt, b ^ 1);
+        uint4 d2;
+        double n2;
+        fetch(grp + 2 * nslices, d2, n2);
+        if (active) {
+            uint32_t kd[kCosG], sidx[kCosG], len[kCosG], nchunk[kCosG];
+            const double* xg[kCosG];
+            double p[kCosG][8];
+            bool uniform = true, all_staged = true;
+            uint32_t maxchunk = 0;
 #pragma unroll
-        for (int u = 0; u < kCosG; u++) {
-            len[u] = (uint32_t)(kd[u] < kq ? kd[u] : kq);
-            nchunk[u] = len[u] / 8;
-            maxchunk = nchunk[u] > maxchunk ? nchunk[u] : maxchunk;
-            all_staged = all_staged && kd[u] <= (size_t)kCosSegCap;
+            for (int u = 0; u < kCosG; u++) {
+                const uint4 dsc = sdesc[cur][u];
+                sidx[u] = dsc.w;
+                kd[u] = dsc.w != kCosNone ? dsc.z * (uint32_t)c : 0;
+                xg[u] = dmfcc + (((uint64_t)dsc.y << 32) | dsc.x) * c;
+                len[u] = kd[u] < kq ? kd[u] : kq;
+                nchunk[u] = len[u] / 8;
+                maxchunk = nchunk[u] > maxchunk ? nchunk[u] : maxchunk;
+                uniform = uniform && dsc.w != kCosNone && kd[u] == kd[0];
+                all_staged = all_staged && kd[u] <= (uint32_t)kCosSegCap;
 #pragma unroll
-            for (int v = 0; v < 8; v++) p[u][v] = 0.0;
-        }
-        if (all_staged) {
-            // every segment of the group sits in shared memory (always, for segments of <= 39 frames): 32-bit indices, and the
-            // query's next chunk is fetched while the current one is consumed
-            const double* yp = y;
-            double yv[8];
-            if (maxchunk) {
-#pragma unroll
-                for (int v = 0; v < 8; v++) yv[v] = yp[v * 32];
+                for (int v = 0; v < 8; v++) p[u][v] = 0.0;
             }
-            for (uint32_t ch = 0; ch < maxchunk; ch++) {
-                double yn[8];
-                yp += 8 * 32;
-                if (ch + 1 < maxchunk) {
+            const double2* xs = reinterpret_cast<const double2*>(&sseg[b][0][0]);
+            if (uniform && all_staged) {
+                // ---- four segments of one length: straight-line chunks, two per iteration ----------------------------------
+                const uint32_t nch = nchunk[0];
+                const double* yp = y;
+                double ya[8], yb[8];
+                if (nch) {
 #pragma unroll
-                    for (int v = 0; v < 8; v++) yn[v] = yp[v * 32];
+                    for (int v = 0; v < 8; v++) ya[v] = yp[v * 32];
                 }
+                uint32_t ch = 0;
+                for (; ch + 2 <= nch; ch += 2) {
 #pragma unroll
-                for (int u = 0; u < kCosG; u++) {
-                    if (ch < nchunk[u]) {  // warp-uniform
-                        const double2* xs = reinterpret_cast<const double2*>(&sseg[u][ch * 8]);
+                    for (int v = 0; v < 8; v++) yb[v] = yp[(8 + v) * 32];
+                    cos_chunk(p, ya, xs);
+                    // (may read one chunk past the query's last: the lane buffer is padded by a chunk, the values go unused)
 #pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            const double2 xx = xs[v];
-                            p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
-                            p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
-                        }
-                    }
+                    for (int v = 0; v < 8; v++) ya[v] = yp[(16 + v) * 32];
+                    cos_chunk(p, yb, xs + 4);
+                    yp += 16 * 32;
+                    xs += 8;
                 }
-#pragma unroll
-                for (int v = 0; v < 8; v++) yv[v] = yn[v];
-            }
-        } else {
-            for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                if (ch < nch) cos_chunk(p, ya, xs);
+            } else if (all_staged) {
+                // ---- mixed lengths, all in shared memory: the query's next chunk is fetched while the current one is consumed
+                const double* yp = y;
                 double yv[8];
+                if (maxchunk) {
 #pragma unroll
-                for (int v = 0; v < 8; v++) yv[v] = y[((size_t)ch * 8 + v) * 32];
+                    for (int v = 0; v < 8; v++) yv[v] = yp[v * 32];
+                }
+                for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                    double yn[8];
+                    yp += 8 * 32;
+                    if (ch + 1 < maxchunk) {
 #pragma unroll
-                for (int u = 0; u < kCosG; u++) {
-                    if (ch < nchunk[u]) {  // warp-uniform
-                        if (kd[u] <= (size_t)kCosSegCap) {
-                            const double2* xs = reinterpret_cast<const double2*>(&sseg[u][ch * 8]);
+                        for (int v = 0; v < 8; v++) yn[v] = yp[v * 32];
+                    }
+#pragma unroll
+                    for (int u = 0; u < kCosG; u++) {
+                        if (ch < nchunk[u]) {  // warp-uniform
 #pragma unroll
                             for (int v = 0; v < 4; v++) {
-                                const double2 xx = xs[v];
+                                const double2 xx = xs[u * (kCosSegCap / 2) + ch * 4 + v];
                                 p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
                                 p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
                             }
-                        } else {
+                        }
+                    }
 #pragma unroll
-                            for (int v = 0; v < 8; v++) p[u][v] = p[u][v] + __ldg(xg[u] + (size_t)ch * 8 + v) * yv[v];
+                    for (int v = 0; v < 8; v++) yv[v] = yn[v];
+                }
+            } else {
+                // ---- some segment longer than the staging buffer: its frames come from global memory ----------------------
+                for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                    double yv[8];
+#pragma unroll
+                    for (int v = 0; v < 8; v++) yv[v] = y[((size_t)ch * 8 + v) * 32];
+#pragma unroll
+                    for (int u = 0; u < kCosG; u++) {
+                        if (ch < nchunk[u]) {  // warp-uniform
+                            if (kd[u] <= (uint32_t)kCosSegCap) {
+#pragma unroll
+                                for (int v = 0; v < 4; v++) {
+                                    const double2 xx = xs[u * (kCosSegCap / 2) + ch * 4 + v];
+                                    p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
+                                    p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+                                }
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < 8; v++) p[u][v] = p[u][v] + __ldg(xg[u] + (size_t)ch * 8 + v) * yv[v];
+                            }
                         }
                     }
                 }
             }
-        }
-        // ---- combine, tail, similarity, argmin (segments in index order: first minimum wins) ---------------------------
+            // ---- combine, tail, similarity, argmin by (distance, index) ------------------------------------------------------
 #pragma unroll
-        for (int u = 0; u < kCosG; u++) {
-            if (u < ng) {
-                double sum = 0.0;
-                sum = sum + (p[u][0] + p[u][4]);
-                sum = sum + (p[u][1] + p[u][5]);
-                sum = sum + (p[u][2] + p[u][6]);
-                sum = sum + (p[u][3] + p[u][7]);
-                for (uint32_t e = nchunk[u] * 8; e < len[u]; e++) {
-                    const double xv = kd[u] <= (size_t)kCosSegCap ? sseg[u][e] : __ldg(xg[u] + e);
-                    sum = sum + xv * y[(size_t)e * 32];
-                }
-                const double nrm = dnorm[s0 + u] * nq;   // norm(me) * norm(you), src/sound.rs:30
-                const double sim = sum / nrm;            // src/sound.rs:32
-                const double dist = fabs(sim - target);  // src/sound.rs:359
-                if (dist < best) {                       // strict '<': first minimum wins, NaN never wins (src/sound.rs:362)
-                    best = dist;
-                    best_idx = s0 + u;
+            for (int u = 0; u < kCosG; u++) {
+                if (sidx[u] != kCosNone) {
+                    double sum = 0.0;
+                    sum = sum + (p[u][0] + p[u][4]);
+                    sum = sum + (p[u][1] + p[u][5]);
+                    sum = sum + (p[u][2] + p[u][6]);
+                    sum = sum + (p[u][3] + p[u][7]);
+                    for (uint32_t e = nchunk[u] * 8; e < len[u]; e++) {
+                        const double xv = kd[u] <= (uint32_t)kCosSegCap ? sseg[b][u][e] : __ldg(xg[u] + e);
+                        sum = sum + xv * y[(size_t)e * 32];
+                    }
+                    const double nrm = snorm[cur][u] * nq;   // norm(me) * norm(you), src/sound.rs:30
+                    const double sim = sum / nrm;            // src/sound.rs:32
+                    const double dist = fabs(sim - target);  // src/sound.rs:359
+                    // strict '<' in index order (src/sound.rs:362): a smaller distance wins, an equal one only with a smaller
+                    // index than a winner already found; NaN never wins, 2.0 never beats the fold's seed
+                    if (dist < best || (dist == best && sidx[u] < best_idx && best_idx != kCosNone)) {
+                        best = dist;
+                        best_idx = sidx[u];
+                    }
                 }
             }
         }
+        if (threadIdx.x < kCosG) sdesc[nxt2][threadIdx.x] = d2, snorm[nxt2][threadIdx.x] = n2;
+        cur = nxt;
+        b ^= 1;
     }
+    cos_cp_async_wait_all();
     if (!active) return;
     const size_t o = (size_t)slice * ngroups * 32 + (size_t)g * 32 + lane;
     part_dist[o] = best;
@@ -190,16 +280,23 @@ __global__ void k_cosine_merge(const double* __restrict__ part_dist, const uint3
     const uint32_t qid = group_qid[slot];
     if (qid == 0xFFFFFFFFu) return;
     double best = 2.0;
-    uint32_t idx = 0;  // nothing < 2.0 -> index 0, as the reference's fold seed (src/sound.rs:361, 369)
+    uint32_t idx = kCosNone;  // nothing < 2.0 -> index 0, as the reference's fold seed (src/sound.rs:361, 369)
     for (uint32_t sl = 0; sl < nslices; sl++) {
         const double d = part_dist[(size_t)sl * nslots + slot];
-        if (d < best) {
+        const uint32_t i = part_idx[(size_t)sl * nslots + slot];
+        // slices interleave the dictionary: equal distances go to the smaller index (first minimum wins, src/sound.rs:362)
+        if (i != kCosNone && (d < best || (d == best && i < idx))) {
             best = d;
-            idx = part_idx[(size_t)sl * nslots + slot];
+            idx = i;
         }
     }
-    out_idx[qid] = idx + index_base;
+    out_idx[qid] = (idx != kCosNone ? idx : 0) + index_base;
     out_dist[qid] = best;
+}
+
+__global__ void k_cos_gather_norm(const double* __restrict__ norm, const uint4* __restrict__ cseg, uint32_t n, double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = norm[cseg[i].w];
 }
 
 // empty queries never reach a lane: their similarity is 0/0 = NaN against everything, so the fold keeps (0, 2.0)
@@ -221,10 +318,25 @@ int fill_result(ss_ctx* ctx, uint32_t* d_idx, double* d_dist, size_t n) {
 int cosine_dict_build(ss_dict* d) {
     ss_ctx* ctx = d->ctx;
     SS_CUDA(ctx, d->d_norm.reserve(std::max<size_t>(d->nseg, 1)));
-    if (d->nseg) {
-        k_seg_norm<<<ceil_div((long long)d->nseg, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->nseg, d->c, d->d_norm.p);
-        SS_LAUNCHED(ctx);
+    if (!d->nseg) return SS_OK;
+    k_seg_norm<<<ceil_div((long long)d->nseg, 128), 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->nseg, d->c, d->d_norm.p);
+    SS_LAUNCHED(ctx);
+    // the scan's walk order: segments by (length, index), so that the four segments a CTA stages together have one length;
+    // {first frame, frames, index} per position + the norms in the same order (ss_dict_create synchronises the stream
+    // before it returns: the upload has left the local table by then)
+    std::vector<uint64_t> key(d->nseg);
+    for (size_t s = 0; s < d->nseg; s++) key[s] = ((d->h_off[s + 1] - d->h_off[s]) << 32) | (uint64_t)s;
+    std::sort(key.begin(), key.end());
+    d->h_cos_seg.resize(d->nseg);
+    for (size_t i = 0; i < d->nseg; i++) {
+        const uint32_t s = (uint32_t)key[i];
+        const uint64_t f0 = d->h_off[s];
+        d->h_cos_seg[i] = make_uint4((uint32_t)f0, (uint32_t)(f0 >> 32), (uint32_t)(d->h_off[s + 1] - f0), s);
     }
+    SS_TRY(upload(ctx, d->d_cos_seg, d->h_cos_seg.data(), d->h_cos_seg.size()));
+    SS_CUDA(ctx, d->d_cos_norm.reserve(d->nseg));
+    k_cos_gather_norm<<<ceil_div((long long)d->nseg, 256), 256, 0, ctx->stream>>>(d->d_norm.p, d->d_cos_seg.p, (uint32_t)d->nseg, d->d_cos_norm.p);
+    SS_LAUNCHED(ctx);
     return SS_OK;
 }
 
@@ -237,7 +349,8 @@ int cosine_queries_build(ss_queries* q) {
         k_seg_norm<<<ceil_div((long long)q->nq, 128), 128, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->nq, q->c, q->d_norm.p);
         SS_LAUNCHED(ctx);
     }
-    SS_CUDA(ctx, q->d_lane64.reserve(std::max<uint64_t>(q->total_rows, 1) * q->c * 32));
+    // (+ one chunk: the scan's double-buffered query loads may run a chunk past the last group's rows)
+    SS_CUDA(ctx, q->d_lane64.reserve(std::max<uint64_t>(q->total_rows, 1) * q->c * 32 + 8 * 32));
     if (q->ngroups) {
         k_query_lanes64<<<q->ngroups, 256, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, q->d_group_len.p,
                                                             q->d_group_rowbase.p, q->d_group_qid.p, q->d_lane64.p);
@@ -276,21 +389,9 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     const uint32_t nqb = (q->ngroups + 3) / 4;
     if (!nqb || !d->nseg) return SS_OK;
     const uint32_t nslots = q->ngroups * 32;
-    uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)d->nseg, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
-    if (d->cos_slices_for != nslices) {  // slice table (contiguous segment ranges balanced by frames), cached per slice count
-        std::vector<uint32_t> ss(1, 0);
-        const uint64_t total = d->total_frames + d->nseg;  // +1 per segment so empty segments still spread
-        uint64_t acc = 0;
-        for (size_t s = 0; s < d->nseg; s++) {
-            if (s > 0 && ss.size() < nslices && acc >= (uint64_t)ss.size() * ((total + nslices - 1) / nslices)) ss.push_back((uint32_t)s);
-            acc += d->h_off[s + 1] - d->h_off[s] + 1;
-        }
-        ss.push_back((uint32_t)d->nseg);
-        SS_TRY(upload(ctx, d->d_cos_slice_seg, ss.data(), ss.size()));
-        d->cos_slices_for = nslices;
-        d->cos_nslices = (uint32_t)ss.size() - 1;
-    }
-    nslices = d->cos_nslices;
+    // slice sl takes the groups sl, sl + nslices, ... of that order: every slice sees the same mix of lengths
+    const uint32_t ngrp = (uint32_t)((d->nseg + kCosG - 1) / kCosG);
+    const uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(ngrp, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
     SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
     if (!d->ev_scan0) {
@@ -298,7 +399,7 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
     }
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
-    k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_off.p, d->d_norm.p, d->c, d->d_cos_slice_seg.p, nslices,
+    k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_cos_seg.p, d->d_cos_norm.p, (uint32_t)d->nseg, d->c, nslices,
                                                          q->d_lane64.p, q->d_group_len.p, q->d_group_rowbase.p, q->d_group_qid.p,
                                                          q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p);
     SS_LAUNCHED(ctx);
@@ -307,7 +408,6 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices, nslots,
                                                                   q->d_group_qid.p, d->index_base, d_out_idx, d_out_dist);
     SS_LAUNCHED(ctx);
-    // (the slice table was staged by cudaMemcpyAsync before it returned: asynchronous from here)
     return SS_OK;
 }
 

@@ -45,8 +45,9 @@ struct ss_dict {
     // cosine-ref
     ss::DevBuf<double> d_norm;  // per segment: norm(mfccs) (src/sound.rs:36-38)
     std::vector<uint64_t> h_len_sorted, h_len_prefix;  // work accounting (sum of min(Kq, Kd)), built on first use
-    ss::DevBuf<uint32_t> d_cos_slice_seg;              // cached slice table of the cosine scan
-    uint32_t cos_slices_for = 0xFFFFFFFFu, cos_nslices = 0;
+    ss::DevBuf<uint4> d_cos_seg;     // the cosine scan's walk order: {first frame lo, hi, frames, index} by (length, index)
+    ss::DevBuf<double> d_cos_norm;   // d_norm in that order
+    std::vector<uint4> h_cos_seg;    // host copy (source of the asynchronous upload)
     // DTW scan
     ss::DevBuf<float> d_stream;  // frames x kSlots
     ss::DevBuf<int4> d_strips, d_tiles;

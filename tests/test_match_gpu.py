@@ -103,6 +103,46 @@ def test_ties_and_self_match(ctx):
     assert cidx[0, 0] == oc[0] and cdist[0, 0] == od[0]
 
 
+def test_cosine_ref_first_minimum_wins_whatever_the_scan_order(ctx):
+    """The cosine scan walks the dictionary by (length, index), not by index: equal distances must still go to the
+    lowest index (the reference's strict '<' fold in index order, src/sound.rs:361-366), across staged groups and slices."""
+    rng = np.random.default_rng(5)
+    # every segment is orthogonal to the query -> sim = 0, |sim - 1| = 1 for all of them: index 0 (a LONG segment, last in
+    # the scan order) must win; then a dictionary where only a few mixed-length segments tie at the minimum
+    lens = np.array([9, 1, 2, 1, 7, 3, 1, 2, 2, 5, 1, 40, 1, 1, 6], dtype=np.uint64)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    d = np.zeros((int(off[-1]), 2))
+    d[:, 1] = rng.uniform(1.0, 3.0, size=len(d))
+    q = np.zeros((3, 2))
+    q[:, 0] = [1.0, 2.0, 0.5]
+    qoff = np.array([0, 1, 3], dtype=np.uint64)
+    dev = api.DeviceDictionary(ctx, d, off)
+    idx, dist = dev.match(q, qoff, SS_COSINE_REF, 1)
+    oidx, odist = O.cosine_match(d, off, q, qoff, 2)
+    assert np.array_equal(idx[:, 0], oidx) and np.array_equal(dist[:, 0], odist) and list(idx[:, 0]) == [0, 0]
+    for n in (37, 1000, 5003):  # many staged groups / several slices: copies of one segment under different indices
+        dd, doff = synth.segments(n, 13, seed=n)
+        qq, qo = synth.segments(40, 13, seed=n + 1)
+        lens = np.diff(doff).astype(np.int64)
+        copies = rng.choice(n, size=n // 3, replace=False)
+        src = copies[rng.permutation(len(copies))]
+        for a, b in zip(copies, src):  # overwrite segment a with (a prefix / tiling of) segment b
+            la, lb = int(lens[a]), int(lens[b])
+            rows = dd[int(doff[b]):int(doff[b]) + lb]
+            dd[int(doff[a]):int(doff[a]) + la] = np.resize(rows, (la, 13))
+        dev = api.DeviceDictionary(ctx, dd, doff)
+        idx, dist = dev.match(qq, qo, SS_COSINE_REF, 1)
+        oidx, odist = O.cosine_match(dd, doff, qq, qo, 13)
+        assert np.array_equal(idx[:, 0], oidx) and np.array_equal(dist[:, 0], odist)
+        # a query that IS a dictionary segment several times over
+        s0 = int(src[0])
+        qseg = dd[int(doff[s0]):int(doff[s0 + 1])]
+        i1, d1 = dev.match(qseg, np.array([0, len(qseg)], dtype=np.uint64), SS_COSINE_REF, 1)
+        o1, od1 = O.cosine_match(dd, doff, qseg, np.array([0, len(qseg)], dtype=np.uint64), 13)
+        assert i1[0, 0] == o1[0] and d1[0, 0] == od1[0]
+
+
 def test_ragged_edge_cases(ctx):
     rng = np.random.default_rng(11)
     # lengths 1, 0 (empty), 33, 64, 65, 200 on both sides
