@@ -183,6 +183,29 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                     xs += 8;
                 }
                 if (ch < nch) cos_chunk(p, ya, xs);
+                // the four tails advance together (one query load per element), then the four divisions
+                double sum[kCosG];
+#pragma unroll
+                for (int u = 0; u < kCosG; u++) {
+                    sum[u] = 0.0 + (p[u][0] + p[u][4]);
+                    sum[u] = sum[u] + (p[u][1] + p[u][5]);
+                    sum[u] = sum[u] + (p[u][2] + p[u][6]);
+                    sum[u] = sum[u] + (p[u][3] + p[u][7]);
+                }
+                for (uint32_t e = nch * 8; e < len[0]; e++) {
+                    const double yv = y[(size_t)e * 32];
+#pragma unroll
+                    for (int u = 0; u < kCosG; u++) sum[u] = sum[u] + sseg[b][u][e] * yv;
+                }
+#pragma unroll
+                for (int u = 0; u < kCosG; u++) {
+                    const double dist = fabs(sum[u] / (snorm[cur][u] * nq) - target);  // src/sound.rs:30-32, 359
+                    if (dist < best || (dist == best && sidx[u] < best_idx && best_idx != kCosNone)) {
+                        best = dist;
+                        best_idx = sidx[u];
+                    }
+                    sidx[u] = kCosNone;  // done: the general epilogue below skips it
+                }
             } else if (all_staged) {
                 // ---- mixed lengths, all in shared memory: the query's next chunk is fetched while the current one is consumed
                 const double* yp = y;

@@ -11,6 +11,9 @@
 // Stockham FFT (three radix-8 passes, 2 butterflies per lane per pass, the first pass reading the windowed samples
 // straight from global memory with coalesced 16-byte loads, the others exchanging through the warp's 8 KB of shared
 // memory), followed by the even/odd split for the bins the mel bank needs (2..229 for C = 12 at 44.1 kHz).
+// What bounds it is the SM's L1 data pipe (shared-memory and global-load wavefronts share it: 93 % busy in round 2's
+// profile), so every table the warp reads is stored in the order the warp reads it - twiddles per (pass, t, lane), mel
+// weights per (step, half band), the DCT matrix transposed: one coalesced load where a gather touched up to 32 lines.
 #include <cmath>
 #include <map>
 
@@ -32,6 +35,24 @@ struct SoundTables {
     DevBuf<double> d_melw;
     DevBuf<int> d_half;       // 2 c x 3 ints (padded to 4)
     int melw_count = 0;
+    // the same tables in the order the warp reads them (one coalesced load per step instead of a gather over up to 32 cache
+    // lines - the gathers were half of the kernel's L1 wavefronts, and the L1 data pipe is what bounds it):
+    DevBuf<double2> d_tw1;    // [t - 1][lane]      pass 1: tw[16 t (lane & 7)],       t = 1..7
+    DevBuf<double2> d_tw2;    // [h][t - 1][lane]   pass 2: tw[2 t (lane + 32 h)],     t = 1..7
+    DevBuf<double> d_melw_t;  // [i][lane]          weight i of half band `lane` (0 beyond its count)
+    DevBuf<double> d_dct_t;   // [n][16]            dct[k][n] at [n][k]
+    int melw_rows = 0;
+};
+
+struct MfccTabs {  // device pointers of one SoundTables, by value into k_mfcc
+    const double* win;
+    const double2* tw;
+    const double2* tw1;
+    const double2* tw2;
+    const double* dct_t;
+    const int* bins;
+    const double* melw_t;
+    const int4* half;
 };
 
 struct SoundState {
@@ -110,12 +131,30 @@ static int get_tables(ss_ctx* ctx, double sample_rate, int c, SoundTables** out)
         for (int i = 0; i < b2 - b1; i++) melw.push_back(1.0 - (double)i / down);
     }
     t->melw_count = (int)melw.size();
+    std::vector<double2> tw1(7 * 32), tw2(2 * 7 * 32);
+    for (int tt = 1; tt < 8; tt++)
+        for (int l = 0; l < 32; l++) {
+            tw1[(tt - 1) * 32 + l] = tw[(tt * (l & 7) * 16) & (SS_BIN - 1)];
+            for (int h = 0; h < 2; h++) tw2[(h * 7 + tt - 1) * 32 + l] = tw[(tt * (l + 32 * h) * 2) & (SS_BIN - 1)];
+        }
+    int rows = 1;
+    for (int h = 0; h < 2 * c; h++) rows = std::max(rows, half[4 * h + 1]);
+    t->melw_rows = rows;
+    std::vector<double> melw_t((size_t)rows * 32, 0.0), dct_t((size_t)c * 16, 0.0);
+    for (int h = 0; h < 2 * c; h++)
+        for (int i = 0; i < half[4 * h + 1]; i++) melw_t[(size_t)i * 32 + h] = melw[half[4 * h + 2] + i];
+    for (int k = 0; k < c; k++)
+        for (int n = 0; n < c; n++) dct_t[(size_t)n * 16 + k] = dct[(size_t)k * c + n];
     int rc = upload(ctx, t->d_win, win.data(), win.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_melw, melw.data(), melw.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_half, half.data(), half.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_tw, tw.data(), tw.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_dct, dct.data(), dct.size());
     if (rc == SS_OK) rc = upload(ctx, t->d_bins, t->bins, (size_t)c + 2);
+    if (rc == SS_OK) rc = upload(ctx, t->d_tw1, tw1.data(), tw1.size());
+    if (rc == SS_OK) rc = upload(ctx, t->d_tw2, tw2.data(), tw2.size());
+    if (rc == SS_OK) rc = upload(ctx, t->d_melw_t, melw_t.data(), melw_t.size());
+    if (rc == SS_OK) rc = upload(ctx, t->d_dct_t, dct_t.data(), dct_t.size());
     if (rc == SS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_error(ctx, SS_ERR_CUDA, "table upload failed");
     if (rc != SS_OK) {
         delete t;
@@ -124,6 +163,10 @@ static int get_tables(ss_ctx* ctx, double sample_rate, int c, SoundTables** out)
     st->tables.push_back(t);
     *out = t;
     return SS_OK;
+}
+
+static MfccTabs mfcc_tabs(const SoundTables* t) {
+    return MfccTabs{t->d_win.p, t->d_tw.p, t->d_tw1.p, t->d_tw2.p, t->d_dct_t.p, t->d_bins.p, t->d_melw_t.p, reinterpret_cast<const int4*>(t->d_half.p)};
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -190,11 +233,29 @@ __device__ __forceinline__ uint32_t seg_of(const uint64_t* __restrict__ off, uin
 #ifndef SS_MFCC_MINBLOCKS
 #define SS_MFCC_MINBLOCKS 4
 #endif
+// Measured and NOT kept (1 h of audio, same commit; the kernel sits at the 128-register edge and every variant below spills
+// 90 - 670 B per thread through the L1 data pipe, which is the unit that bounds the kernel):
+//   SS_MFCC_PREFETCH 1 (first half of the next frame's samples fetched before the band / DCT stages)  2.91 - 3.16 ms
+//   SS_MFCC_PREFETCH 2 (prefetch.global.L2 of the next frame, no registers)                           2.60 ms with SPLIT 2
+//   SS_MFCC_SPLIT 2 / 4 (independent bins per lane and step in the even/odd split)                     2.54 / 2.72 ms
+// against 2.39 ms for the plain loop.
+#ifndef SS_MFCC_PREFETCH
+#define SS_MFCC_PREFETCH 0
+#endif
+#ifndef SS_MFCC_SPLIT
+#define SS_MFCC_SPLIT 1
+#endif
 __global__ void __launch_bounds__(kMfccWarps * 32, SS_MFCC_MINBLOCKS)
-k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restrict__ win, const double2* __restrict__ tw,
-       const double* __restrict__ dctm, const int* __restrict__ bins, const double* __restrict__ melw, const int4* __restrict__ halfband, int c,
-       int pw_len, double energy_floor, double* __restrict__ out, const uint64_t* __restrict__ frame_off = nullptr,
-       const uint64_t* __restrict__ samp_off = nullptr, uint32_t nsounds = 0) {
+k_mfcc(const double* __restrict__ samples, size_t frames, const MfccTabs tabs, int c, int pw_len, double energy_floor,
+       double* __restrict__ out, const uint64_t* __restrict__ frame_off = nullptr, const uint64_t* __restrict__ samp_off = nullptr,
+       uint32_t nsounds = 0) {
+    const double* __restrict__ win = tabs.win;
+    const double2* __restrict__ tw = tabs.tw;
+    const double2* __restrict__ tw1 = tabs.tw1 + (threadIdx.x & 31);
+    const double2* __restrict__ tw2 = tabs.tw2 + (threadIdx.x & 31);
+    const double* __restrict__ dct_t = tabs.dct_t;
+    const int* __restrict__ bins = tabs.bins;
+    const int4* __restrict__ halfband = tabs.half;
     extern __shared__ __align__(16) unsigned char mfcc_smem[];
     double2* s_buf = reinterpret_cast<double2*>(mfcc_smem);                                   // [warps][512]  32 KB
     double* s_pw = reinterpret_cast<double*>(mfcc_smem + sizeof(double2) * kMfccWarps * kHalf);  // [warps][pw_len]: bins below the bank's top edge
@@ -206,49 +267,78 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
     const int kb0 = bins[0], kb1 = bins[c + 1];
     // lane h < 2 c sums half band h (rising or falling part of band h / 2) sequentially, in the CPU path's element order
     const int4 hb = lane < 2 * c ? __ldg(&halfband[lane]) : make_int4(0, 0, 0, 0);
-    const double* hw = melw + hb.z;
+    const double* hw = tabs.melw_t + lane;  // weight i of this lane's half band at hw[32 i]
 
-    for (size_t f = (size_t)blockIdx.x * kMfccWarps + warp; f < frames; f += (size_t)gridDim.x * kMfccWarps) {
-        // one sound: frame f starts at sample f * HOP. Batch (ss_sound_analyze_batch): frame f belongs to the sound whose
-        // frame range holds it and starts at that sound's first sample + local frame * HOP (any alignment: scalar loads)
-        size_t start = f * SS_HOP;
-        if (frame_off) {
-            const uint32_t snd = seg_of(frame_off, nsounds, f);
-            start = samp_off[snd] + (f - frame_off[snd]) * SS_HOP;
-        }
-        const bool aligned = (start & 1) == 0;
+    // first sample of frame f. One sound: f * HOP. Batch (ss_sound_analyze_batch): frame f belongs to the sound whose frame
+    // range holds it and starts at that sound's first sample + local frame * HOP (any alignment: scalar loads)
+    auto frame_start = [&](size_t f) -> size_t {
+        if (!frame_off) return f * SS_HOP;
+        const uint32_t snd = seg_of(frame_off, nsounds, f);
+        return samp_off[snd] + (f - frame_off[snd]) * SS_HOP;
+    };
+    // half h of the frame's 1024 samples as double2: element i + 64 t of lane i = lane + 32 h in sv[t]
+    auto load_half = [&](size_t f, int h, double2 (&sv)[8]) {
+        const size_t start = frame_start(f);
         const double* s1 = samples + start;
-        const double2* s2 = reinterpret_cast<const double2*>(s1);
+        if ((start & 1) == 0) {
+            const double2* s2 = reinterpret_cast<const double2*>(s1);
+#pragma unroll
+            for (int t = 0; t < 8; t++) sv[t] = s2[lane + 32 * h + 64 * t];
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int n = lane + 32 * h + 64 * t;
+                sv[t] = make_double2(s1[2 * n], s1[2 * n + 1]);
+            }
+        }
+    };
+    const size_t fstride = (size_t)gridDim.x * kMfccWarps;
+    size_t f = (size_t)blockIdx.x * kMfccWarps + warp;
+    double2 sv0[8];
+#if SS_MFCC_PREFETCH == 1
+    if (f < frames) load_half(f, 0, sv0);
+#endif
+    for (; f < frames; f += fstride) {
         const double2* w2 = reinterpret_cast<const double2*>(win);
-        // ---- pass 0 (Ns = 1): z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]) straight from global memory --------------------
+        // ---- pass 0 (Ns = 1): z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]) straight from global memory (coalesced 16-byte loads) ---
         cplx u[2][8];
+        double2 sv1[8];
+#if SS_MFCC_PREFETCH != 1
+        load_half(f, 0, sv0);
+#endif
+        load_half(f, 1, sv1);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int i = lane + 32 * h;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                const double2 sv = aligned ? s2[i + 64 * t] : make_double2(s1[2 * (i + 64 * t)], s1[2 * (i + 64 * t) + 1]);
                 const double2 wv = __ldg(&w2[i + 64 * t]);
-                u[h][t] = cplx{sv.x * wv.x, sv.y * wv.y};
+                const double2 x = h == 0 ? sv0[t] : sv1[t];
+                u[h][t] = cplx{x.x * wv.x, x.y * wv.y};
             }
             dft8(u[h]);
 #pragma unroll
-            for (int t = 0; t < 8; t++) buf[mfcc_sw(8 * i + t)] = make_double2(u[h][t].x, u[h][t].y);
+            for (int t = 0; t < 8; t++) buf[8 * i + (t ^ (i & 7))] = make_double2(u[h][t].x, u[h][t].y);  // = mfcc_sw(8 i + t)
         }
         __syncwarp();
         // ---- passes 1, 2 (Ns = 8, 64) -------------------------------------------------------------------------------
 #pragma unroll
         for (int pass = 1; pass <= 2; pass++) {
             const int p = pass == 1 ? 8 : 64;
-            const int tstep = pass == 1 ? 16 : 2;  // twiddle exp(-2 pi i t k / (8p)) = tw[t k 128 / p]
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int i = lane + 32 * h;
-                const int k = i & (p - 1);
+                const int bi = mfcc_sw(i);  // mfcc_sw(i + 64 t) = mfcc_sw(i) + 64 t
+                // twiddle exp(-2 pi i t k / (8 p)) = tw[t k 128 / p], k = i & (p - 1), from the lane-ordered tables; t = 0 is 1
+                const double2* twp = pass == 1 ? tw1 : tw2 + h * 7 * 32;
+                {
+                    const double2 v = buf[bi];
+                    u[h][0] = cplx{v.x, v.y};
+                }
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const double2 v = buf[mfcc_sw(i + 64 * t)];
-                    const double2 w = __ldg(&tw[(t * k * tstep) & (SS_BIN - 1)]);
+                for (int t = 1; t < 8; t++) {
+                    const double2 v = buf[bi + 64 * t];
+                    const double2 w = __ldg(&twp[(t - 1) * 32]);
                     u[h][t] = cmul(cplx{v.x, v.y}, cplx{w.x, w.y});
                 }
                 dft8(u[h]);
@@ -259,27 +349,52 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
                 const int i = lane + 32 * h;
                 const int k = i & (p - 1);
                 const int jo = ((i - k) << 3) + k;
+                // mfcc_sw(jo + t p): p = 8 -> (i - k) 8 + 8 t + (k ^ t);  p = 64 -> mfcc_sw(jo) + 64 t
+                const int js = mfcc_sw(jo);
 #pragma unroll
-                for (int t = 0; t < 8; t++) buf[mfcc_sw(jo + t * p)] = make_double2(u[h][t].x, u[h][t].y);
+                for (int t = 0; t < 8; t++)
+                    buf[pass == 1 ? ((i - k) << 3) + 8 * t + (k ^ t) : js + 64 * t] = make_double2(u[h][t].x, u[h][t].y);
             }
             __syncwarp();
         }
+#if SS_MFCC_PREFETCH == 1
+        if (f + fstride < frames) load_half(f + fstride, 0, sv0);  // consumed by the next iteration's pass 0
+#elif SS_MFCC_PREFETCH == 2
+        if (f + fstride < frames) {  // the next frame's 64 cache lines towards L2, two per lane (no registers held)
+            const char* nx = reinterpret_cast<const char*>(samples + frame_start(f + fstride)) + 128 * lane;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 4096));
+        }
+#endif
         // ---- even/odd split: X[k] = E[k] + W_1024^k O[k] for the bins of the mel bank; power |X|^2 (A3) -------------
-        for (int k = kb0 + lane; k < kb1; k += 32) {
-            const double2 zk = buf[mfcc_sw(k & (kHalf - 1))];
-            const double2 zm = buf[mfcc_sw((kHalf - k) & (kHalf - 1))];
-            const cplx e = {0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y)};
-            const cplx o = {0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x)};  // (Zk - conj(Zm)) / (2i)
-            const double2 w = __ldg(&tw[k]);
-            const cplx x = cadd(e, cmul(cplx{w.x, w.y}, o));
-            pw[k] = x.x * x.x + x.y * x.y;
+        for (int k0 = kb0 + lane; k0 < kb1; k0 += 32 * SS_MFCC_SPLIT) {
+            double2 zk[SS_MFCC_SPLIT], zm[SS_MFCC_SPLIT], w[SS_MFCC_SPLIT];
+#pragma unroll
+            for (int j = 0; j < SS_MFCC_SPLIT; j++) {
+                const int k = k0 + 32 * j;
+                if (k < kb1) {
+                    zk[j] = buf[mfcc_sw(k & (kHalf - 1))];
+                    zm[j] = buf[mfcc_sw((kHalf - k) & (kHalf - 1))];
+                    w[j] = __ldg(&tw[k]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SS_MFCC_SPLIT; j++) {
+                const int k = k0 + 32 * j;
+                if (k < kb1) {
+                    const cplx e = {0.5 * (zk[j].x + zm[j].x), 0.5 * (zk[j].y - zm[j].y)};
+                    const cplx o = {0.5 * (zk[j].y + zm[j].y), -0.5 * (zk[j].x - zm[j].x)};  // (Zk - conj(Zm)) / (2i)
+                    const cplx x = cadd(e, cmul(cplx{w[j].x, w[j].y}, o));
+                    pw[k] = x.x * x.x + x.y * x.y;
+                }
+            }
         }
         __syncwarp();
         // ---- triangular bands (un-normalised; rise starts at 0, fall starts at 1), log10 with the A4 floor ------------
         // 2 c lanes each fold one half band (weights from the table: no division in the loop), then band f = rise + fall
         {
             double part = 0.0;
-            for (int i = 0; i < hb.y; i++) part = part + pw[hb.x + i] * __ldg(&hw[i]);
+            for (int i = 0; i < hb.y; i++) part = part + pw[hb.x + i] * __ldg(&hw[32 * i]);
             const double up_sum = __shfl_sync(0xffffffffu, part, (2 * lane) & 31), down_sum = __shfl_sync(0xffffffffu, part, (2 * lane + 1) & 31);
             if (lane < c) {
                 const double e = up_sum + down_sum;
@@ -290,7 +405,7 @@ k_mfcc(const double* __restrict__ samples, size_t frames, const double* __restri
         // ---- DCT-II x 2 ---------------------------------------------------------------------------------------------
         if (lane < c) {
             double acc = 0.0;
-            for (int n = 0; n < c; n++) acc = acc + s_le[n] * __ldg(&dctm[lane * c + n]);
+            for (int n = 0; n < c; n++) acc = acc + s_le[n] * __ldg(&dct_t[n * 16 + lane]);
             out[f * c + lane] = 2.0 * acc;
         }
         __syncwarp();
@@ -387,8 +502,7 @@ static int mfcc_launch(ss_ctx* ctx, const double* d_samples, size_t n, double sa
     const int pw_len = (t->bins[c + 1] + 32) & ~31;  // 256 at 44.1 kHz (top edge bin 230)
     const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * pw_len + sizeof(double) * kMfccWarps * 16);
     SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(d_samples, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, t->d_melw.p,
-                                                         reinterpret_cast<const int4*>(t->d_half.p), c, pw_len, 1e-10, d_out);
+    k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(d_samples, frames, mfcc_tabs(t), c, pw_len, 1e-10, d_out);
     SS_LAUNCHED(ctx);
     (void)n;
     return SS_OK;
@@ -610,8 +724,7 @@ int ss_sound_analyze_batch(ss_ctx* ctx, const double* samples, const uint64_t* s
         const int pw_len = (t->bins[ncoeffs + 1] + 32) & ~31;
         const int smem = (int)(sizeof(double2) * kMfccWarps * kHalf + sizeof(double) * kMfccWarps * pw_len + sizeof(double) * kMfccWarps * 16);
         SS_CUDA(ctx, cudaFuncSetAttribute(k_mfcc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(st->d_samples.p, frames, t->d_win.p, t->d_tw.p, t->d_dct.p, t->d_bins.p, t->d_melw.p,
-                                                             reinterpret_cast<const int4*>(t->d_half.p), ncoeffs, pw_len, 1e-10, st->d_mfcc.p, st->d_off_b.p,
+        k_mfcc<<<grid, kMfccWarps * 32, smem, ctx->stream>>>(st->d_samples.p, frames, mfcc_tabs(t), ncoeffs, pw_len, 1e-10, st->d_mfcc.p, st->d_off_b.p,
                                                              st->d_off_a.p, (uint32_t)nsounds);
         SS_LAUNCHED(ctx);
         if (out_mfcc)
