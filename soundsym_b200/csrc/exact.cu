@@ -54,6 +54,10 @@ __global__ void k_query_lanes64(const double* __restrict__ mfcc, const uint64_t*
 // index order, the reference's "first minimum wins" (strict '<' in index order, src/sound.rs:361-366) is carried by an
 // explicit (distance, index) comparison.
 constexpr int kCosG = 4;        // segments in flight per thread
+#ifndef SS_COS_STAGE
+#define SS_COS_STAGE 8
+#endif
+constexpr int kCosStage = SS_COS_STAGE;  // segments staged per barrier (a multiple of kCosG: consumed kCosG at a time)
 constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments are read from global memory)
 constexpr uint32_t kCosNone = 0xFFFFFFFFu;
 
@@ -76,15 +80,36 @@ __device__ __forceinline__ void cos_chunk(double (&p)[kCosG][8], const double (&
     }
 }
 
+// rulinalg's combine of the 8 partial sums, then the scalar tail (elements 8 nch .. len - 1: yt = the query's chunk nch,
+// xs = that chunk of segment 0 in shared memory), per pair in the CPU path's order
+__device__ __forceinline__ void cos_finish(const double (&p)[kCosG][8], double (&sum)[kCosG], const double (&yt)[8], const double2* xs,
+                                           uint32_t ntail) {
+#pragma unroll
+    for (int u = 0; u < kCosG; u++) {
+        sum[u] = 0.0 + (p[u][0] + p[u][4]);
+        sum[u] = sum[u] + (p[u][1] + p[u][5]);
+        sum[u] = sum[u] + (p[u][2] + p[u][6]);
+        sum[u] = sum[u] + (p[u][3] + p[u][7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        if ((uint32_t)j < ntail) {  // warp-uniform
+#pragma unroll
+            for (int u = 0; u < kCosG; u++) sum[u] = sum[u] + reinterpret_cast<const double*>(xs + u * (kCosSegCap / 2))[j] * yt[j];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128, 3)
 k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, const double* __restrict__ cnorm, uint32_t nseg, int c,
               uint32_t nslices, const double* __restrict__ qlanes, const uint32_t* __restrict__ group_len,
               const uint32_t* __restrict__ group_rowbase, const uint32_t* __restrict__ group_qid, uint32_t ngroups,
               const double* __restrict__ qnorm, const double* __restrict__ targets, double* __restrict__ part_dist,
               uint32_t* __restrict__ part_idx) {
-    __shared__ __align__(16) double sseg[2][kCosG][kCosSegCap];  // 32 KB
-    __shared__ uint4 sdesc[3][kCosG];                            // {first frame lo, hi, frames, local segment index}
-    __shared__ double snorm[3][kCosG];
+    extern __shared__ __align__(16) double cos_sseg[];  // [2][kCosStage][kCosSegCap]: 32 KB per 4 staged segments
+    double (*sseg)[kCosStage][kCosSegCap] = reinterpret_cast<double (*)[kCosStage][kCosSegCap]>(cos_sseg);
+    __shared__ uint4 sdesc[3][kCosStage];  // {first frame lo, hi, frames, local segment index}
+    __shared__ double snorm[3][kCosStage];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qb = blockIdx.x / nslices, slice = blockIdx.x % nslices;
     const uint32_t g = qb * 4 + warp;
@@ -96,21 +121,21 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
     const double target = (qid != kCosNone && targets) ? targets[qid] : 1.0;
     double best = 2.0;  // fold((0, 2.0)), src/sound.rs:361
     uint32_t best_idx = kCosNone;
-    const uint32_t ngrp = (nseg + kCosG - 1) / kCosG;
+    const uint32_t ngrp = (nseg + kCosStage - 1) / kCosStage;
 
     // descriptor of sorted position grp * G + t (thread t < G), absent beyond the table
     auto fetch = [&](uint32_t grp, uint4& dsc, double& nrm) {
-        const uint64_t s = (uint64_t)grp * kCosG + threadIdx.x;
+        const uint64_t s = (uint64_t)grp * kCosStage + threadIdx.x;
         dsc = make_uint4(0, 0, 0, kCosNone);
         nrm = 1.0;
-        if (threadIdx.x < kCosG && s < nseg) {
+        if (threadIdx.x < kCosStage && s < nseg) {
             dsc = __ldg(&cseg[s]);
             nrm = __ldg(&cnorm[s]);
         }
     };
     auto stage = [&](int slot, int b) {
 #pragma unroll
-        for (int u = 0; u < kCosG; u++) {
+        for (int u = 0; u < kCosStage; u++) {
             const uint4 dsc = sdesc[slot][u];
             const uint32_t kd = dsc.z * (uint32_t)c;
             if (dsc.w != kCosNone && kd <= (uint32_t)kCosSegCap) {
@@ -124,7 +149,7 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
         double n0, n1;
         fetch(slice, d0, n0);
         fetch(slice + nslices, d1, n1);
-        if (threadIdx.x < kCosG) {
+        if (threadIdx.x < kCosStage) {
             sdesc[0][threadIdx.x] = d0, snorm[0][threadIdx.x] = n0;
             sdesc[1][threadIdx.x] = d1, snorm[1][threadIdx.x] = n1;
         }
@@ -141,6 +166,8 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
         double n2;
         fetch(grp + 2 * nslices, d2, n2);
         if (active) {
+#pragma unroll 1
+          for (int u0 = 0; u0 < kCosStage; u0 += kCosG) {
             uint32_t kd[kCosG], sidx[kCosG], len[kCosG], nchunk[kCosG];
             const double* xg[kCosG];
             double p[kCosG][8];
@@ -148,7 +175,7 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
             uint32_t maxchunk = 0;
 #pragma unroll
             for (int u = 0; u < kCosG; u++) {
-                const uint4 dsc = sdesc[cur][u];
+                const uint4 dsc = sdesc[cur][u0 + u];
                 sidx[u] = dsc.w;
                 kd[u] = dsc.w != kCosNone ? dsc.z * (uint32_t)c : 0;
                 xg[u] = dmfcc + (((uint64_t)dsc.y << 32) | dsc.x) * c;
@@ -160,46 +187,42 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
 #pragma unroll
                 for (int v = 0; v < 8; v++) p[u][v] = 0.0;
             }
-            const double2* xs = reinterpret_cast<const double2*>(&sseg[b][0][0]);
+            const double2* xs = reinterpret_cast<const double2*>(&sseg[b][u0][0]);
             if (uniform && all_staged) {
                 // ---- four segments of one length: straight-line chunks, two per iteration ----------------------------------
-                const uint32_t nch = nchunk[0];
+                const uint32_t nch = nchunk[0], ntail = len[0] - nch * 8;
                 const double* yp = y;
                 double ya[8], yb[8];
-                if (nch) {
+                // (query loads may run up to a chunk past the query's last element - the chunk that holds the tail: the lane
+                // buffer is padded by a chunk, values beyond the tail go unused)
 #pragma unroll
-                    for (int v = 0; v < 8; v++) ya[v] = yp[v * 32];
-                }
+                for (int v = 0; v < 8; v++) ya[v] = yp[v * 32];
                 uint32_t ch = 0;
                 for (; ch + 2 <= nch; ch += 2) {
 #pragma unroll
                     for (int v = 0; v < 8; v++) yb[v] = yp[(8 + v) * 32];
                     cos_chunk(p, ya, xs);
-                    // (may read one chunk past the query's last: the lane buffer is padded by a chunk, the values go unused)
 #pragma unroll
                     for (int v = 0; v < 8; v++) ya[v] = yp[(16 + v) * 32];
                     cos_chunk(p, yb, xs + 4);
                     yp += 16 * 32;
                     xs += 8;
                 }
-                if (ch < nch) cos_chunk(p, ya, xs);
-                // the four tails advance together (one query load per element), then the four divisions
+                // the chunk after the last whole one holds the <= 7 tail elements: it is in registers by the time the sums are
+                // combined (a tail read from global memory element by element was 9 % of the kernel's stall samples); the four
+                // tails advance together, then the four divisions
                 double sum[kCosG];
+                if (ch < nch) {
 #pragma unroll
-                for (int u = 0; u < kCosG; u++) {
-                    sum[u] = 0.0 + (p[u][0] + p[u][4]);
-                    sum[u] = sum[u] + (p[u][1] + p[u][5]);
-                    sum[u] = sum[u] + (p[u][2] + p[u][6]);
-                    sum[u] = sum[u] + (p[u][3] + p[u][7]);
-                }
-                for (uint32_t e = nch * 8; e < len[0]; e++) {
-                    const double yv = y[(size_t)e * 32];
-#pragma unroll
-                    for (int u = 0; u < kCosG; u++) sum[u] = sum[u] + sseg[b][u][e] * yv;
+                    for (int v = 0; v < 8; v++) yb[v] = yp[(8 + v) * 32];
+                    cos_chunk(p, ya, xs);
+                    cos_finish(p, sum, yb, xs + 4, ntail);
+                } else {
+                    cos_finish(p, sum, ya, xs, ntail);
                 }
 #pragma unroll
                 for (int u = 0; u < kCosG; u++) {
-                    const double dist = fabs(sum[u] / (snorm[cur][u] * nq) - target);  // src/sound.rs:30-32, 359
+                    const double dist = fabs(sum[u] / (snorm[cur][u0 + u] * nq) - target);  // src/sound.rs:30-32, 359
                     if (dist < best || (dist == best && sidx[u] < best_idx && best_idx != kCosNone)) {
                         best = dist;
                         best_idx = sidx[u];
@@ -269,10 +292,10 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                     sum = sum + (p[u][2] + p[u][6]);
                     sum = sum + (p[u][3] + p[u][7]);
                     for (uint32_t e = nchunk[u] * 8; e < len[u]; e++) {
-                        const double xv = kd[u] <= (uint32_t)kCosSegCap ? sseg[b][u][e] : __ldg(xg[u] + e);
+                        const double xv = kd[u] <= (uint32_t)kCosSegCap ? sseg[b][u0 + u][e] : __ldg(xg[u] + e);
                         sum = sum + xv * y[(size_t)e * 32];
                     }
-                    const double nrm = snorm[cur][u] * nq;   // norm(me) * norm(you), src/sound.rs:30
+                    const double nrm = snorm[cur][u0 + u] * nq;   // norm(me) * norm(you), src/sound.rs:30
                     const double sim = sum / nrm;            // src/sound.rs:32
                     const double dist = fabs(sim - target);  // src/sound.rs:359
                     // strict '<' in index order (src/sound.rs:362): a smaller distance wins, an equal one only with a smaller
@@ -283,8 +306,9 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                     }
                 }
             }
+          }
         }
-        if (threadIdx.x < kCosG) sdesc[nxt2][threadIdx.x] = d2, snorm[nxt2][threadIdx.x] = n2;
+        if (threadIdx.x < kCosStage) sdesc[nxt2][threadIdx.x] = d2, snorm[nxt2][threadIdx.x] = n2;
         cur = nxt;
         b ^= 1;
     }
@@ -413,7 +437,7 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     if (!nqb || !d->nseg) return SS_OK;
     const uint32_t nslots = q->ngroups * 32;
     // slice sl takes the groups sl, sl + nslices, ... of that order: every slice sees the same mix of lengths
-    const uint32_t ngrp = (uint32_t)((d->nseg + kCosG - 1) / kCosG);
+    const uint32_t ngrp = (uint32_t)((d->nseg + kCosStage - 1) / kCosStage);
     const uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(ngrp, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
     SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
@@ -422,7 +446,9 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
     }
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
-    k_cosine_scan<<<nqb * nslices, 128, 0, ctx->stream>>>(d->d_mfcc.p, d->d_cos_seg.p, d->d_cos_norm.p, (uint32_t)d->nseg, d->c, nslices,
+    const int cos_smem = (int)(sizeof(double) * 2 * kCosStage * kCosSegCap);
+    SS_CUDA(ctx, cudaFuncSetAttribute(k_cosine_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, cos_smem));
+    k_cosine_scan<<<nqb * nslices, 128, cos_smem, ctx->stream>>>(d->d_mfcc.p, d->d_cos_seg.p, d->d_cos_norm.p, (uint32_t)d->nseg, d->c, nslices,
                                                          q->d_lane64.p, q->d_group_len.p, q->d_group_rowbase.p, q->d_group_qid.p,
                                                          q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p);
     SS_LAUNCHED(ctx);
