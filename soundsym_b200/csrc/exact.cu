@@ -58,6 +58,20 @@ constexpr int kCosG = 4;        // segments in flight per thread
 #define SS_COS_STAGE 8
 #endif
 constexpr int kCosStage = SS_COS_STAGE;  // segments staged per barrier (a multiple of kCosG: consumed kCosG at a time)
+// Measured at config 4 and NOT kept (45.0 ms for the defaults):
+//   SS_COS_SHARE 2    two warps of a CTA work on the same 32 queries, each on its own kCosG of a stage, so that the second
+//                     warp's query loads hit L1 (halves the 7.4 TB/s query stream from L2)                       49.9 ms
+//   SS_COS_DEPTH 3    query chunks fetched two chunks ahead through three register buffers                        46.9 ms
+//   SS_COS_MINB 2     255 registers, 8 warps / SM (with depth 2 / 3)                                       46.7 / 46.3 ms
+//   SS_COS_STAGE 4    four segments per barrier                                                                   46.6 ms
+// - neither the L2 -> SM traffic nor the load latency is what the chunk loop waits for: the L1 data pipe is 66 % busy
+// (a broadcast LDS.128 costs two wavefronts, a coalesced LDG.64 two), the FP64 pipe 44 %.
+#ifndef SS_COS_SHARE
+#define SS_COS_SHARE 1
+#endif
+constexpr int kCosShare = SS_COS_SHARE;
+constexpr int kCosQG = 4 / kCosShare;    // query groups per CTA
+static_assert(kCosShare == 1 || kCosStage == kCosShare * kCosG, "each sharing warp takes one kCosG of a stage");
 constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments are read from global memory)
 constexpr uint32_t kCosNone = 0xFFFFFFFFu;
 
@@ -100,7 +114,13 @@ __device__ __forceinline__ void cos_finish(const double (&p)[kCosG][8], double (
     }
 }
 
-__global__ void __launch_bounds__(128, 3)
+#ifndef SS_COS_DEPTH
+#define SS_COS_DEPTH 2
+#endif
+#ifndef SS_COS_MINB
+#define SS_COS_MINB 3
+#endif
+__global__ void __launch_bounds__(128, SS_COS_MINB)
 k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, const double* __restrict__ cnorm, uint32_t nseg, int c,
               uint32_t nslices, const double* __restrict__ qlanes, const uint32_t* __restrict__ group_len,
               const uint32_t* __restrict__ group_rowbase, const uint32_t* __restrict__ group_qid, uint32_t ngroups,
@@ -112,7 +132,8 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
     __shared__ double snorm[3][kCosStage];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qb = blockIdx.x / nslices, slice = blockIdx.x % nslices;
-    const uint32_t g = qb * 4 + warp;
+    const uint32_t g = qb * kCosQG + warp / kCosShare;
+    const int share = warp % kCosShare;  // which kCosG of every stage this warp takes
     const bool active = g < ngroups;
     const uint32_t qid = active ? group_qid[g * 32 + lane] : kCosNone;
     const uint32_t kq = active ? group_len[g] * (uint32_t)c : 0;
@@ -167,7 +188,7 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
         fetch(grp + 2 * nslices, d2, n2);
         if (active) {
 #pragma unroll 1
-          for (int u0 = 0; u0 < kCosStage; u0 += kCosG) {
+          for (int u0 = kCosShare == 1 ? 0 : share * kCosG; u0 < (kCosShare == 1 ? kCosStage : (share + 1) * kCosG); u0 += kCosG) {
             uint32_t kd[kCosG], sidx[kCosG], len[kCosG], nchunk[kCosG];
             const double* xg[kCosG];
             double p[kCosG][8];
@@ -192,9 +213,42 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                 // ---- four segments of one length: straight-line chunks, two per iteration ----------------------------------
                 const uint32_t nch = nchunk[0], ntail = len[0] - nch * 8;
                 const double* yp = y;
+                double sum[kCosG];
+#if SS_COS_DEPTH == 3
+                // three register buffers: the query's chunks are fetched two chunks ahead of their use
+                double ya[8], yb[8], yc[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++) ya[v] = yp[v * 32], yb[v] = yp[(8 + v) * 32];
+                uint32_t ch = 0;
+                for (; ch + 3 <= nch; ch += 3) {
+#pragma unroll
+                    for (int v = 0; v < 8; v++) yc[v] = yp[(16 + v) * 32];
+                    cos_chunk(p, ya, xs);
+#pragma unroll
+                    for (int v = 0; v < 8; v++) ya[v] = yp[(24 + v) * 32];
+                    cos_chunk(p, yb, xs + 4);
+#pragma unroll
+                    for (int v = 0; v < 8; v++) yb[v] = yp[(32 + v) * 32];
+                    cos_chunk(p, yc, xs + 8);
+                    yp += 24 * 32;
+                    xs += 12;
+                }
+                if (ch == nch) {
+                    cos_finish(p, sum, ya, xs, ntail);
+                } else if (ch + 1 == nch) {
+                    cos_chunk(p, ya, xs);
+                    cos_finish(p, sum, yb, xs + 4, ntail);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 8; v++) yc[v] = yp[(16 + v) * 32];
+                    cos_chunk(p, ya, xs);
+                    cos_chunk(p, yb, xs + 4);
+                    cos_finish(p, sum, yc, xs + 8, ntail);
+                }
+#else
                 double ya[8], yb[8];
                 // (query loads may run up to a chunk past the query's last element - the chunk that holds the tail: the lane
-                // buffer is padded by a chunk, values beyond the tail go unused)
+                // buffer is padded, values beyond the tail go unused)
 #pragma unroll
                 for (int v = 0; v < 8; v++) ya[v] = yp[v * 32];
                 uint32_t ch = 0;
@@ -211,7 +265,6 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                 // the chunk after the last whole one holds the <= 7 tail elements: it is in registers by the time the sums are
                 // combined (a tail read from global memory element by element was 9 % of the kernel's stall samples); the four
                 // tails advance together, then the four divisions
-                double sum[kCosG];
                 if (ch < nch) {
 #pragma unroll
                     for (int v = 0; v < 8; v++) yb[v] = yp[(8 + v) * 32];
@@ -220,6 +273,7 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                 } else {
                     cos_finish(p, sum, ya, xs, ntail);
                 }
+#endif
 #pragma unroll
                 for (int u = 0; u < kCosG; u++) {
                     const double dist = fabs(sum[u] / (snorm[cur][u0 + u] * nq) - target);  // src/sound.rs:30-32, 359
@@ -314,7 +368,7 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
     }
     cos_cp_async_wait_all();
     if (!active) return;
-    const size_t o = (size_t)slice * ngroups * 32 + (size_t)g * 32 + lane;
+    const size_t o = ((size_t)slice * kCosShare + share) * ngroups * 32 + (size_t)g * 32 + lane;
     part_dist[o] = best;
     part_idx[o] = best_idx;
 }
@@ -396,8 +450,8 @@ int cosine_queries_build(ss_queries* q) {
         k_seg_norm<<<ceil_div((long long)q->nq, 128), 128, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->nq, q->c, q->d_norm.p);
         SS_LAUNCHED(ctx);
     }
-    // (+ one chunk: the scan's double-buffered query loads may run a chunk past the last group's rows)
-    SS_CUDA(ctx, q->d_lane64.reserve(std::max<uint64_t>(q->total_rows, 1) * q->c * 32 + 8 * 32));
+    // (+ two chunks: the scan's register-buffered query loads run up to two chunks past the last group's rows)
+    SS_CUDA(ctx, q->d_lane64.reserve(std::max<uint64_t>(q->total_rows, 1) * q->c * 32 + 16 * 32));
     if (q->ngroups) {
         k_query_lanes64<<<q->ngroups, 256, 0, ctx->stream>>>(q->d_mfcc.p, q->d_off.p, q->c, q->d_group_len.p,
                                                             q->d_group_rowbase.p, q->d_group_qid.p, q->d_lane64.p);
@@ -433,14 +487,14 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
         k_fill_result<<<ceil_div((long long)q->nq, 256), 256, 0, ctx->stream>>>(d_out_idx, d_out_dist, q->nq, d->index_base, 2.0);
         SS_LAUNCHED(ctx);
     }
-    const uint32_t nqb = (q->ngroups + 3) / 4;
+    const uint32_t nqb = (q->ngroups + kCosQG - 1) / kCosQG;
     if (!nqb || !d->nseg) return SS_OK;
     const uint32_t nslots = q->ngroups * 32;
     // slice sl takes the groups sl, sl + nslices, ... of that order: every slice sees the same mix of lengths
     const uint32_t ngrp = (uint32_t)((d->nseg + kCosStage - 1) / kCosStage);
     const uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(ngrp, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
-    SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
-    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
+    SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * kCosShare * nslots));
+    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * kCosShare * nslots));
     if (!d->ev_scan0) {
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
@@ -454,7 +508,7 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
     d->scan_timed = true;
-    k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices, nslots,
+    k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices * kCosShare, nslots,
                                                                   q->d_group_qid.p, d->index_base, d_out_idx, d_out_dist);
     SS_LAUNCHED(ctx);
     return SS_OK;
