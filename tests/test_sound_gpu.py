@@ -55,6 +55,15 @@ def test_c13_and_synthetic_audio(ctx):
     assert ctx.max_power(s) == O.max_power(s)
 
 
+def test_other_sample_rates_change_the_mel_bank_layout(ctx):
+    """The kernel reads its mel weights / DCT matrix / twiddles from tables laid out per lane: other sample rates give other
+    band edges (wider half bands at 22.05 kHz, bins up to 342 instead of 229), other table shapes."""
+    s = synth.audio(1.5, seed=9)
+    for sr in (22050.0, 32000.0, 48000.0, 96000.0):
+        for c in (12, 13):
+            assert_mfcc_close(ctx.mfcc(s, sr, c), O.mfcc(s, sr, c))
+
+
 def test_frame_edge_cases(ctx):
     assert ctx.mfcc(np.zeros(0)).shape == (0, 12)
     assert ctx.mfcc(np.zeros(1023)).shape == (0, 12)

@@ -19,7 +19,13 @@ METRICS = [
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe (%)"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe (%)"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe (%)"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "L1 data pipe: all LSU wavefronts (% of peak)"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory wavefronts (% of peak)"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "global-load requests"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit rate (%)"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2 -> L1 bytes"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "L2 -> L1 throughput"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate (%)"),
     ("dram__bytes_read.sum", "DRAM read"),
     ("dram__bytes_write.sum", "DRAM written"),
