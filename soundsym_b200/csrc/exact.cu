@@ -44,34 +44,31 @@ __global__ void k_query_lanes64(const double* __restrict__ mfcc, const uint64_t*
 // (p0+p4) + (p1+p5) + (p2+p6) + (p3+p7), then the scalar tail — per pair exactly as the CPU path; products and sums are
 // rounded separately (--fmad=false), so one DMUL + one DADD per product on the FP64 pipe is the floor.
 //
-// The kernel walks the dictionary in (length, index) order (CosSeg table, built once per dictionary): a CTA stages G = 4
-// consecutive segments of that order in shared memory — almost always four segments of the SAME length, so that all four
-// pairs of a thread run the same number of chunks and the chunk loop is branch-free straight-line code: 8 coalesced query
-// loads + 16 broadcast LDS.128 feed 64 FP64 instructions, the query's chunks double-buffered in registers two chunks per
-// iteration (no register copies). Staging is asynchronous (cp.async into the other half of a double buffer while the
-// current group is consumed, descriptors two groups ahead): one barrier per group and no exposed global latency. Slice
-// `sl` takes groups sl, sl + nslices, ... — every slice sees the same mix of lengths. Because the walk is no longer in
-// index order, the reference's "first minimum wins" (strict '<' in index order, src/sound.rs:361-366) is carried by an
-// explicit (distance, index) comparison.
+// The kernel walks the dictionary in (length, index) order (CosSeg table, built once per dictionary): a CTA stages
+// kCosStage consecutive segments of that order in shared memory and consumes them G = 4 at a time — almost always four
+// segments of the SAME length, so that all pairs of a thread run the same number of chunks and the chunk loop is
+// branch-free straight-line code. A warp works on NQ query groups of one length at once (a "work item", table built per
+// query batch): NQ = 2 wherever two groups of a length exist, NQ = 1 for the odd group of a length. With NQ = 2 a thread
+// holds 2 queries x 4 segments = 64 partial sums: the 16 broadcast LDS.128 of a chunk feed 128 FP64 instructions instead
+// of 64 (1.0 instead of 1.5 L1 wavefronts per product), and the query chunk is refilled IN PLACE — element pair v of the
+// next chunk is loaded as soon as pair v of the current chunk has been consumed, a whole chunk (128 FP64 instructions)
+// ahead of its use — so the 128 accumulator registers leave room for it without a second buffer. NQ = 1 keeps two
+// register buffers, two chunks per iteration. Staging is asynchronous (cp.async into the other half of a double buffer
+// while the current group is consumed, descriptors two groups ahead): one barrier per group and no exposed global
+// latency. Slice `sl` takes groups sl, sl + nslices, ... — every slice sees the same mix of lengths. Because the walk is
+// not in index order, the reference's "first minimum wins" (strict '<' in index order, src/sound.rs:361-366) is carried by
+// an explicit (distance, index) comparison.
 constexpr int kCosG = 4;        // segments in flight per thread
-#ifndef SS_COS_STAGE
-#define SS_COS_STAGE 8
-#endif
-constexpr int kCosStage = SS_COS_STAGE;  // segments staged per barrier (a multiple of kCosG: consumed kCosG at a time)
-// Measured at config 4 and NOT kept (45.0 ms for the defaults):
-//   SS_COS_SHARE 2    two warps of a CTA work on the same 32 queries, each on its own kCosG of a stage, so that the second
-//                     warp's query loads hit L1 (halves the 7.4 TB/s query stream from L2)                       49.9 ms
-//   SS_COS_DEPTH 3    query chunks fetched two chunks ahead through three register buffers                        46.9 ms
-//   SS_COS_MINB 2     255 registers, 8 warps / SM (with depth 2 / 3)                                       46.7 / 46.3 ms
-//   SS_COS_STAGE 4    four segments per barrier                                                                   46.6 ms
-// - neither the L2 -> SM traffic nor the load latency is what the chunk loop waits for: the L1 data pipe is 66 % busy
+constexpr int kCosStage = 8;    // segments staged per barrier (a multiple of kCosG: consumed kCosG at a time)
+constexpr int kCosWarps = 4;    // work items per CTA
+// Measured at config 4 and NOT kept (45.0 ms for NQ = 1 everywhere, the state before the 2 x 4 tile):
+//   two warps of a CTA on the same 32 queries, each on its own kCosG of a stage, so that the second warp's query loads
+//   hit L1 (halves the 7.4 TB/s query stream from L2)                                                              49.9 ms
+//   query chunks fetched two chunks ahead through three register buffers                                          46.9 ms
+//   255 registers, 8 warps / SM (with two / three buffers)                                                 46.7 / 46.3 ms
+//   four segments per barrier                                                                                     46.6 ms
+// - neither the L2 -> SM traffic nor the load latency is what the NQ = 1 chunk loop waits for: the L1 data pipe is 66 % busy
 // (a broadcast LDS.128 costs two wavefronts, a coalesced LDG.64 two), the FP64 pipe 44 %.
-#ifndef SS_COS_SHARE
-#define SS_COS_SHARE 1
-#endif
-constexpr int kCosShare = SS_COS_SHARE;
-constexpr int kCosQG = 4 / kCosShare;    // query groups per CTA
-static_assert(kCosShare == 1 || kCosStage == kCosShare * kCosG, "each sharing warp takes one kCosG of a stage");
 constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments are read from global memory)
 constexpr uint32_t kCosNone = 0xFFFFFFFFu;
 
@@ -81,70 +78,95 @@ __device__ __forceinline__ void cos_cp_async8(double* smem_dst, const double* gs
 }
 __device__ __forceinline__ void cos_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// the 8 partial sums of all G pairs advance by one chunk: yv = the query's 8 values, xs = chunk of segment 0 in shared memory
-__device__ __forceinline__ void cos_chunk(double (&p)[kCosG][8], const double (&yv)[8], const double2* xs) {
+// the 8 partial sums of all NQ x G pairs advance by one chunk: yv = the queries' 8 values, xs = chunk of segment 0 in shared memory
+template <int NQ>
+__device__ __forceinline__ void cos_chunk(double (&p)[NQ][kCosG][8], const double (&yv)[NQ][8], const double2* xs) {
 #pragma unroll
     for (int u = 0; u < kCosG; u++) {
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             const double2 xx = xs[u * (kCosSegCap / 2) + v];
-            p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
-            p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                p[q][u][2 * v] = p[q][u][2 * v] + xx.x * yv[q][2 * v];
+                p[q][u][2 * v + 1] = p[q][u][2 * v + 1] + xx.y * yv[q][2 * v + 1];
+            }
         }
     }
 }
 
-// rulinalg's combine of the 8 partial sums, then the scalar tail (elements 8 nch .. len - 1: yt = the query's chunk nch,
+// rulinalg's combine of the 8 partial sums, then the scalar tail (elements 8 nch .. len - 1: yt = the queries' chunk nch,
 // xs = that chunk of segment 0 in shared memory), per pair in the CPU path's order
-__device__ __forceinline__ void cos_finish(const double (&p)[kCosG][8], double (&sum)[kCosG], const double (&yt)[8], const double2* xs,
-                                           uint32_t ntail) {
+template <int NQ>
+__device__ __forceinline__ void cos_finish(const double (&p)[NQ][kCosG][8], double (&sum)[NQ][kCosG], const double (&yt)[NQ][8],
+                                           const double2* xs, uint32_t ntail) {
 #pragma unroll
-    for (int u = 0; u < kCosG; u++) {
-        sum[u] = 0.0 + (p[u][0] + p[u][4]);
-        sum[u] = sum[u] + (p[u][1] + p[u][5]);
-        sum[u] = sum[u] + (p[u][2] + p[u][6]);
-        sum[u] = sum[u] + (p[u][3] + p[u][7]);
+    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+        for (int u = 0; u < kCosG; u++) {
+            sum[q][u] = 0.0 + (p[q][u][0] + p[q][u][4]);
+            sum[q][u] = sum[q][u] + (p[q][u][1] + p[q][u][5]);
+            sum[q][u] = sum[q][u] + (p[q][u][2] + p[q][u][6]);
+            sum[q][u] = sum[q][u] + (p[q][u][3] + p[q][u][7]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 7; j++) {
         if ((uint32_t)j < ntail) {  // warp-uniform
 #pragma unroll
-            for (int u = 0; u < kCosG; u++) sum[u] = sum[u] + reinterpret_cast<const double*>(xs + u * (kCosSegCap / 2))[j] * yt[j];
+            for (int u = 0; u < kCosG; u++) {
+                const double xv = reinterpret_cast<const double*>(xs + u * (kCosSegCap / 2))[j];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) sum[q][u] = sum[q][u] + xv * yt[q][j];
+            }
         }
     }
 }
 
-#ifndef SS_COS_DEPTH
-#define SS_COS_DEPTH 2
-#endif
-#ifndef SS_COS_MINB
-#define SS_COS_MINB 3
-#endif
-__global__ void __launch_bounds__(128, SS_COS_MINB)
-k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, const double* __restrict__ cnorm, uint32_t nseg, int c,
-              uint32_t nslices, const double* __restrict__ qlanes, const uint32_t* __restrict__ group_len,
-              const uint32_t* __restrict__ group_rowbase, const uint32_t* __restrict__ group_qid, uint32_t ngroups,
-              const double* __restrict__ qnorm, const double* __restrict__ targets, double* __restrict__ part_dist,
-              uint32_t* __restrict__ part_idx) {
-    extern __shared__ __align__(16) double cos_sseg[];  // [2][kCosStage][kCosSegCap]: 32 KB per 4 staged segments
-    double (*sseg)[kCosStage][kCosSegCap] = reinterpret_cast<double (*)[kCosStage][kCosSegCap]>(cos_sseg);
-    __shared__ uint4 sdesc[3][kCosStage];  // {first frame lo, hi, frames, local segment index}
-    __shared__ double snorm[3][kCosStage];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t qb = blockIdx.x / nslices, slice = blockIdx.x % nslices;
-    const uint32_t g = qb * kCosQG + warp / kCosShare;
-    const int share = warp % kCosShare;  // which kCosG of every stage this warp takes
-    const bool active = g < ngroups;
-    const uint32_t qid = active ? group_qid[g * 32 + lane] : kCosNone;
-    const uint32_t kq = active ? group_len[g] * (uint32_t)c : 0;
-    const double* y = active ? qlanes + (size_t)group_rowbase[g] * c * 32 + lane : qlanes;
-    const double nq = qid != kCosNone ? qnorm[qid] : 1.0;
-    const double target = (qid != kCosNone && targets) ? targets[qid] : 1.0;
-    double best = 2.0;  // fold((0, 2.0)), src/sound.rs:361
-    uint32_t best_idx = kCosNone;
-    const uint32_t ngrp = (nseg + kCosStage - 1) / kCosStage;
+struct CosShared {
+    uint4 sdesc[3][kCosStage];  // {first frame lo, hi, frames, local segment index}
+    double snorm[3][kCosStage];
+};
 
-    // descriptor of sorted position grp * G + t (thread t < G), absent beyond the table
+// one CTA = kCosWarps work items (NQ query groups of one length each) x one slice of the dictionary's staged groups
+template <int NQ>
+__device__ __forceinline__ void cos_scan_body(double (*sseg)[kCosStage][kCosSegCap], CosShared& sh, const double* __restrict__ dmfcc,
+                                              const uint4* __restrict__ cseg, const double* __restrict__ cnorm, uint32_t nseg, int c,
+                                              uint32_t nslices, uint32_t slice, const double* __restrict__ qlanes,
+                                              const uint32_t* __restrict__ group_len, const uint32_t* __restrict__ group_rowbase,
+                                              const uint32_t* __restrict__ group_qid, uint32_t ngroups, const double* __restrict__ qnorm,
+                                              const double* __restrict__ targets, double* __restrict__ part_dist,
+                                              uint32_t* __restrict__ part_idx, const uint2* __restrict__ item) {
+    const int lane = threadIdx.x & 31;
+    const bool active = item != nullptr;  // warp-uniform
+    uint32_t g[NQ], qid[NQ], best_idx[NQ];
+    const double* y[NQ];
+    double nq[NQ], target[NQ], best[NQ];
+    {
+        const uint2 it = active ? __ldg(item) : make_uint2(0, 0);
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            g[q] = q == 0 ? it.x : it.y;
+            qid[q] = active ? group_qid[g[q] * 32 + lane] : kCosNone;
+            y[q] = active ? qlanes + (size_t)group_rowbase[g[q]] * c * 32 + lane : qlanes;
+            nq[q] = qid[q] != kCosNone ? qnorm[qid[q]] : 1.0;
+            target[q] = (qid[q] != kCosNone && targets) ? targets[qid[q]] : 1.0;
+            best[q] = 2.0;  // fold((0, 2.0)), src/sound.rs:361
+            best_idx[q] = kCosNone;
+        }
+    }
+    const uint32_t kq = active ? group_len[g[0]] * (uint32_t)c : 0;  // the groups of an item have one length
+    const uint32_t ngrp = (nseg + kCosStage - 1) / kCosStage;
+    // strict '<' in index order (src/sound.rs:362): a smaller distance wins, an equal one only with a smaller index than a
+    // winner already found; NaN never wins, 2.0 never beats the fold's seed
+    auto consider = [&](int q, double dist, uint32_t idx) {
+        if (dist < best[q] || (dist == best[q] && idx < best_idx[q] && best_idx[q] != kCosNone)) {
+            best[q] = dist;
+            best_idx[q] = idx;
+        }
+    };
+
+    // descriptor of sorted position grp * kCosStage + t (thread t < kCosStage), absent beyond the table
     auto fetch = [&](uint32_t grp, uint4& dsc, double& nrm) {
         const uint64_t s = (uint64_t)grp * kCosStage + threadIdx.x;
         dsc = make_uint4(0, 0, 0, kCosNone);
@@ -157,11 +179,11 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
     auto stage = [&](int slot, int b) {
 #pragma unroll
         for (int u = 0; u < kCosStage; u++) {
-            const uint4 dsc = sdesc[slot][u];
+            const uint4 dsc = sh.sdesc[slot][u];
             const uint32_t kd = dsc.z * (uint32_t)c;
             if (dsc.w != kCosNone && kd <= (uint32_t)kCosSegCap) {
                 const double* src = dmfcc + (((uint64_t)dsc.y << 32) | dsc.x) * c;
-                for (uint32_t e = threadIdx.x; e < kd; e += 128) cos_cp_async8(&sseg[b][u][e], src + e);
+                for (uint32_t e = threadIdx.x; e < kd; e += 32 * kCosWarps) cos_cp_async8(&sseg[b][u][e], src + e);
             }
         }
     };
@@ -171,8 +193,8 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
         fetch(slice, d0, n0);
         fetch(slice + nslices, d1, n1);
         if (threadIdx.x < kCosStage) {
-            sdesc[0][threadIdx.x] = d0, snorm[0][threadIdx.x] = n0;
-            sdesc[1][threadIdx.x] = d1, snorm[1][threadIdx.x] = n1;
+            sh.sdesc[0][threadIdx.x] = d0, sh.snorm[0][threadIdx.x] = n0;
+            sh.sdesc[1][threadIdx.x] = d1, sh.snorm[1][threadIdx.x] = n1;
         }
         __syncthreads();
         stage(0, 0);
@@ -188,15 +210,15 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
         fetch(grp + 2 * nslices, d2, n2);
         if (active) {
 #pragma unroll 1
-          for (int u0 = kCosShare == 1 ? 0 : share * kCosG; u0 < (kCosShare == 1 ? kCosStage : (share + 1) * kCosG); u0 += kCosG) {
+          for (int u0 = 0; u0 < kCosStage; u0 += kCosG) {
             uint32_t kd[kCosG], sidx[kCosG], len[kCosG], nchunk[kCosG];
             const double* xg[kCosG];
-            double p[kCosG][8];
+            double p[NQ][kCosG][8];
             bool uniform = true, all_staged = true;
             uint32_t maxchunk = 0;
 #pragma unroll
             for (int u = 0; u < kCosG; u++) {
-                const uint4 dsc = sdesc[cur][u0 + u];
+                const uint4 dsc = sh.sdesc[cur][u0 + u];
                 sidx[u] = dsc.w;
                 kd[u] = dsc.w != kCosNone ? dsc.z * (uint32_t)c : 0;
                 xg[u] = dmfcc + (((uint64_t)dsc.y << 32) | dsc.x) * c;
@@ -206,118 +228,170 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
                 uniform = uniform && dsc.w != kCosNone && kd[u] == kd[0];
                 all_staged = all_staged && kd[u] <= (uint32_t)kCosSegCap;
 #pragma unroll
-                for (int v = 0; v < 8; v++) p[u][v] = 0.0;
+                for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                    for (int v = 0; v < 8; v++) p[q][u][v] = 0.0;
+                }
             }
             const double2* xs = reinterpret_cast<const double2*>(&sseg[b][u0][0]);
             if (uniform && all_staged) {
-                // ---- four segments of one length: straight-line chunks, two per iteration ----------------------------------
-                const uint32_t nch = nchunk[0], ntail = len[0] - nch * 8;
-                const double* yp = y;
-                double sum[kCosG];
-#if SS_COS_DEPTH == 3
-                // three register buffers: the query's chunks are fetched two chunks ahead of their use
-                double ya[8], yb[8], yc[8];
-#pragma unroll
-                for (int v = 0; v < 8; v++) ya[v] = yp[v * 32], yb[v] = yp[(8 + v) * 32];
-                uint32_t ch = 0;
-                for (; ch + 3 <= nch; ch += 3) {
-#pragma unroll
-                    for (int v = 0; v < 8; v++) yc[v] = yp[(16 + v) * 32];
-                    cos_chunk(p, ya, xs);
-#pragma unroll
-                    for (int v = 0; v < 8; v++) ya[v] = yp[(24 + v) * 32];
-                    cos_chunk(p, yb, xs + 4);
-#pragma unroll
-                    for (int v = 0; v < 8; v++) yb[v] = yp[(32 + v) * 32];
-                    cos_chunk(p, yc, xs + 8);
-                    yp += 24 * 32;
-                    xs += 12;
-                }
-                if (ch == nch) {
-                    cos_finish(p, sum, ya, xs, ntail);
-                } else if (ch + 1 == nch) {
-                    cos_chunk(p, ya, xs);
-                    cos_finish(p, sum, yb, xs + 4, ntail);
-                } else {
-#pragma unroll
-                    for (int v = 0; v < 8; v++) yc[v] = yp[(16 + v) * 32];
-                    cos_chunk(p, ya, xs);
-                    cos_chunk(p, yb, xs + 4);
-                    cos_finish(p, sum, yc, xs + 8, ntail);
-                }
-#else
-                double ya[8], yb[8];
+                // ---- four segments of one length: straight-line chunks -------------------------------------------------------
                 // (query loads may run up to a chunk past the query's last element - the chunk that holds the tail: the lane
                 // buffer is padded, values beyond the tail go unused)
+                const uint32_t nch = nchunk[0], ntail = len[0] - nch * 8;
+                double sum[NQ][kCosG];
+                if constexpr (NQ == 1) {
+                    // two register buffers, two chunks per iteration (no register copies)
+                    const double* yp = y[0];
+                    double ya[1][8], yb[1][8];
 #pragma unroll
-                for (int v = 0; v < 8; v++) ya[v] = yp[v * 32];
-                uint32_t ch = 0;
-                for (; ch + 2 <= nch; ch += 2) {
+                    for (int v = 0; v < 8; v++) ya[0][v] = yp[v * 32];
+                    uint32_t ch = 0;
+                    for (; ch + 2 <= nch; ch += 2) {
 #pragma unroll
-                    for (int v = 0; v < 8; v++) yb[v] = yp[(8 + v) * 32];
-                    cos_chunk(p, ya, xs);
+                        for (int v = 0; v < 8; v++) yb[0][v] = yp[(8 + v) * 32];
+                        cos_chunk<1>(p, ya, xs);
 #pragma unroll
-                    for (int v = 0; v < 8; v++) ya[v] = yp[(16 + v) * 32];
-                    cos_chunk(p, yb, xs + 4);
-                    yp += 16 * 32;
-                    xs += 8;
-                }
-                // the chunk after the last whole one holds the <= 7 tail elements: it is in registers by the time the sums are
-                // combined (a tail read from global memory element by element was 9 % of the kernel's stall samples); the four
-                // tails advance together, then the four divisions
-                if (ch < nch) {
+                        for (int v = 0; v < 8; v++) ya[0][v] = yp[(16 + v) * 32];
+                        cos_chunk<1>(p, yb, xs + 4);
+                        yp += 16 * 32;
+                        xs += 8;
+                    }
+                    // the chunk after the last whole one holds the <= 7 tail elements: it is in registers by the time the sums
+                    // are combined (a tail read from global memory element by element was 9 % of the kernel's stall samples);
+                    // the four tails advance together, then the four divisions
+                    if (ch < nch) {
 #pragma unroll
-                    for (int v = 0; v < 8; v++) yb[v] = yp[(8 + v) * 32];
-                    cos_chunk(p, ya, xs);
-                    cos_finish(p, sum, yb, xs + 4, ntail);
+                        for (int v = 0; v < 8; v++) yb[0][v] = yp[(8 + v) * 32];
+                        cos_chunk<1>(p, ya, xs);
+                        cos_finish<1>(p, sum, yb, xs + 4, ntail);
+                    } else {
+                        cos_finish<1>(p, sum, ya, xs, ntail);
+                    }
                 } else {
-                    cos_finish(p, sum, ya, xs, ntail);
+                    // one register buffer refilled in place: pair v of the next chunk is requested right after pair v of the
+                    // current chunk has served all NQ x G pairs
+                    const double* yp[NQ];
+                    double yv[NQ][8];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        yp[q] = y[q];
+#pragma unroll
+                        for (int v = 0; v < 8; v++) yv[q][v] = yp[q][v * 32];
+                    }
+                    for (uint32_t ch = 0; ch < nch; ch++) {
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) yp[q] += 8 * 32;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+#pragma unroll
+                            for (int u = 0; u < kCosG; u++) {
+                                const double2 xx = xs[u * (kCosSegCap / 2) + v];
+#pragma unroll
+                                for (int q = 0; q < NQ; q++) {
+                                    p[q][u][2 * v] = p[q][u][2 * v] + xx.x * yv[q][2 * v];
+                                    p[q][u][2 * v + 1] = p[q][u][2 * v + 1] + xx.y * yv[q][2 * v + 1];
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < NQ; q++) {
+                                yv[q][2 * v] = yp[q][(2 * v) * 32];
+                                yv[q][2 * v + 1] = yp[q][(2 * v + 1) * 32];
+                            }
+                        }
+                        xs += 4;
+                    }
+                    cos_finish<NQ>(p, sum, yv, xs, ntail);
                 }
-#endif
 #pragma unroll
                 for (int u = 0; u < kCosG; u++) {
-                    const double dist = fabs(sum[u] / (snorm[cur][u0 + u] * nq) - target);  // src/sound.rs:30-32, 359
-                    if (dist < best || (dist == best && sidx[u] < best_idx && best_idx != kCosNone)) {
-                        best = dist;
-                        best_idx = sidx[u];
-                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; q++)
+                        consider(q, fabs(sum[q][u] / (sh.snorm[cur][u0 + u] * nq[q]) - target[q]), sidx[u]);  // src/sound.rs:30-32, 359
                     sidx[u] = kCosNone;  // done: the general epilogue below skips it
                 }
             } else if (all_staged) {
-                // ---- mixed lengths, all in shared memory: the query's next chunk is fetched while the current one is consumed
-                const double* yp = y;
-                double yv[8];
-                if (maxchunk) {
+                // ---- mixed lengths, all in shared memory: the queries' next chunk is fetched while the current one is consumed
+                if constexpr (NQ == 1) {
+                    double yv[NQ][8];
+                    if (maxchunk) {
 #pragma unroll
-                    for (int v = 0; v < 8; v++) yv[v] = yp[v * 32];
-                }
-                for (uint32_t ch = 0; ch < maxchunk; ch++) {
-                    double yn[8];
-                    yp += 8 * 32;
-                    if (ch + 1 < maxchunk) {
+                        for (int q = 0; q < NQ; q++) {
 #pragma unroll
-                        for (int v = 0; v < 8; v++) yn[v] = yp[v * 32];
+                            for (int v = 0; v < 8; v++) yv[q][v] = y[q][v * 32];
+                        }
                     }
+                    for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                        double yn[NQ][8];
+                        if (ch + 1 < maxchunk) {
 #pragma unroll
-                    for (int u = 0; u < kCosG; u++) {
-                        if (ch < nchunk[u]) {  // warp-uniform
+                            for (int q = 0; q < NQ; q++) {
 #pragma unroll
-                            for (int v = 0; v < 4; v++) {
-                                const double2 xx = xs[u * (kCosSegCap / 2) + ch * 4 + v];
-                                p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
-                                p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+                                for (int v = 0; v < 8; v++) yn[q][v] = y[q][((size_t)(ch + 1) * 8 + v) * 32];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kCosG; u++) {
+                            if (ch < nchunk[u]) {  // warp-uniform
+#pragma unroll
+                                for (int v = 0; v < 4; v++) {
+                                    const double2 xx = xs[u * (kCosSegCap / 2) + ch * 4 + v];
+#pragma unroll
+                                    for (int q = 0; q < NQ; q++) {
+                                        p[q][u][2 * v] = p[q][u][2 * v] + xx.x * yv[q][2 * v];
+                                        p[q][u][2 * v + 1] = p[q][u][2 * v + 1] + xx.y * yv[q][2 * v + 1];
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                            for (int v = 0; v < 8; v++) yv[q][v] = yn[q][v];
+                        }
+                    }
+                } else {
+                    // (in place, as above: the loads run at most one chunk past the last whole chunk of the query)
+                    double yv[NQ][8];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                        for (int v = 0; v < 8; v++) yv[q][v] = y[q][v * 32];
+                    }
+                    for (uint32_t ch = 0; ch < maxchunk; ch++) {
+                        bool on[kCosG];
+#pragma unroll
+                        for (int u = 0; u < kCosG; u++) on[u] = ch < nchunk[u];  // warp-uniform
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+#pragma unroll
+                            for (int u = 0; u < kCosG; u++) {
+                                if (on[u]) {
+                                    const double2 xx = xs[u * (kCosSegCap / 2) + ch * 4 + v];
+#pragma unroll
+                                    for (int q = 0; q < NQ; q++) {
+                                        p[q][u][2 * v] = p[q][u][2 * v] + xx.x * yv[q][2 * v];
+                                        p[q][u][2 * v + 1] = p[q][u][2 * v + 1] + xx.y * yv[q][2 * v + 1];
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < NQ; q++) {
+                                yv[q][2 * v] = y[q][((size_t)(ch + 1) * 8 + 2 * v) * 32];
+                                yv[q][2 * v + 1] = y[q][((size_t)(ch + 1) * 8 + 2 * v + 1) * 32];
                             }
                         }
                     }
-#pragma unroll
-                    for (int v = 0; v < 8; v++) yv[v] = yn[v];
                 }
             } else {
                 // ---- some segment longer than the staging buffer: its frames come from global memory ----------------------
                 for (uint32_t ch = 0; ch < maxchunk; ch++) {
-                    double yv[8];
+                    double yv[NQ][8];
 #pragma unroll
-                    for (int v = 0; v < 8; v++) yv[v] = y[((size_t)ch * 8 + v) * 32];
+                    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                        for (int v = 0; v < 8; v++) yv[q][v] = y[q][((size_t)ch * 8 + v) * 32];
+                    }
 #pragma unroll
                     for (int u = 0; u < kCosG; u++) {
                         if (ch < nchunk[u]) {  // warp-uniform
@@ -325,12 +399,19 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
 #pragma unroll
                                 for (int v = 0; v < 4; v++) {
                                     const double2 xx = xs[u * (kCosSegCap / 2) + ch * 4 + v];
-                                    p[u][2 * v] = p[u][2 * v] + xx.x * yv[2 * v];
-                                    p[u][2 * v + 1] = p[u][2 * v + 1] + xx.y * yv[2 * v + 1];
+#pragma unroll
+                                    for (int q = 0; q < NQ; q++) {
+                                        p[q][u][2 * v] = p[q][u][2 * v] + xx.x * yv[q][2 * v];
+                                        p[q][u][2 * v + 1] = p[q][u][2 * v + 1] + xx.y * yv[q][2 * v + 1];
+                                    }
                                 }
                             } else {
 #pragma unroll
-                                for (int v = 0; v < 8; v++) p[u][v] = p[u][v] + __ldg(xg[u] + (size_t)ch * 8 + v) * yv[v];
+                                for (int v = 0; v < 8; v++) {
+                                    const double xv = __ldg(xg[u] + (size_t)ch * 8 + v);
+#pragma unroll
+                                    for (int q = 0; q < NQ; q++) p[q][u][v] = p[q][u][v] + xv * yv[q][v];
+                                }
                             }
                         }
                     }
@@ -340,37 +421,67 @@ k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, 
 #pragma unroll
             for (int u = 0; u < kCosG; u++) {
                 if (sidx[u] != kCosNone) {
-                    double sum = 0.0;
-                    sum = sum + (p[u][0] + p[u][4]);
-                    sum = sum + (p[u][1] + p[u][5]);
-                    sum = sum + (p[u][2] + p[u][6]);
-                    sum = sum + (p[u][3] + p[u][7]);
+                    double sum[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        sum[q] = 0.0;
+                        sum[q] = sum[q] + (p[q][u][0] + p[q][u][4]);
+                        sum[q] = sum[q] + (p[q][u][1] + p[q][u][5]);
+                        sum[q] = sum[q] + (p[q][u][2] + p[q][u][6]);
+                        sum[q] = sum[q] + (p[q][u][3] + p[q][u][7]);
+                    }
                     for (uint32_t e = nchunk[u] * 8; e < len[u]; e++) {
                         const double xv = kd[u] <= (uint32_t)kCosSegCap ? sseg[b][u0 + u][e] : __ldg(xg[u] + e);
-                        sum = sum + xv * y[(size_t)e * 32];
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) sum[q] = sum[q] + xv * y[q][(size_t)e * 32];
                     }
-                    const double nrm = snorm[cur][u0 + u] * nq;   // norm(me) * norm(you), src/sound.rs:30
-                    const double sim = sum / nrm;            // src/sound.rs:32
-                    const double dist = fabs(sim - target);  // src/sound.rs:359
-                    // strict '<' in index order (src/sound.rs:362): a smaller distance wins, an equal one only with a smaller
-                    // index than a winner already found; NaN never wins, 2.0 never beats the fold's seed
-                    if (dist < best || (dist == best && sidx[u] < best_idx && best_idx != kCosNone)) {
-                        best = dist;
-                        best_idx = sidx[u];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const double nrm = sh.snorm[cur][u0 + u] * nq[q];  // norm(me) * norm(you), src/sound.rs:30
+                        const double sim = sum[q] / nrm;                   // src/sound.rs:32
+                        consider(q, fabs(sim - target[q]), sidx[u]);       // src/sound.rs:359
                     }
                 }
             }
           }
         }
-        if (threadIdx.x < kCosStage) sdesc[nxt2][threadIdx.x] = d2, snorm[nxt2][threadIdx.x] = n2;
+        if (threadIdx.x < kCosStage) sh.sdesc[nxt2][threadIdx.x] = d2, sh.snorm[nxt2][threadIdx.x] = n2;
         cur = nxt;
         b ^= 1;
     }
     cos_cp_async_wait_all();
     if (!active) return;
-    const size_t o = ((size_t)slice * kCosShare + share) * ngroups * 32 + (size_t)g * 32 + lane;
-    part_dist[o] = best;
-    part_idx[o] = best_idx;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        const size_t o = (size_t)slice * ngroups * 32 + (size_t)g[q] * 32 + lane;
+        part_dist[o] = best[q];
+        part_idx[o] = best_idx[q];
+    }
+}
+
+// blocks [0, nqb2 * nslices) take the paired work items (two groups of one length per warp), the rest the single groups
+// (half as long per CTA: they fill the tail); items = {g0, g1} x npairs, then {g, -} x nsingles
+__global__ void __launch_bounds__(32 * kCosWarps, 2)
+k_cosine_scan(const double* __restrict__ dmfcc, const uint4* __restrict__ cseg, const double* __restrict__ cnorm, uint32_t nseg, int c,
+              uint32_t nslices, const double* __restrict__ qlanes, const uint32_t* __restrict__ group_len,
+              const uint32_t* __restrict__ group_rowbase, const uint32_t* __restrict__ group_qid, uint32_t ngroups,
+              const double* __restrict__ qnorm, const double* __restrict__ targets, double* __restrict__ part_dist,
+              uint32_t* __restrict__ part_idx, const uint2* __restrict__ items, uint32_t npairs, uint32_t nsingles) {
+    extern __shared__ __align__(16) double cos_sseg[];  // [2][kCosStage][kCosSegCap]: 32 KB per 4 staged segments
+    double (*sseg)[kCosStage][kCosSegCap] = reinterpret_cast<double (*)[kCosStage][kCosSegCap]>(cos_sseg);
+    __shared__ CosShared sh;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t pair_blocks = (npairs + kCosWarps - 1) / kCosWarps * nslices;
+    if (blockIdx.x < pair_blocks) {
+        const uint32_t it = blockIdx.x / nslices * kCosWarps + warp;
+        cos_scan_body<2>(sseg, sh, dmfcc, cseg, cnorm, nseg, c, nslices, blockIdx.x % nslices, qlanes, group_len, group_rowbase, group_qid,
+                         ngroups, qnorm, targets, part_dist, part_idx, it < npairs ? items + it : nullptr);
+    } else {
+        const uint32_t r = blockIdx.x - pair_blocks;
+        const uint32_t it = r / nslices * kCosWarps + warp;
+        cos_scan_body<1>(sseg, sh, dmfcc, cseg, cnorm, nseg, c, nslices, r % nslices, qlanes, group_len, group_rowbase, group_qid,
+                         ngroups, qnorm, targets, part_dist, part_idx, it < nsingles ? items + npairs + it : nullptr);
+    }
 }
 
 __global__ void k_cosine_merge(const double* __restrict__ part_dist, const uint32_t* __restrict__ part_idx, uint32_t nslices,
@@ -457,6 +568,26 @@ int cosine_queries_build(ss_queries* q) {
                                                             q->d_group_rowbase.p, q->d_group_qid.p, q->d_lane64.p);
         SS_LAUNCHED(ctx);
     }
+    // work items of the scan: two groups of one length per warp wherever a length has two, the odd group of a length alone
+    {
+        std::vector<uint2> pairs, singles;
+        for (uint32_t g = 0; g < q->ngroups;) {
+            if (g + 1 < q->ngroups && q->h_group_len[g + 1] == q->h_group_len[g]) {
+                pairs.push_back(make_uint2(g, g + 1));
+                g += 2;
+            } else {
+                singles.push_back(make_uint2(g, kCosNone));
+                g += 1;
+            }
+        }
+        q->cos_npairs = (uint32_t)pairs.size();
+        q->cos_nsingles = (uint32_t)singles.size();
+        pairs.insert(pairs.end(), singles.begin(), singles.end());
+        if (!pairs.empty()) {
+            SS_TRY(upload(ctx, q->d_cos_items, pairs.data(), pairs.size()));
+            SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the table is local
+        }
+    }
     q->cos_built = true;
     return SS_OK;
 }
@@ -487,14 +618,15 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
         k_fill_result<<<ceil_div((long long)q->nq, 256), 256, 0, ctx->stream>>>(d_out_idx, d_out_dist, q->nq, d->index_base, 2.0);
         SS_LAUNCHED(ctx);
     }
-    const uint32_t nqb = (q->ngroups + kCosQG - 1) / kCosQG;
+    const uint32_t nqb2 = (q->cos_npairs + kCosWarps - 1) / kCosWarps, nqb1 = (q->cos_nsingles + kCosWarps - 1) / kCosWarps;
+    const uint32_t nqb = nqb2 + nqb1;  // CTAs per slice: paired work items first, single groups last
     if (!nqb || !d->nseg) return SS_OK;
     const uint32_t nslots = q->ngroups * 32;
     // slice sl takes the groups sl, sl + nslices, ... of that order: every slice sees the same mix of lengths
     const uint32_t ngrp = (uint32_t)((d->nseg + kCosStage - 1) / kCosStage);
     const uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(ngrp, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
-    SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * kCosShare * nslots));
-    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * kCosShare * nslots));
+    SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
+    SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
     if (!d->ev_scan0) {
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan0));
         SS_CUDA(ctx, cudaEventCreate(&d->ev_scan1));
@@ -502,13 +634,14 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan0, ctx->stream));
     const int cos_smem = (int)(sizeof(double) * 2 * kCosStage * kCosSegCap);
     SS_CUDA(ctx, cudaFuncSetAttribute(k_cosine_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, cos_smem));
-    k_cosine_scan<<<nqb * nslices, 128, cos_smem, ctx->stream>>>(d->d_mfcc.p, d->d_cos_seg.p, d->d_cos_norm.p, (uint32_t)d->nseg, d->c, nslices,
+    k_cosine_scan<<<nqb * nslices, 32 * kCosWarps, cos_smem, ctx->stream>>>(d->d_mfcc.p, d->d_cos_seg.p, d->d_cos_norm.p, (uint32_t)d->nseg, d->c, nslices,
                                                          q->d_lane64.p, q->d_group_len.p, q->d_group_rowbase.p, q->d_group_qid.p,
-                                                         q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p);
+                                                         q->ngroups, q->d_norm.p, d_targets, d->d_cand_exact.p, d->d_cand_idx.p, q->d_cos_items.p,
+                                                         q->cos_npairs, q->cos_nsingles);
     SS_LAUNCHED(ctx);
     SS_CUDA(ctx, cudaEventRecord(d->ev_scan1, ctx->stream));
     d->scan_timed = true;
-    k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices * kCosShare, nslots,
+    k_cosine_merge<<<ceil_div(nslots, 128), 128, 0, ctx->stream>>>(d->d_cand_exact.p, d->d_cand_idx.p, nslices, nslots,
                                                                   q->d_group_qid.p, d->index_base, d_out_idx, d_out_dist);
     SS_LAUNCHED(ctx);
     return SS_OK;

@@ -160,6 +160,8 @@ struct ss_queries {
     ss::DevBuf<float4> d_lane;                                       // [row][4][32] float4 (DTW)
     ss::DevBuf<float> d_max_norm;                                    // [0] = max |a|^2
     ss::DevBuf<double> d_lane64;                                     // [row*c + e][32] f64 (cosine-ref), built on first use
+    ss::DevBuf<uint2> d_cos_items;                                   // cosine-ref work items: {g0, g1} pairs of one length, then single groups
+    uint32_t cos_npairs = 0, cos_nsingles = 0;
     bool cos_built = false;
     bool lane_built = false;
     // tensor-core scan: groups of 128 (nearly) equal-length queries. The grouping only depends on the lengths: it is built
