@@ -67,6 +67,8 @@ constexpr int kCosWarps = 4;    // work items per CTA
 //   query chunks fetched two chunks ahead through three register buffers                                          46.9 ms
 //   255 registers, 8 warps / SM (with two / three buffers)                                                 46.7 / 46.3 ms
 //   four segments per barrier                                                                                     46.6 ms
+// and with the 2 x 4 tile (39.5 ms):
+//   one prefetch.global.L1 (CCTL.PF1) per chunk, lane l on line l of the two groups' chunk two / three chunks ahead     46.4 ms
 // - neither the L2 -> SM traffic nor the load latency is what the NQ = 1 chunk loop waits for: the L1 data pipe is 66 % busy
 // (a broadcast LDS.128 costs two wavefronts, a coalesced LDG.64 two), the FP64 pipe 44 %.
 constexpr int kCosSegCap = 512; // doubles of shared memory per staged segment (longer segments are read from global memory)
