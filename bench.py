@@ -31,6 +31,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -338,6 +339,27 @@ def run_match(args):
             step_e2e()
         # e2e blocks on the host every step (the call returns results in host memory): wall clock == device time here
         _, ms_e2e = timed(step_e2e, args.steps)
+        # one more untimed step with the scan's per-CTA timeline hook on (SS_DTW_H2_TIMELINE): clock64 cycles over globaltimer ns
+        # of every CTA's DP phase = the SM clock the scan actually runs at. NVML reports 1 965 MHz under this load while the
+        # SMs count 1 842 MHz (15/16 of it); the ceilings of the roofline block are in clock64 cycles (tools/microbench_band2.cu),
+        # so the achieved rate has to be, too.
+        sm_mhz_kernel = None
+        tl_path = os.path.join(tempfile.gettempdir(), "ss_h2_timeline_%d_%d.txt" % (os.getpid(), rank))
+        os.environ["SS_DTW_H2_TIMELINE"] = tl_path
+        try:
+            step_resident()
+            ctx.check(lib.ss_dict_match_finish(shard.h))
+            barrier()
+        finally:
+            del os.environ["SS_DTW_H2_TIMELINE"]
+        if os.path.exists(tl_path):
+            try:
+                tl = np.loadtxt(tl_path, dtype=np.int64, comments="#", ndmin=2)
+                tl = tl[(tl[:, 1] > 0) & (tl[:, 3] > tl[:, 2])] if tl.shape[1] >= 12 else tl[:0]
+                if len(tl):
+                    sm_mhz_kernel = float(np.median(tl[:, 10] / (tl[:, 3] - tl[:, 2])) * 1e3)
+            finally:
+                os.remove(tl_path)
     res_idx = o_idx.cpu().numpy().view(np.uint32)
     res_dist = o_dist.cpu().numpy()
     assert np.array_equal(res_idx, h_idx.numpy().view(np.uint32)) and np.array_equal(res_dist, h_dist.numpy()), "e2e and resident paths disagree"
@@ -372,7 +394,9 @@ def run_match(args):
         if os.path.exists(tp) and world == 1 and args.nd == ND and args.nq == NQ:
             tj = json.load(open(tp)).get({1: "h2", 2: "tc"}.get(kind, "fp32"), {})
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-        sm_mhz = ((clocks or {}).get("sm_mhz") or 1965.0)
+        if clocks is not None:
+            clocks["sm_mhz_in_kernel"] = sm_mhz_kernel
+        sm_mhz = sm_mhz_kernel or ((clocks or {}).get("sm_mhz") or 1965.0)
         sms = 148.0
         cells_clk_sm = shard_cells / (scan_ms * 1e-3) / sms / (sm_mhz * 1e6) if scan_ms > 0 else None
         cpu = None
@@ -402,8 +426,9 @@ def run_match(args):
                          "unit": "DP cells/clk/SM", "frac": (cells_clk_sm / alu_peak) if cells_clk_sm else None,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "measured on B200: every DP cell needs one three-input min on the ALU pipe, which issues FMNMX3 (1 cell) / VHMNMX "
-                                        "(2 cells) at 63.9 lanes/clk/SM (tools/microbench_band2.cu, profiles/r2_microbench_band2.log); SM clock = median "
-                                        "sampled under load",
+                                        "(2 cells) at 63.9 lanes/clk/SM (tools/microbench_band2.cu, profiles/r2_microbench_band2.log) per clock64 cycle; SM clock = "
+                                        "clocks.sm_mhz_in_kernel: clock64 cycles / globaltimer ns over the DP phase of every CTA of one untimed step "
+                                        "(NVML's sm clock when that is unavailable)",
                          "band_ceiling": band_ceiling,
                          "frac_of_band_ceiling": (cells_clk_sm / band_ceiling) if cells_clk_sm else None,
                          "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / ms_step if ms_step else None,

@@ -77,7 +77,8 @@ struct H2Params {
     uint32_t bnd_rows;
     float eta;                    // LONG kernel: subtracted from a pair's scan distance before its key is deflated (bound_mode 3)
     // measurement hook (SS_DTW_H2_TIMELINE=<file>, nullptr otherwise): per CTA {start, setup done, DP done, end} in %globaltimer ns,
-    // then {smid, kind, group, slice} - [grid][8] u64, written by thread 0
+    // then {smid | kind << 16 | group << 32, SM cycles (clock64) between stamps 1 and 2, end of the first half of the tiles,
+    // L << 32 | tiles} - [grid][8] u64, written by thread 0
     unsigned long long* timeline;
 };
 __device__ __forceinline__ unsigned long long h2_now() {
@@ -400,7 +401,20 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
     unsigned long long* topk = reinterpret_cast<unsigned long long*>(bars + 32);  // [KP][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x / p.nslices, slice = p.slice_begin + blockIdx.x % p.nslices;
+    // CTA order: the FIRST slice of every group, then the other slices group by group (longest groups first in both parts).
+    // The slices of a group otherwise start together and none of them ever sees a sibling's threshold: with an empty
+    // threshold a thread's list takes 8 (1 + ln(n / 8)) sorted insertions over the n pairs of its slice, whatever n - per
+    // unit of work 5 times more on a 1/8 shard (ncu: 2.8 x the shared-memory wavefronts, + 5.7 % instructions, + 8 % cycles
+    // per step). With the first slice's threshold published before most of the others start, ~KP pairs per slice pass.
+    // Measured: 4.90 -> 4.85 ms on a 1/8 shard, 36.08 -> 35.97 ms at config 4 (the insertions were a part of the loss, not all
+    // of it: profiles/r2_h2_cycles_per_tile_eighth_vs_full.txt). Restricting the order to the first launch measured the same.
+    uint32_t g, slice;
+    if (blockIdx.x < p.ngroups) {
+        g = blockIdx.x, slice = p.slice_begin;
+    } else {
+        const uint32_t r = blockIdx.x - p.ngroups;
+        g = r / (p.nslices - 1), slice = p.slice_begin + 1 + r % (p.nslices - 1);
+    }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next tile kind's launch may start filling SMs
     const uint32_t glen = p.group_len[g];
     const uint32_t L = glen & 0xFFFFu, lmin = glen >> 16;
@@ -410,7 +424,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
     if (tl && threadIdx.x == 0) {
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        tl[0] = h2_now(), tl[4] = smid, tl[5] = NB, tl[6] = g, tl[7] = ((unsigned long long)L << 32) | ntiles;
+        tl[0] = h2_now(), tl[4] = smid | ((unsigned long long)NB << 16) | ((unsigned long long)g << 32), tl[7] = ((unsigned long long)L << 32) | ntiles;
     }
 
     if (threadIdx.x == 0) {
@@ -427,7 +441,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tl && threadIdx.x == 0) tl[1] = h2_now();
+    if (tl && threadIdx.x == 0) tl[1] = h2_now(), tl[5] = clock64();
     if (warp == kH2DpWarps) {
         if (lane == 0 && ntiles) {
             // ---- producer: TMA + MMA issue ---------------------------------------------------------------------------------
@@ -510,6 +524,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
                 if (ng == 1) h2_tile<4, 1>(L, lmin, Lm, sc, cur, res);
                 else h2_tile<4, 2>(L, lmin, Lm, sc, cur, res);
             }
+            if (tl && threadIdx.x == 0 && n + 1 == (ntiles + 1) / 2) tl[6] = h2_now();  // (measurement: the slice's half-way mark)
             if (Lm) {
 #pragma unroll
                 for (int b = 0; b < NB; b++) {
@@ -531,7 +546,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         }
         // the two slots' lists of query m (threads m, m + 128) are merged by the slot-0 thread
         asm volatile("bar.sync 1, %0;" ::"n"(kH2DpThreads) : "memory");
-        if (tl && threadIdx.x == 0) tl[2] = h2_now();
+        if (tl && threadIdx.x == 0) tl[2] = h2_now(), tl[5] = clock64() - tl[5];  // SM cycles of the DP phase (-> the SM clock under load)
         if (slot == 0) {
             const unsigned long long* other = list + kTcM;
             for (int s = 0; s < KP; s++) {  // ascending: stop at the first key that does not make the cut
@@ -1182,10 +1197,11 @@ int dtw_h2_match_dev(ss_dict* d, ss_queries* q, int k, uint32_t* d_out_idx, doub
         SS_CUDA(ctx, cudaMemcpyAsync(h.data(), plan.p.timeline, n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         SS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (FILE* f = fopen(getenv("SS_DTW_H2_TIMELINE"), "w")) {
-            fprintf(f, "# cta start_ns setup_ns dp_done_ns end_ns smid kind group L ntiles\n");
+            fprintf(f, "# cta start_ns setup_ns dp_done_ns end_ns smid kind group L ntiles dp_cycles half_ns\n");
             for (size_t i = 0; i < n; i++)
-                fprintf(f, "%zu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i, h[i * 8], h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3], h[i * 8 + 4], h[i * 8 + 5],
-                        h[i * 8 + 6], h[i * 8 + 7] >> 32, h[i * 8 + 7] & 0xFFFFFFFFull);
+                fprintf(f, "%zu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i, h[i * 8], h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3],
+                        h[i * 8 + 4] & 0xFFFFull, (h[i * 8 + 4] >> 16) & 0xFFFFull, h[i * 8 + 4] >> 32, h[i * 8 + 7] >> 32, h[i * 8 + 7] & 0xFFFFFFFFull,
+                        h[i * 8 + 5], h[i * 8 + 6]);
             fclose(f);
         }
     }

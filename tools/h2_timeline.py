@@ -9,7 +9,7 @@ import numpy as np
 
 rows = np.loadtxt(sys.argv[1], dtype=np.int64, comments="#", ndmin=2)
 rows = rows[rows[:, 1] > 0]
-cta, t0, t1, t2, t3, smid, kind, group, L, ntiles = rows.T
+cta, t0, t1, t2, t3, smid, kind, group, L, ntiles = rows[:, :10].T
 T0, T1 = t0.min(), t3.max()
 span = (T1 - T0) / 1e6
 nsm = len(np.unique(smid))
@@ -41,3 +41,18 @@ for k in sorted(np.unique(kind)):
     steps = ((L[m] + 1) // 2) * ntiles[m]
     print("kind NB=%d: %d CTAs, duration median %.1f us (min %.1f, max %.1f); first start %.3f ms, last end %.3f ms; %.3f us per (tile, 2-row step)"
           % (k, m.sum(), np.median(d), d.min(), d.max(), (t0[m].min() - T0) / 1e6, (t3[m].max() - T0) / 1e6, ((t2 - t1)[m].sum() / 1e3) / steps.sum()))
+
+# the SM clock the DP phase ran at (clock64 cycles / globaltimer ns), and the two halves of every slice
+if rows.shape[1] >= 12:
+    cyc, th = rows[:, 10], rows[:, 11]
+    f = cyc / np.maximum(t2 - t1, 1)
+    print("SM clock over the DP phases (clock64 / globaltimer): median %.1f MHz, p10 %.1f, p90 %.1f" % (1e3 * np.median(f), 1e3 * np.percentile(f, 10), 1e3 * np.percentile(f, 90)))
+    for k in sorted(np.unique(kind)):
+        m = (kind == k) & (ntiles >= 4) & (th > 0)
+        if not m.any():
+            continue
+        h1 = (ntiles[m] + 1) // 2
+        a = (th - t1)[m] / 1e3 / h1
+        b = (t2 - th)[m] / 1e3 / np.maximum(ntiles[m] - h1, 1)
+        print("kind NB=%d: us per tile, first half of the slice %.3f, second half %.3f (ratio %.3f); SM cycles per tile %.0f"
+              % (k, a.mean(), b.mean(), a.mean() / b.mean(), (cyc[m] / ntiles[m]).mean()))
