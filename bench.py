@@ -343,15 +343,17 @@ def run_match(args):
         # of every CTA's DP phase = the SM clock the scan actually runs at. NVML reports 1 965 MHz under this load while the
         # SMs count 1 842 MHz (15/16 of it); the ceilings of the roofline block are in clock64 cycles (tools/microbench_band2.cu),
         # so the achieved rate has to be, too.
+        # (one GPU only: the N > 1 lines keep NVML's clock - the hook synchronises inside the match, between scan and exchange)
         sm_mhz_kernel = None
         tl_path = os.path.join(tempfile.gettempdir(), "ss_h2_timeline_%d_%d.txt" % (os.getpid(), rank))
-        os.environ["SS_DTW_H2_TIMELINE"] = tl_path
-        try:
-            step_resident()
-            ctx.check(lib.ss_dict_match_finish(shard.h))
-            barrier()
-        finally:
-            del os.environ["SS_DTW_H2_TIMELINE"]
+        if world == 1:
+            os.environ["SS_DTW_H2_TIMELINE"] = tl_path
+            try:
+                step_resident()
+                ctx.check(lib.ss_dict_match_finish(shard.h))
+                barrier()
+            finally:
+                del os.environ["SS_DTW_H2_TIMELINE"]
         if os.path.exists(tl_path):
             try:
                 tl = np.loadtxt(tl_path, dtype=np.int64, comments="#", ndmin=2)
