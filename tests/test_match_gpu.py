@@ -143,6 +143,43 @@ def test_cosine_ref_first_minimum_wins_whatever_the_scan_order(ctx):
         assert i1[0, 0] == o1[0] and d1[0, 0] == od1[0]
 
 
+def test_cosine_ref_paired_and_single_query_groups(ctx):
+    """The cosine scan gives a warp two query groups of one length wherever a length has two (2 queries x 4 segments per
+    thread) and the odd group of a length to a warp of its own, in one launch: every mix of the two, against dictionaries
+    whose staged groups of four are uniform, mixed, and longer than the staging buffer (39 frames at C = 13) - bit-exact
+    (src/sound.rs:23-38, 351-370), with per-query targets."""
+    rng = np.random.default_rng(77)
+
+    def make(lens, c):
+        lens = np.asarray(lens, dtype=np.uint64)
+        off = np.zeros(len(lens) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        return rng.normal(size=(int(off[-1]), c)), off
+
+    dict_lens = {
+        "uniform": np.repeat([5, 17, 32], 40),                                    # staged fours of one length
+        "mixed": rng.integers(1, 39, size=203),                                   # nearly every staged four is mixed
+        "long": np.concatenate([rng.integers(40, 90, size=21), [3, 12, 39, 40]]),  # beyond the staging buffer (+ boundary)
+    }
+    query_lens = {
+        "pairs only": np.repeat([6, 20], 64),                       # 2 + 2 groups -> two paired items
+        "singles only": np.arange(1, 34),                           # 33 lengths, one group each
+        "pairs + odd group + partial lanes": np.concatenate([np.repeat(9, 32 * 3 + 5), np.repeat(31, 70), [2, 2, 50, 64]]),
+    }
+    for dname, dl in dict_lens.items():
+        d, doff = make(dl, 13)
+        dev = api.DeviceDictionary(ctx, d, doff)
+        for qname, ql in query_lens.items():
+            q, qoff = make(rng.permutation(ql), 13)
+            oidx, odist = O.cosine_match(d, doff, q, qoff, 13)
+            idx, dist = dev.match(q, qoff, SS_COSINE_REF, 1)
+            assert np.array_equal(idx[:, 0], oidx) and np.array_equal(dist[:, 0], odist), (dname, qname)
+            targets = rng.uniform(-1.0, 1.0, size=len(ql))
+            ot, odt = O.cosine_match(d, doff, q, qoff, 13, targets=targets)
+            it, dt = dev.match(q, qoff, SS_COSINE_REF, 1, targets=targets)
+            assert np.array_equal(it[:, 0], ot) and np.array_equal(dt[:, 0], odt), (dname, qname, "targets")
+
+
 def test_ragged_edge_cases(ctx):
     rng = np.random.default_rng(11)
     # lengths 1, 0 (empty), 33, 64, 65, 200 on both sides
