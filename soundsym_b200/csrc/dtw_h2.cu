@@ -494,6 +494,13 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
         for (int s = 0; s < KP; s++) list[s * kH2DpThreads] = 0xFFFFFFFFFFFFFFFFull;
         const unsigned long long thr0 = __ldcg(p.thr + g * kTcM + m);  // (L2: other CTAs update it)
         unsigned long long worst = thr0;
+        // The list is kept UNSORTED while the slice is scanned: a candidate below `worst` goes to the next free place or, once
+        // the list is full, replaces its largest key, and the new largest key and its place are found with KP independent loads
+        // - the same work for every lane of the warp, where a sorted insertion is a walk of data-dependent length through
+        // dependent shared-memory loads and stores that a warp pays at its slowest lane's pace (on a 1/8 shard, where a slice is
+        // 80 tiles, that was most of the + 400 SM cycles per tile of profiles/r2_h2_cycles_per_tile_eighth_vs_full.txt). The
+        // list is sorted once, at the end of the slice.
+        int cnt = 0, wpos = 0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * kH2SlotCols;
         const uint32_t Lm = p.slot_len[g * kTcM + m];  // this lane's own query length
         TcCursor cur;
@@ -536,14 +543,25 @@ __global__ void __launch_bounds__(kH2Threads, 1) k_dtw_scan_h2(const H2Params p)
                             const float v = hsel ? __high2float(res[b]) : __low2float(res[b]);
                             // D16 / (S (Lq + Ld)); an overflowed path sum stays +inf and is never inserted
                             const float dist = __fdividef(v * p.inv_s, (float)(Lm + (uint32_t)h2_len_of(sc, e)));
-                            tc_insert<KP, kH2DpThreads>(list, worst, dist, (uint32_t)seg);
-                            worst = worst < thr0 ? worst : thr0;  // (an insertion reloads `worst` from the list's last place)
+                            const unsigned long long key = ((unsigned long long)tc_f2ord(dist) << 32) | (uint32_t)seg;
+                            if (key < worst && dist == dist) {
+                                const bool full = cnt == KP;
+                                list[(full ? wpos : cnt) * kH2DpThreads] = key;
+                                cnt += full ? 0 : 1;
+                                if (cnt == KP) {
+                                    tc_list_max<KP, kH2DpThreads>(list, worst, wpos);
+                                    worst = worst < thr0 ? worst : thr0;
+                                }
+                            }
                             if constexpr (DBG) p.dbg[(size_t)(g * kTcM + m) * p.dbg_nseg + seg] = dist;
                         }
                     }
                 }
             }
         }
+        tc_sort_list<KP, kH2DpThreads>(list, cnt);  // (the places beyond cnt still hold the initial +inf keys)
+        worst = list[(KP - 1) * kH2DpThreads];
+        worst = worst < thr0 ? worst : thr0;
         // the two slots' lists of query m (threads m, m + 128) are merged by the slot-0 thread
         asm volatile("bar.sync 1, %0;" ::"n"(kH2DpThreads) : "memory");
         if (tl && threadIdx.x == 0) tl[2] = h2_now(), tl[5] = clock64() - tl[5];  // SM cycles of the DP phase (-> the SM clock under load)

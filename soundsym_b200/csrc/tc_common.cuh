@@ -189,6 +189,32 @@ __device__ __forceinline__ void tc_insert_key(unsigned long long* list, unsigned
     list[s * STRIDE] = key;
     worst = list[(KP - 1) * STRIDE];
 }
+// unsorted lists (dtw_h2.cu): the largest key of a full list and its place - KP independent loads, no data-dependent loop
+template <int KP, int STRIDE = kTcDpThreads>
+__device__ __forceinline__ void tc_list_max(const unsigned long long* list, unsigned long long& mx, int& pos) {
+    unsigned long long m = list[0];
+    int p = 0;
+#pragma unroll
+    for (int s = 1; s < KP; s++) {
+        const unsigned long long v = list[s * STRIDE];
+        p = v > m ? s : p;
+        m = v > m ? v : m;
+    }
+    mx = m, pos = p;
+}
+// ascending insertion sort of the first n places of a list that was filled in no particular order
+template <int KP, int STRIDE = kTcDpThreads>
+__device__ __forceinline__ void tc_sort_list(unsigned long long* list, int n) {
+    for (int i = 1; i < n; i++) {
+        const unsigned long long key = list[i * STRIDE];
+        int s = i;
+        while (s > 0 && list[(s - 1) * STRIDE] > key) {
+            list[s * STRIDE] = list[(s - 1) * STRIDE];
+            s--;
+        }
+        list[s * STRIDE] = key;
+    }
+}
 template <int KP, int STRIDE = kTcDpThreads>
 __device__ __forceinline__ void tc_insert(unsigned long long* list, unsigned long long& worst, float dist, uint32_t idx) {
     const unsigned long long key = ((unsigned long long)tc_f2ord(dist) << 32) | idx;
