@@ -624,9 +624,12 @@ int cosine_match_dev(ss_dict* d, ss_queries* q, const double* d_targets, uint32_
     const uint32_t nqb = nqb2 + nqb1;  // CTAs per slice: paired work items first, single groups last
     if (!nqb || !d->nseg) return SS_OK;
     const uint32_t nslots = q->ngroups * 32;
-    // slice sl takes the groups sl, sl + nslices, ... of that order: every slice sees the same mix of lengths
+    // slice sl takes the groups sl, sl + nslices, ... of that order: every slice sees the same mix of lengths. CTAs per SM over
+    // the launch (two are resident), measured at config 4: 8 -> 41.0 ms, 16 -> 39.4, 32 -> 38.8; small batches keep 16 (the merge
+    // walks a slot's slices one after the other)
+    const uint32_t waves = nqb >= 8 ? 32 : 16;
     const uint32_t ngrp = (uint32_t)((d->nseg + kCosStage - 1) / kCosStage);
-    const uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(ngrp, ((uint32_t)ctx->sm_count * 16 + nqb - 1) / nqb));
+    const uint32_t nslices = std::max<uint32_t>(1, std::min<uint32_t>(ngrp, ((uint32_t)ctx->sm_count * waves + nqb - 1) / nqb));
     SS_CUDA(ctx, d->d_cand_exact.reserve((size_t)nslices * nslots));
     SS_CUDA(ctx, d->d_cand_idx.reserve((size_t)nslices * nslots));
     if (!d->ev_scan0) {
